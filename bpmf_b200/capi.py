@@ -1,0 +1,208 @@
+"""ctypes binding of libbpmf_b200.so — one method per entry point of include/bpmf_gpu.h.
+
+There is no fallback: if the shared library is missing or no sm_100 GPU is present this raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libbpmf_b200.so")
+
+MOVIES, USERS = 0, 1
+KERNEL_AUTO, KERNEL_EXACT, KERNEL_DMMA = 0, 1, 2
+
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_opt = C.c_void_p  # nullable pointer arguments
+
+# every symbol include/bpmf_gpu.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "bpmf_gpu_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int]),
+    "bpmf_gpu_destroy": (C.c_int, [C.c_void_p]),
+    "bpmf_gpu_last_error": (C.c_char_p, [C.c_void_p]),
+    "bpmf_gpu_num_latent": (C.c_int, [C.c_void_p]),
+    "bpmf_gpu_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bpmf_gpu_sync": (C.c_int, [C.c_void_p]),
+    "bpmf_gpu_load_side": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _i64p, _i32p, _f64p, C.c_double]),
+    "bpmf_gpu_load_test": (C.c_int, [C.c_void_p, C.c_int, _i64p, _i32p, _f64p]),
+    "bpmf_gpu_set_range": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "bpmf_gpu_bind_items": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "bpmf_gpu_set_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "bpmf_gpu_items_device_ptr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "bpmf_gpu_set_items": (C.c_int, [C.c_void_p, C.c_int, _f64p]),
+    "bpmf_gpu_get_items": (C.c_int, [C.c_void_p, C.c_int, _f64p]),
+    "bpmf_gpu_get_iter": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    "bpmf_gpu_set_iter": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "bpmf_gpu_sample": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int]),
+    "bpmf_gpu_sample_hyper": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, _opt, _opt]),
+    "bpmf_gpu_set_hyper": (C.c_int, [C.c_void_p, C.c_int, _f64p, _f64p]),
+    "bpmf_gpu_get_hyper": (C.c_int, [C.c_void_p, C.c_int, _f64p, _f64p, _f64p]),
+    "bpmf_gpu_sample_items": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_double, C.c_int]),
+    "bpmf_gpu_reduce_stats": (C.c_int, [C.c_void_p, C.c_int]),
+    "bpmf_gpu_get_stats": (C.c_int, [C.c_void_p, C.c_int, _f64p, _f64p, _f64p, C.POINTER(C.c_double)]),
+    "bpmf_gpu_predict": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                   C.POINTER(C.c_int64)]),
+    "bpmf_gpu_get_predictions": (C.c_int, [C.c_void_p, C.c_int, _f64p, _f64p]),
+    "bpmf_gpu_launch_count": (C.c_int64, [C.c_void_p]),
+    "bpmf_gpu_last_items_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "bpmf_gpu_debug_randn": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, _f64p]),
+}
+
+_lib = None
+
+
+class BpmfGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("bpmf_gpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+def load_library():
+    """dlopen the in-tree shared library and type every entry point. Raises if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise FileNotFoundError(SO_PATH + " is missing: run `python -m bpmf_b200.build` (there is no CPU fallback)")
+        L = C.CDLL(SO_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            f = getattr(L, name)  # AttributeError if the library does not export it
+            f.restype, f.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One GPU's BPMF state (both factors). Mirrors the call sequence of a `CUDA_Sys : Sys` backend."""
+
+    def __init__(self, num_latent, device=0):
+        self.L = load_library()
+        self.K = int(num_latent)
+        h = C.c_void_p()
+        rc = self.L.bpmf_gpu_create(C.byref(h), device, self.K)
+        if rc:
+            raise BpmfGpuError(rc, self.L.bpmf_gpu_last_error(None).decode())
+        self.h = h
+        self.num = [0, 0]
+        self.nnz_test = [0, 0]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.bpmf_gpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise BpmfGpuError(rc, self.L.bpmf_gpu_last_error(self.h).decode())
+
+    # ---- plumbing
+    def set_stream(self, stream_handle): self._ck(self.L.bpmf_gpu_set_stream(self.h, C.c_void_p(stream_handle)))
+    def sync(self): self._ck(self.L.bpmf_gpu_sync(self.h))
+    def launch_count(self): return self.L.bpmf_gpu_launch_count(self.h)
+
+    # ---- data
+    def load_side(self, side, num_items, num_other, colptr, rowidx, val, mean_rating):
+        colptr = np.ascontiguousarray(colptr, np.int64)
+        rowidx = np.ascontiguousarray(rowidx, np.int32)
+        val = np.ascontiguousarray(val, np.float64)
+        assert colptr.shape == (num_items + 1,)
+        self._ck(self.L.bpmf_gpu_load_side(self.h, side, num_items, num_other, colptr, rowidx, val, mean_rating))
+        self.num[side] = num_items
+
+    def load_test(self, side, colptr, rowidx, val):
+        colptr = np.ascontiguousarray(colptr, np.int64)
+        self._ck(self.L.bpmf_gpu_load_test(self.h, side, colptr, np.ascontiguousarray(rowidx, np.int32),
+                                           np.ascontiguousarray(val, np.float64)))
+        self.nnz_test[side] = int(colptr[-1])
+
+    def set_range(self, side, lo, hi): self._ck(self.L.bpmf_gpu_set_range(self.h, side, lo, hi))
+    def bind_items(self, side, dev_ptr): self._ck(self.L.bpmf_gpu_bind_items(self.h, side, C.c_void_p(dev_ptr)))
+
+    def set_peers(self, side, ptrs):
+        arr = (C.c_void_p * max(1, len(ptrs)))(*[C.c_void_p(p) for p in ptrs])
+        self._ck(self.L.bpmf_gpu_set_peers(self.h, side, len(ptrs), arr))
+
+    def items_device_ptr(self, side):
+        p = C.c_void_p()
+        self._ck(self.L.bpmf_gpu_items_device_ptr(self.h, side, C.byref(p)))
+        return p.value
+
+    def set_items(self, side, a):
+        a = np.ascontiguousarray(a, np.float64)
+        assert a.size == self.K * self.num[side]
+        self._ck(self.L.bpmf_gpu_set_items(self.h, side, a.reshape(-1)))
+
+    def get_items(self, side):
+        out = np.empty((self.num[side], self.K), np.float64)
+        self._ck(self.L.bpmf_gpu_get_items(self.h, side, out.reshape(-1)))
+        return out
+
+    def get_iter(self, side):
+        i = C.c_int()
+        self._ck(self.L.bpmf_gpu_get_iter(self.h, side, C.byref(i)))
+        return i.value
+
+    def set_iter(self, side, it): self._ck(self.L.bpmf_gpu_set_iter(self.h, side, it))
+
+    # ---- hot path
+    def sample(self, side, alpha=2.0, variant=KERNEL_AUTO): self._ck(self.L.bpmf_gpu_sample(self.h, side, alpha, variant))
+
+    def sample_hyper(self, side, it, sum_=None, cov=None):
+        s = None if sum_ is None else np.ascontiguousarray(sum_, np.float64)
+        c = None if cov is None else np.ascontiguousarray(cov, np.float64)
+        self._ck(self.L.bpmf_gpu_sample_hyper(self.h, side, it, _ptr(s), _ptr(c)))
+
+    def set_hyper(self, side, mu, LambdaF):
+        self._ck(self.L.bpmf_gpu_set_hyper(self.h, side, np.ascontiguousarray(mu, np.float64),
+                                           np.ascontiguousarray(LambdaF, np.float64).reshape(-1)))
+
+    def get_hyper(self, side):
+        K = self.K
+        mu, LU, LF = np.empty(K), np.empty(K * K), np.empty(K * K)
+        self._ck(self.L.bpmf_gpu_get_hyper(self.h, side, mu, LU, LF))
+        return mu, LU, LF
+
+    def sample_items(self, side, it, alpha=2.0, variant=KERNEL_AUTO):
+        self._ck(self.L.bpmf_gpu_sample_items(self.h, side, it, alpha, variant))
+
+    def reduce_stats(self, side): self._ck(self.L.bpmf_gpu_reduce_stats(self.h, side))
+
+    def get_stats(self, side):
+        K = self.K
+        s, p, c = np.empty(K), np.empty(K * K), np.empty(K * K)
+        n = C.c_double()
+        self._ck(self.L.bpmf_gpu_get_stats(self.h, side, s, p, c, C.byref(n)))
+        return s, p, c, n.value
+
+    def predict(self, side, burnin):
+        a, b, n = C.c_double(), C.c_double(), C.c_int64()
+        self._ck(self.L.bpmf_gpu_predict(self.h, side, burnin, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
+
+    def get_predictions(self, side):
+        n = self.nnz_test[side]
+        a, b = np.empty(n), np.empty(n)
+        self._ck(self.L.bpmf_gpu_get_predictions(self.h, side, a, b))
+        return a, b
+
+    def last_items_kernel_ms(self):
+        ms = C.c_float()
+        self._ck(self.L.bpmf_gpu_last_items_kernel_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def debug_randn(self, c, n):
+        out = np.empty(n)
+        self._ck(self.L.bpmf_gpu_debug_randn(self.h, c, n, out))
+        return out

@@ -1,0 +1,506 @@
+// capi.cu — the extern "C" surface declared in include/bpmf_gpu.h. Host-side only: owns device memory,
+// orders the kernels of one Sys::sample (c++/sample.cpp:341-385) on the context's stream and turns
+// CUDA / kernel errors into return codes. There is deliberately no CPU fallback anywhere in this file.
+#include "../../include/bpmf_gpu.h"
+#include "common.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace bpmf;
+
+namespace {
+
+std::string g_create_err;
+
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess) {                                                                      \
+            char b__[512];                                                                             \
+            snprintf(b__, sizeof b__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            ctx->err = b__;                                                                            \
+            return BPMF_GPU_ECUDA;                                                                     \
+        }                                                                                              \
+    } while (0)
+
+int fail(bpmf_gpu_ctx *ctx, int code, const std::string &msg)
+{
+    ctx->err = msg;
+    return code;
+}
+
+template <typename T>
+void dfree(T *&p)
+{
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+void free_side(SideDev &s)
+{
+    dfree(s.colptr); dfree(s.rowidx); dfree(s.val);
+    dfree(s.t_colptr); dfree(s.t_rowidx); dfree(s.t_col); dfree(s.t_val); dfree(s.pavg); dfree(s.pm2);
+    dfree(s.items_own); s.items = nullptr;
+    dfree(s.peers_dev);
+    dfree(s.hp.mu); dfree(s.hp.LambdaU); dfree(s.hp.LambdaF);
+    dfree(s.sum); dfree(s.prod); dfree(s.cov); dfree(s.norm); dfree(s.partials); dfree(s.pred_partials);
+    dfree(s.work_counter);
+    s = SideDev();
+}
+
+bool side_ok(int side) { return side == 0 || side == 1; }
+
+// deferred kernel-side errors (the word kernels atomicMax into)
+int check_device_error(bpmf_gpu_ctx *ctx)
+{
+    CU(cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const unsigned long long w = *ctx->h_err;
+    if (!w) return BPMF_GPU_OK;
+    CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(unsigned long long), ctx->stream));
+    const unsigned code = (unsigned)(w >> 32), detail = (unsigned)(w & 0xffffffffu);
+    char b[256];
+    if (code == 3) { snprintf(b, sizeof b, "Cholesky failed (item %u)", detail); return fail(ctx, BPMF_GPU_ECHOLESKY, b); }
+    if (code == 4) return fail(ctx, BPMF_GPU_ERNG, "hyper-parameter draw ran out of pre-generated Philox blocks");
+    if (code == 5) { snprintf(b, sizeof b, "hyper-parameter draw: T_c not positive definite (pivot %u)", detail); return fail(ctx, BPMF_GPU_ECHOLESKY, b); }
+    snprintf(b, sizeof b, "device error word %llx", w);
+    return fail(ctx, BPMF_GPU_ECUDA, b);
+}
+
+int pick_variant(const bpmf_gpu_ctx *ctx, int v)
+{
+    if (v == BPMF_GPU_KERNEL_AUTO) return ctx->K == 32 ? BPMF_GPU_KERNEL_DMMA : BPMF_GPU_KERNEL_EXACT;
+    return v;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *bpmf_gpu_last_error(const bpmf_gpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int bpmf_gpu_create(bpmf_gpu_ctx **out, int device, int num_latent)
+{
+    if (!out) return BPMF_GPU_EINVAL;
+    *out = nullptr;
+    if (num_latent < 1 || num_latent > 128) { g_create_err = "num_latent must be in [1,128]"; return BPMF_GPU_EINVAL; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_err = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libbpmf_b200 has no CPU fallback)";
+        return BPMF_GPU_ENODEVICE;
+    }
+    if (device < 0 || device >= ndev) { g_create_err = "device index out of range"; return BPMF_GPU_EINVAL; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_create_err = cudaGetErrorString(e); return BPMF_GPU_ECUDA; }
+    if (prop.major != 10) {
+        g_create_err = std::string("device ") + prop.name + " is not sm_100 (this library is built for sm_100a only)";
+        return BPMF_GPU_ENODEVICE;
+    }
+    bpmf_gpu_ctx *ctx = new (std::nothrow) bpmf_gpu_ctx();
+    if (!ctx) return BPMF_GPU_EINVAL;
+    ctx->device = device; ctx->K = num_latent; ctx->sm_count = prop.multiProcessorCount;
+    const int K = num_latent, KK = K * K;
+    auto bail = [&](cudaError_t ee) { g_create_err = cudaGetErrorString(ee); bpmf_gpu_destroy(ctx); return BPMF_GPU_ECUDA; };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&ctx->d_err, sizeof(unsigned long long))) != cudaSuccess) return bail(e);
+    if ((e = cudaMemset(ctx->d_err, 0, sizeof(unsigned long long))) != cudaSuccess) return bail(e);
+    if ((e = cudaMallocHost(&ctx->h_err, sizeof(unsigned long long))) != cudaSuccess) return bail(e);
+    if ((e = cudaMallocHost(&ctx->h_pinned, sizeof(double) * (KK + K + 8))) != cudaSuccess) return bail(e);
+    if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e);
+    if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e);
+    HyperScratch &h = ctx->hs;
+    // expected consumption is 1.27 (K^2+K) + K/2 blocks; 2 (K^2+4K) + 64 is > 40 standard deviations above it
+    h.nblk = 2 * (KK + 4 * K) + 64;
+    if ((e = cudaMalloc(&h.words, sizeof(uint32_t) * 4 * h.nblk)) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&h.acc, 2 * h.nblk)) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&h.rank, sizeof(int) * 2 * h.nblk)) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&h.pos_of_rank, sizeof(int) * 2 * h.nblk)) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&h.row_start, sizeof(int) * (K + 1))) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&h.row_cls, sizeof(int) * (K + 1))) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&h.mats, sizeof(double) * 6 * KK)) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&h.vecs, sizeof(double) * 4 * K)) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&h.piv, sizeof(int) * K)) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&h.host_in, sizeof(double) * (KK + K))) != cudaSuccess) return bail(e);
+    *out = ctx;
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_destroy(bpmf_gpu_ctx *ctx)
+{
+    if (!ctx) return BPMF_GPU_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    free_side(ctx->side[0]); free_side(ctx->side[1]);
+    HyperScratch &h = ctx->hs;
+    dfree(h.words); dfree(h.acc); dfree(h.rank); dfree(h.pos_of_rank); dfree(h.row_start); dfree(h.row_cls);
+    dfree(h.mats); dfree(h.vecs); dfree(h.piv); dfree(h.host_in);
+    dfree(ctx->d_err);
+    if (ctx->h_err) cudaFreeHost(ctx->h_err);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    delete ctx;
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_num_latent(const bpmf_gpu_ctx *ctx) { return ctx ? ctx->K : -1; }
+
+int bpmf_gpu_set_stream(bpmf_gpu_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return BPMF_GPU_EINVAL;
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_sync(bpmf_gpu_ctx *ctx)
+{
+    if (!ctx) return BPMF_GPU_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    return check_device_error(ctx);
+}
+
+int bpmf_gpu_load_side(bpmf_gpu_ctx *ctx, int side, int num_items, int num_other, const int64_t *colptr, const int32_t *rowidx,
+                       const double *val, double mean_rating)
+{
+    if (!ctx || !side_ok(side) || num_items < 0 || num_other < 0 || !colptr) return BPMF_GPU_EINVAL;
+    const int64_t nnz = colptr[num_items];
+    if (colptr[0] != 0 || nnz < 0 || (nnz > 0 && (!rowidx || !val))) return fail(ctx, BPMF_GPU_EINVAL, "bad CSC arrays");
+    for (int i = 0; i < num_items; ++i)
+        if (colptr[i + 1] < colptr[i]) return fail(ctx, BPMF_GPU_EINVAL, "colptr not monotone");
+    for (int64_t p = 0; p < nnz; ++p)
+        if (rowidx[p] < 0 || rowidx[p] >= num_other) return fail(ctx, BPMF_GPU_EINVAL, "row index out of range");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    SideDev &s = ctx->side[side];
+    free_side(s);
+    const int K = ctx->K, KK = K * K;
+    s.num = num_items; s.num_other = num_other; s.nnz = nnz; s.from = 0; s.to = num_items; s.iter = -1;
+    s.mean_rating = mean_rating;
+    CU(cudaMalloc(&s.colptr, sizeof(int64_t) * ((size_t)num_items + 1)));
+    CU(cudaMalloc(&s.rowidx, sizeof(int32_t) * (size_t)(nnz + 32)));  // +32: the DMMA kernel reads index chunks of 32
+    CU(cudaMalloc(&s.val, sizeof(double) * (size_t)(nnz + 32)));
+    CU(cudaMemset(s.rowidx, 0, sizeof(int32_t) * (size_t)(nnz + 32)));
+    CU(cudaMemset(s.val, 0, sizeof(double) * (size_t)(nnz + 32)));
+    CU(cudaMemcpy(s.colptr, colptr, sizeof(int64_t) * ((size_t)num_items + 1), cudaMemcpyHostToDevice));
+    if (nnz) {
+        CU(cudaMemcpy(s.rowidx, rowidx, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(s.val, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice));
+    }
+    const size_t nitems = (size_t)K * (size_t)(num_items > 0 ? num_items : 1);
+    CU(cudaMalloc(&s.items_own, sizeof(double) * nitems));
+    CU(cudaMemset(s.items_own, 0, sizeof(double) * nitems));  // items().setZero() (sample.cpp:185)
+    s.items = s.items_own;
+    CU(cudaMalloc(&s.peers_dev, sizeof(double *) * MAX_PEERS));
+    CU(cudaMemset(s.peers_dev, 0, sizeof(double *) * MAX_PEERS));
+    CU(cudaMalloc(&s.hp.mu, sizeof(double) * K));
+    CU(cudaMalloc(&s.hp.LambdaU, sizeof(double) * KK));
+    CU(cudaMalloc(&s.hp.LambdaF, sizeof(double) * KK));
+    CU(cudaMemset(s.hp.mu, 0, sizeof(double) * K));
+    CU(cudaMemset(s.hp.LambdaU, 0, sizeof(double) * KK));
+    CU(cudaMemset(s.hp.LambdaF, 0, sizeof(double) * KK));
+    CU(cudaMalloc(&s.sum, sizeof(double) * K));
+    CU(cudaMalloc(&s.prod, sizeof(double) * KK));
+    CU(cudaMalloc(&s.cov, sizeof(double) * KK));
+    CU(cudaMalloc(&s.norm, sizeof(double)));
+    CU(cudaMemset(s.sum, 0, sizeof(double) * K));       // sum.setZero(); cov.setZero(); norm = 0 (sample.cpp:187-189)
+    CU(cudaMemset(s.prod, 0, sizeof(double) * KK));
+    CU(cudaMemset(s.cov, 0, sizeof(double) * KK));
+    CU(cudaMemset(s.norm, 0, sizeof(double)));
+    CU(cudaMalloc(&s.partials, sizeof(double) * (size_t)STATS_BLOCKS * (KK + K + 1)));
+    CU(cudaMalloc(&s.work_counter, sizeof(unsigned int)));
+    CU(cudaMemset(s.work_counter, 0, sizeof(unsigned int)));
+    s.loaded = true;
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_load_test(bpmf_gpu_ctx *ctx, int side, const int64_t *colptr, const int32_t *rowidx, const double *val)
+{
+    if (!ctx || !side_ok(side) || !colptr) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "load_side must come before load_test");
+    const int64_t nnz = colptr[s.num];
+    if (colptr[0] != 0 || nnz < 0) return fail(ctx, BPMF_GPU_EINVAL, "bad test CSC arrays");
+    std::vector<int32_t> col((size_t)nnz);
+    for (int i = 0; i < s.num; ++i) {
+        if (colptr[i + 1] < colptr[i]) return fail(ctx, BPMF_GPU_EINVAL, "test colptr not monotone");
+        for (int64_t p = colptr[i]; p < colptr[i + 1]; ++p) {
+            if (rowidx[p] < 0 || rowidx[p] >= s.num_other) return fail(ctx, BPMF_GPU_EINVAL, "test row index out of range");
+            col[(size_t)p] = i;
+        }
+    }
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    dfree(s.t_colptr); dfree(s.t_rowidx); dfree(s.t_col); dfree(s.t_val); dfree(s.pavg); dfree(s.pm2); dfree(s.pred_partials);
+    s.nnz_test = nnz;
+    const size_t n1 = (size_t)(nnz > 0 ? nnz : 1);
+    CU(cudaMalloc(&s.t_colptr, sizeof(int64_t) * ((size_t)s.num + 1)));
+    CU(cudaMalloc(&s.t_rowidx, sizeof(int32_t) * n1));
+    CU(cudaMalloc(&s.t_col, sizeof(int32_t) * n1));
+    CU(cudaMalloc(&s.t_val, sizeof(double) * n1));
+    CU(cudaMalloc(&s.pavg, sizeof(double) * n1));
+    CU(cudaMalloc(&s.pm2, sizeof(double) * n1));
+    CU(cudaMemcpy(s.t_colptr, colptr, sizeof(int64_t) * ((size_t)s.num + 1), cudaMemcpyHostToDevice));
+    if (nnz) {
+        CU(cudaMemcpy(s.t_rowidx, rowidx, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(s.t_col, col.data(), sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(s.t_val, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(s.pavg, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice));  // Pm2 = Pavg = T (sample.cpp:123)
+        CU(cudaMemcpy(s.pm2, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice));
+    }
+    s.pred_blocks = ctx->sm_count * 8;
+    CU(cudaMalloc(&s.pred_partials, sizeof(double) * (2 * (size_t)s.pred_blocks + 2)));
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_set_range(bpmf_gpu_ctx *ctx, int side, int from, int to)
+{
+    if (!ctx || !side_ok(side)) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded || from < 0 || to < from || to > s.num) return fail(ctx, BPMF_GPU_EINVAL, "bad range");
+    s.from = from; s.to = to;
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_bind_items(bpmf_gpu_ctx *ctx, int side, double *dev_items)
+{
+    if (!ctx || !side_ok(side)) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
+    CU(cudaSetDevice(ctx->device));
+    double *target = dev_items ? dev_items : s.items_own;
+    if (target != s.items) {
+        CU(cudaMemcpyAsync(target, s.items, sizeof(double) * (size_t)ctx->K * s.num, cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        s.items = target;
+    }
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_set_peers(bpmf_gpu_ctx *ctx, int side, int npeers, double *const *dev_peer_items)
+{
+    if (!ctx || !side_ok(side) || npeers < 0 || npeers > MAX_PEERS) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
+    CU(cudaSetDevice(ctx->device));
+    double *tmp[MAX_PEERS] = {nullptr};
+    for (int i = 0; i < npeers; ++i) tmp[i] = dev_peer_items[i];
+    CU(cudaMemcpyAsync(s.peers_dev, tmp, sizeof(tmp), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    s.npeers = npeers;
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_items_device_ptr(bpmf_gpu_ctx *ctx, int side, double **dev_items)
+{
+    if (!ctx || !side_ok(side) || !dev_items) return BPMF_GPU_EINVAL;
+    *dev_items = ctx->side[side].items;
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_set_items(bpmf_gpu_ctx *ctx, int side, const double *host_items)
+{
+    if (!ctx || !side_ok(side) || !host_items) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(s.items, host_items, sizeof(double) * (size_t)ctx->K * s.num, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_get_items(bpmf_gpu_ctx *ctx, int side, double *host_items)
+{
+    if (!ctx || !side_ok(side) || !host_items) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(host_items, s.items, sizeof(double) * (size_t)ctx->K * s.num, cudaMemcpyDeviceToHost, ctx->stream));
+    return check_device_error(ctx);
+}
+
+int bpmf_gpu_get_iter(bpmf_gpu_ctx *ctx, int side, int *iter)
+{
+    if (!ctx || !side_ok(side) || !iter) return BPMF_GPU_EINVAL;
+    *iter = ctx->side[side].iter;
+    return BPMF_GPU_OK;
+}
+int bpmf_gpu_set_iter(bpmf_gpu_ctx *ctx, int side, int iter)
+{
+    if (!ctx || !side_ok(side)) return BPMF_GPU_EINVAL;
+    ctx->side[side].iter = iter;
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_sample_hyper(bpmf_gpu_ctx *ctx, int side, uint32_t iter, const double *host_sum, const double *host_cov)
+{
+    if (!ctx || !side_ok(side)) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
+    if (s.num < 1) return fail(ctx, BPMF_GPU_EINVAL, "hyper draw needs at least one item");
+    CU(cudaSetDevice(ctx->device));
+    const int K = ctx->K, KK = K * K;
+    const double *d_sum = nullptr, *d_cov = s.cov;
+    if (host_sum || host_cov) {
+        CU(cudaStreamSynchronize(ctx->stream));  // h_pinned / host_in may still be in use by an earlier call
+        if (host_sum) {
+            memcpy(ctx->h_pinned, host_sum, sizeof(double) * K);
+            CU(cudaMemcpyAsync(ctx->hs.host_in, ctx->h_pinned, sizeof(double) * K, cudaMemcpyHostToDevice, ctx->stream));
+            d_sum = ctx->hs.host_in;
+        }
+        if (host_cov) {
+            memcpy(ctx->h_pinned + K, host_cov, sizeof(double) * KK);
+            CU(cudaMemcpyAsync(ctx->hs.host_in + K, ctx->h_pinned + K, sizeof(double) * KK, cudaMemcpyHostToDevice, ctx->stream));
+            d_cov = ctx->hs.host_in + K;
+        }
+    }
+    CU(launch_hyper(ctx, side, iter, d_sum, d_cov));
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_set_hyper(bpmf_gpu_ctx *ctx, int side, const double *mu, const double *LambdaF)
+{
+    if (!ctx || !side_ok(side) || !mu || !LambdaF) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
+    CU(cudaSetDevice(ctx->device));
+    const int K = ctx->K;
+    CU(cudaMemcpyAsync(s.hp.mu, mu, sizeof(double) * K, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(s.hp.LambdaF, LambdaF, sizeof(double) * K * K, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_get_hyper(bpmf_gpu_ctx *ctx, int side, double *mu, double *LambdaU, double *LambdaF)
+{
+    if (!ctx || !side_ok(side)) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
+    CU(cudaSetDevice(ctx->device));
+    const int K = ctx->K;
+    if (mu) CU(cudaMemcpyAsync(mu, s.hp.mu, sizeof(double) * K, cudaMemcpyDeviceToHost, ctx->stream));
+    if (LambdaU) CU(cudaMemcpyAsync(LambdaU, s.hp.LambdaU, sizeof(double) * K * K, cudaMemcpyDeviceToHost, ctx->stream));
+    if (LambdaF) CU(cudaMemcpyAsync(LambdaF, s.hp.LambdaF, sizeof(double) * K * K, cudaMemcpyDeviceToHost, ctx->stream));
+    return check_device_error(ctx);
+}
+
+int bpmf_gpu_sample_items(bpmf_gpu_ctx *ctx, int side, uint32_t iter, double alpha, int kernel_variant)
+{
+    if (!ctx || !side_ok(side)) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    const SideDev &o = ctx->side[1 - side];
+    if (!s.loaded || !o.loaded) return fail(ctx, BPMF_GPU_EINVAL, "both sides must be loaded");
+    if (s.num_other != o.num) return fail(ctx, BPMF_GPU_EINVAL, "sides disagree on dimensions");
+    CU(cudaSetDevice(ctx->device));
+    const int v = pick_variant(ctx, kernel_variant);
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (v == BPMF_GPU_KERNEL_EXACT) CU(launch_items_exact(ctx, side, iter, alpha));
+    else if (v == BPMF_GPU_KERNEL_DMMA) {
+        if (ctx->K != 32) return fail(ctx, BPMF_GPU_EINVAL, "the DMMA kernel is built for num_latent == 32");
+        CU(launch_items_dmma32(ctx, side, iter, alpha));
+    } else return fail(ctx, BPMF_GPU_EINVAL, "unknown kernel variant");
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->have_item_timing = true;
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_reduce_stats(bpmf_gpu_ctx *ctx, int side)
+{
+    if (!ctx || !side_ok(side)) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
+    CU(cudaSetDevice(ctx->device));
+    CU(launch_stats(ctx, side));
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_get_stats(bpmf_gpu_ctx *ctx, int side, double *sum, double *prod, double *cov, double *norm)
+{
+    if (!ctx || !side_ok(side)) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
+    CU(cudaSetDevice(ctx->device));
+    const int K = ctx->K;
+    if (sum) CU(cudaMemcpyAsync(sum, s.sum, sizeof(double) * K, cudaMemcpyDeviceToHost, ctx->stream));
+    if (prod) CU(cudaMemcpyAsync(prod, s.prod, sizeof(double) * K * K, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cov) CU(cudaMemcpyAsync(cov, s.cov, sizeof(double) * K * K, cudaMemcpyDeviceToHost, ctx->stream));
+    if (norm) CU(cudaMemcpyAsync(norm, s.norm, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return check_device_error(ctx);
+}
+
+int bpmf_gpu_sample(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_variant)
+{
+    if (!ctx || !side_ok(side)) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
+    s.iter++;                                                             // sample.cpp:344
+    int rc = bpmf_gpu_sample_hyper(ctx, side, (uint32_t)s.iter, nullptr, nullptr);  // :349-350 (sum == 0, Q1)
+    if (rc) return rc;
+    rc = bpmf_gpu_sample_items(ctx, side, (uint32_t)s.iter, alpha, kernel_variant);  // :352-373
+    if (rc) return rc;
+    return bpmf_gpu_reduce_stats(ctx, side);                              // :379-384
+}
+
+int bpmf_gpu_predict(bpmf_gpu_ctx *ctx, int side, int burnin, double *rmse, double *rmse_avg, int64_t *num_predict)
+{
+    if (!ctx || !side_ok(side)) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded || !ctx->side[1 - side].loaded || !s.t_colptr) return fail(ctx, BPMF_GPU_EINVAL, "test data not loaded");
+    CU(cudaSetDevice(ctx->device));
+    const int n = (s.iter < burnin) ? 0 : (s.iter - burnin);              // sample.cpp:50
+    CU(launch_predict(ctx, side, n));
+    double se = 0.0, se_avg = 0.0;
+    if (s.nnz_test) {
+        CU(cudaMemcpyAsync(ctx->h_pinned, s.pred_partials + 2 * (size_t)s.pred_blocks, 2 * sizeof(double), cudaMemcpyDeviceToHost,
+                           ctx->stream));
+        const int rc = check_device_error(ctx);
+        if (rc) return rc;
+        se = ctx->h_pinned[0]; se_avg = ctx->h_pinned[1];
+    }
+    if (rmse) *rmse = sqrt(se / (double)s.nnz_test);                      // sample.cpp:94-95
+    if (rmse_avg) *rmse_avg = sqrt(se_avg / (double)s.nnz_test);
+    if (num_predict) *num_predict = s.nnz_test;
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_get_predictions(bpmf_gpu_ctx *ctx, int side, double *pavg, double *pm2)
+{
+    if (!ctx || !side_ok(side)) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded || !s.t_colptr) return fail(ctx, BPMF_GPU_EINVAL, "test data not loaded");
+    CU(cudaSetDevice(ctx->device));
+    if (pavg && s.nnz_test) CU(cudaMemcpyAsync(pavg, s.pavg, sizeof(double) * (size_t)s.nnz_test, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pm2 && s.nnz_test) CU(cudaMemcpyAsync(pm2, s.pm2, sizeof(double) * (size_t)s.nnz_test, cudaMemcpyDeviceToHost, ctx->stream));
+    return check_device_error(ctx);
+}
+
+int64_t bpmf_gpu_launch_count(const bpmf_gpu_ctx *ctx) { return ctx ? ctx->launches : -1; }
+
+int bpmf_gpu_last_items_kernel_ms(bpmf_gpu_ctx *ctx, float *ms)
+{
+    if (!ctx || !ms) return BPMF_GPU_EINVAL;
+    if (!ctx->have_item_timing) return fail(ctx, BPMF_GPU_EINVAL, "no item kernel has run yet");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventSynchronize(ctx->ev1));
+    CU(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_debug_randn(bpmf_gpu_ctx *ctx, uint32_t c, int n, double *host_out)
+{
+    if (!ctx || n < 1 || n > 4096 || !host_out) return BPMF_GPU_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    double *d = nullptr;
+    CU(cudaMalloc(&d, sizeof(double) * n));
+    cudaError_t e = launch_debug_randn(ctx, c, n, d);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host_out, d, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, BPMF_GPU_ECUDA, cudaGetErrorString(e));
+    return BPMF_GPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,95 @@
+// common.cuh — context / per-side device state shared by the translation units of libbpmf_b200.so
+#pragma once
+#include <cstdint>
+#include <string>
+#include <cuda_runtime.h>
+
+namespace bpmf {
+
+constexpr int MAX_PEERS = 16;
+constexpr int STATS_BLOCKS = 296;  // 2 x 148 SMs; fixed so the reduction order never depends on the GPU count
+
+// error word written by kernels: 0 = ok. code in the high 32 bits, detail (item index) in the low 32.
+constexpr unsigned long long ERR_CHOLESKY = 3ull << 32;
+constexpr unsigned long long ERR_RNG = 4ull << 32;
+
+struct HyperDev {         // HyperParams on the device (c++/bpmf.h:78-104)
+    double *mu = nullptr;       // K
+    double *LambdaU = nullptr;  // K*K upper
+    double *LambdaF = nullptr;  // K*K
+};
+
+struct SideDev {          // the device mirror of one Sys (c++/bpmf.h:112-239)
+    bool loaded = false;
+    int num = 0, num_other = 0;
+    int64_t nnz = 0, nnz_test = 0;
+    int from = 0, to = 0;
+    int iter = -1;
+    double mean_rating = 0.0;
+    // train CSC: column = item of this side
+    int64_t *colptr = nullptr;
+    int32_t *rowidx = nullptr;
+    double *val = nullptr;
+    // test CSC + expanded column index + running predictions
+    int64_t *t_colptr = nullptr;
+    int32_t *t_rowidx = nullptr, *t_col = nullptr;
+    double *t_val = nullptr, *pavg = nullptr, *pm2 = nullptr;
+    // latent matrix
+    double *items = nullptr;        // active storage (own or bound)
+    double *items_own = nullptr;
+    int npeers = 0;
+    double **peers_dev = nullptr;   // device array[MAX_PEERS] of replica pointers
+    HyperDev hp;
+    // reductions
+    double *sum = nullptr, *prod = nullptr, *cov = nullptr, *norm = nullptr;
+    double *partials = nullptr;     // STATS_BLOCKS x (K*K + K + 1)
+    double *pred_partials = nullptr;
+    int pred_blocks = 0;
+    // dynamic work counter for the item kernels
+    unsigned int *work_counter = nullptr;
+};
+
+struct HyperScratch {     // global scratch of the single-block hyper kernel
+    int nblk = 0;               // pre-generated Philox blocks
+    uint32_t *words = nullptr;  // 4*nblk
+    unsigned char *acc = nullptr;   // 2*nblk attempt flags (even word offsets)
+    int *rank = nullptr;        // 2*nblk: # accepted before this attempt within its class
+    int *pos_of_rank = nullptr; // 2 x nblk
+    int *row_start = nullptr;   // K+1 (rank of first kept normal of Bartlett row i, and of z), class in row_cls
+    int *row_cls = nullptr;     // K+1
+    double *mats = nullptr;     // 6 x K*K: X/LU, Tc (transposed work), L, au, spare, spare
+    double *vecs = nullptr;     // 4 x K
+    int *piv = nullptr;         // K
+    double *host_in = nullptr;  // K + K*K staging for host-provided sum / cov
+};
+
+}  // namespace bpmf
+
+struct bpmf_gpu_ctx {
+    int device = 0;
+    int K = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bpmf::SideDev side[2];
+    bpmf::HyperScratch hs;
+    unsigned long long *d_err = nullptr;  // device error word
+    unsigned long long *h_err = nullptr;  // pinned host copy
+    double *h_pinned = nullptr;           // small pinned staging (K*K + K + 8 doubles)
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool have_item_timing = false;
+    long long launches = 0;
+    std::string err;
+};
+
+// ---- launchers implemented in the kernel translation units ------------------------------------
+namespace bpmf {
+// exact_kernels.cu (compiled with -fmad=false)
+cudaError_t launch_hyper(bpmf_gpu_ctx *c, int side, uint32_t iter, const double *d_sum, const double *d_cov);
+cudaError_t launch_items_exact(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha);
+cudaError_t launch_stats(bpmf_gpu_ctx *c, int side);
+cudaError_t launch_predict(bpmf_gpu_ctx *c, int side, int n);
+cudaError_t launch_debug_randn(bpmf_gpu_ctx *c, uint32_t seed, int n, double *d_out);
+size_t exact_items_smem_bytes(int K);
+// fast_kernels.cu
+cudaError_t launch_items_dmma32(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha);
+}  // namespace bpmf

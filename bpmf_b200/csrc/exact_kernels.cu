@@ -1,0 +1,638 @@
+// exact_kernels.cu — reference-order device kernels. COMPILED WITH -fmad=false so that every
+// floating-point operation rounds exactly like the reference's default x86-64 build (no FMA
+// contraction); summation orders are the ones the CPU checker used by tests/ states, which follow
+// c++/sample.cpp and c++/mvnormal.cpp. Contains:
+//   hyper_kernel        CondNormalWishart / NormalWishart / Wishart chain (mvnormal.cpp:56-135,
+//                       bpmf.h:98-103) as ONE single-block kernel
+//   items_exact_kernel  Sys::sample(idx, other) (sample.cpp:263-336) for any K, one CTA per item
+//   stats kernels       sums/prods/norms + cov (sample.cpp:359-362,379-384)
+//   predict kernels     Sys::predict (sample.cpp:48-96)
+#include "common.cuh"
+#include "rng.cuh"
+
+namespace bpmf {
+
+constexpr unsigned long long ERR_HYPER_NOT_PD = 5ull << 32;
+
+// =================================================================================================
+// Hyper-parameter draw
+// =================================================================================================
+struct HyperArgs {
+    int K, N, nblk;
+    uint32_t iter;
+    const double *sum;  // K or nullptr (zeros)
+    const double *cov;  // K*K
+    uint32_t *words;
+    unsigned char *acc;
+    int *rank, *pos_of_rank, *row_start, *row_cls, *piv;
+    double *mats, *vecs;
+    double *mu, *LambdaU, *LambdaF;
+    unsigned long long *err;
+};
+
+__device__ __forceinline__ double normal_at(const uint32_t *words, int q)
+{
+    const Polar p = polar_attempt(words[2 * q], words[2 * q + 1], words[2 * q + 2], words[2 * q + 3]);
+    return p.y * polar_mult(p.r2);
+}
+
+__global__ void __launch_bounds__(1024) hyper_kernel(HyperArgs a)
+{
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int K = a.K, N = a.N, nblk = a.nblk;
+    const int KK = K * K;
+    __shared__ int s_scan[1024];
+    __shared__ int s_total[2];
+    __shared__ int s_piv;
+    __shared__ int s_fail;
+    if (tid == 0) s_fail = 0;
+
+    // ---- 1. the raw word stream of rng_set_pos(iter), in MicroURNG delivery order -------------------
+    for (int b = tid; b < nblk; b += T) {
+        const U4 w = stream_block(a.iter, (uint32_t)b);
+        a.words[4 * b + 0] = w.v[3];
+        a.words[4 * b + 1] = w.v[2];
+        a.words[4 * b + 2] = w.v[1];
+        a.words[4 * b + 3] = w.v[0];
+    }
+    __syncthreads();
+    // ---- 2. acceptance of a polar attempt starting at every even word offset 2q ---------------------
+    // (all consumers take words in pairs, so attempts start at even offsets; q odd = straddles two blocks,
+    //  which happens after std::gamma_distribution has drawn its single uniform = half a block)
+    const int nq = 2 * nblk - 1;
+    for (int q = tid; q < nq; q += T)
+        a.acc[q] = polar_attempt(a.words[2 * q], a.words[2 * q + 1], a.words[2 * q + 2], a.words[2 * q + 3]).ok ? 1 : 0;
+    __syncthreads();
+    // ---- 3. per class (q & 1): rank[q] = #accepted attempts before q, pos_of_rank[class][r] = t ------
+    for (int c = 0; c < 2; ++c) {
+        const int nc = (nq - c + 1) / 2;            // attempts q = 2t + c, t in [0, nc)
+        const int chunk = (nc + T - 1) / T;
+        const int t0 = min(nc, tid * chunk), t1 = min(nc, t0 + chunk);
+        int cnt = 0;
+        for (int t = t0; t < t1; ++t) cnt += a.acc[2 * t + c];
+        s_scan[tid] = cnt;
+        __syncthreads();
+        for (int off = 1; off < T; off <<= 1) {     // inclusive Hillis-Steele scan
+            const int v = (tid >= off) ? s_scan[tid - off] : 0;
+            __syncthreads();
+            s_scan[tid] += v;
+            __syncthreads();
+        }
+        int r = s_scan[tid] - cnt;                  // exclusive prefix
+        if (tid == T - 1) s_total[c] = s_scan[tid];
+        for (int t = t0; t < t1; ++t) {
+            a.rank[2 * t + c] = r;
+            if (a.acc[2 * t + c]) { a.pos_of_rank[c * nblk + r] = t; ++r; }
+        }
+        __syncthreads();
+    }
+    // ---- 4. sequential walk: K gamma draws with the junk / kept normal runs between them ------------
+    // (WishartUnitChol, mvnormal.cpp:64-73; std::gamma_distribution = Marsaglia-Tsang,
+    //  /usr/include/c++/13/bits/random.tcc:2353-2394). Only the stream POSITIONS of the kept normals are
+    //  recorded here; their values are computed in parallel in step 5.
+    double *au = a.mats + 3 * (size_t)KK;
+    for (int e = tid; e < KK; e += T) au[e] = 0.0;
+    __syncthreads();
+    if (tid == 0) {
+        const int nu_c = K + N;  // nu + N, mvnormal.cpp:125
+        int pos = 0;             // word offset, always even
+        bool bad = false;
+        auto next_attempt = [&](int p) -> int {   // first accepted attempt at/after word offset p -> its q, or -1
+            const int q = p >> 1;
+            if (q >= nq) return -1;
+            const int c = q & 1, r = a.rank[q];
+            if (r >= s_total[c]) return -1;
+            return 2 * a.pos_of_rank[c * nblk + r] + c;
+        };
+        auto skip_normals = [&](int p, int n, int *start_rank, int *cls) -> int {  // consume n normals from p
+            const int q = p >> 1;
+            if (q >= nq) return -1;
+            const int c = q & 1, r = a.rank[q];
+            *start_rank = r; *cls = c;
+            if (n == 0) return p;
+            if (r + n - 1 >= s_total[c]) return -1;
+            return 2 * (2 * a.pos_of_rank[c * nblk + r + n - 1] + c) + 4;
+        };
+        for (int i = 0; i < K && !bad; ++i) {
+            const double alpha = 0.5 * (nu_c - i);
+            if (alpha < 1.0) { bad = true; break; }  // would need the pow() branch; N >= 1 never gets here
+            const double a1 = alpha - 1.0 / 3.0;
+            const double a2 = 1.0 / sqrt(9.0 * a1);
+            bool saved_ok = false;
+            double saved = 0.0, n, v, u;
+            bool again;
+            do {
+                do {
+                    if (saved_ok) { saved_ok = false; n = saved; }
+                    else {
+                        const int q = next_attempt(pos);
+                        if (q < 0) { bad = true; break; }
+                        const Polar p = polar_attempt(a.words[2 * q], a.words[2 * q + 1], a.words[2 * q + 2], a.words[2 * q + 3]);
+                        const double mult = polar_mult(p.r2);
+                        saved = p.x * mult; saved_ok = true;
+                        n = p.y * mult;
+                        pos = 2 * q + 4;
+                    }
+                    v = 1.0 + a2 * n;
+                } while (v <= 0.0);
+                if (bad) break;
+                v = v * v * v;
+                if ((pos >> 1) >= 2 * nblk - 0 || pos + 1 >= 4 * nblk) { bad = true; break; }
+                u = canonical(a.words[pos], a.words[pos + 1]);
+                pos += 2;
+                again = (u > 1.0 - 0.0331 * n * n * n * n) && (log(u) > (0.5 * n * n + a1 * (1.0 - v + log(v))));
+            } while (again);
+            if (bad) break;
+            au[i + i * K] = sqrt(2.0 * (a1 * v * 1.0));
+            int r0, c0;
+            pos = skip_normals(pos, K - i - 1, &r0, &c0);   // VectorXd r = nrandn(K-i-1), discarded (:70)
+            if (pos < 0) { bad = true; break; }
+            pos = skip_normals(pos, K - i - 1, &r0, &c0);   // the kept ones (:71)
+            if (pos < 0) { bad = true; break; }
+            a.row_start[i] = r0; a.row_cls[i] = c0;
+        }
+        if (!bad) {
+            int r0, c0;
+            pos = skip_normals(pos, K, &r0, &c0);           // MvNormalChol_prec: nrandn(K) (mvnormal.cpp:58)
+            if (pos < 0) bad = true;
+            a.row_start[K] = r0; a.row_cls[K] = c0;
+        }
+        if (bad) { atomicMax(a.err, ERR_RNG); s_fail = 1; }
+    }
+    __syncthreads();
+    if (s_fail) return;
+    // ---- 5. values of the kept normals ---------------------------------------------------------------
+    double *zv = a.vecs;              // K
+    for (int e = tid; e < KK; e += T) {
+        const int i = e % K, j = e / K;
+        if (j > i) {
+            const int c = a.row_cls[i];
+            au[i + j * K] = normal_at(a.words, 2 * a.pos_of_rank[c * nblk + a.row_start[i] + (j - i - 1)] + c);
+        }
+    }
+    for (int t = tid; t < K; t += T) {
+        const int c = a.row_cls[K];
+        zv[t] = normal_at(a.words, 2 * a.pos_of_rank[c * nblk + a.row_start[K] + t] + c);
+    }
+    // ---- 6. CondNormalWishart (mvnormal.cpp:116-125) --------------------------------------------------
+    const double kappa = 2.0;
+    double *mu_c = a.vecs + K, *mu_m = a.vecs + 2 * K;
+    for (int i = tid; i < K; i += T) {
+        const double Um = (a.sum ? a.sum[i] : 0.0) / N;
+        mu_m[i] = 0.0 - Um;
+        mu_c[i] = (kappa * 0.0 + N * Um) / (kappa + N);
+    }
+    __syncthreads();
+    const double kappa_c = kappa + N;
+    const double kappa_m = (kappa * N) / (kappa + N);
+    double *lu = a.mats;                       // X, then its LU factors
+    double *bt = a.mats + (size_t)KK;          // inverse work, layout [i][c]
+    double *L = a.mats + 2 * (size_t)KK;       // T_c, then its lower Cholesky factor
+    for (int e = tid; e < KK; e += T) {
+        const int i = e % K, j = e / K;
+        lu[e] = ((i == j ? 1.0 : 0.0) + N * a.cov[e]) + kappa_m * (mu_m[i] * mu_m[j]);
+    }
+    __syncthreads();
+    // LU with partial pivoting (first maximum wins, like a sequential strict-> scan)
+    for (int k = 0; k < K; ++k) {
+        if (tid < 32) {
+            double best = -1.0; int bi = K;
+            for (int i = k + tid; i < K; i += 32) {
+                const double v = fabs(lu[i + k * K]);
+                if (v > best) { best = v; bi = i; }
+            }
+            for (int off = 16; off; off >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, best, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            if (tid == 0) { s_piv = bi; a.piv[k] = bi; }
+        }
+        __syncthreads();
+        const int p = s_piv;
+        if (p != k)
+            for (int j = tid; j < K; j += T) {
+                const double t0 = lu[k + j * K];
+                lu[k + j * K] = lu[p + j * K];
+                lu[p + j * K] = t0;
+            }
+        __syncthreads();
+        const double d = lu[k + k * K];
+        for (int i = k + 1 + tid; i < K; i += T) lu[i + k * K] = lu[i + k * K] / d;
+        __syncthreads();
+        const int m = K - k - 1;
+        for (int e = tid; e < m * m; e += T) {
+            const int i = k + 1 + e % m, j = k + 1 + e / m;
+            lu[i + j * K] = lu[i + j * K] - lu[i + k * K] * lu[k + j * K];
+        }
+        __syncthreads();
+    }
+    // T_c = X^-1: thread c solves column c (not symmetrised, mvnormal.cpp:124)
+    for (int c = tid; c < K; c += T) {
+        for (int i = 0; i < K; ++i) bt[i * K + c] = (i == c) ? 1.0 : 0.0;
+        for (int k = 0; k < K; ++k) {
+            const int p = a.piv[k];
+            if (p != k) { const double t0 = bt[k * K + c]; bt[k * K + c] = bt[p * K + c]; bt[p * K + c] = t0; }
+        }
+        for (int i = 0; i < K; ++i) {
+            double s = bt[i * K + c];
+            for (int j = 0; j < i; ++j) s -= lu[i + j * K] * bt[j * K + c];
+            bt[i * K + c] = s;
+        }
+        for (int i = K - 1; i >= 0; --i) {
+            double s = bt[i * K + c];
+            for (int j = i + 1; j < K; ++j) s -= lu[i + j * K] * bt[j * K + c];
+            bt[i * K + c] = s / lu[i + i * K];
+        }
+        for (int i = 0; i < K; ++i) L[i + c * K] = bt[i * K + c];
+    }
+    __syncthreads();
+    // chol = T_c.llt(): lower factor from the lower triangle (mvnormal.cpp:78)
+    for (int k = 0; k < K; ++k) {
+        const double x = L[k + k * K];
+        if (x <= 0.0) { if (tid == 0) atomicMax(a.err, ERR_HYPER_NOT_PD | (unsigned)k); return; }
+        const double sx = sqrt(x);
+        for (int i = k + 1 + tid; i < K; i += T) L[i + k * K] = L[i + k * K] / sx;
+        __syncthreads();
+        if (tid == 0) L[k + k * K] = sx;
+        const int m = K - k - 1;
+        for (int e = tid; e < m * m; e += T) {
+            const int i = k + 1 + e % m, c = k + 1 + e / m;
+            if (i >= c) L[i + c * K] = L[i + c * K] - L[i + k * K] * L[c + k * K];
+        }
+        __syncthreads();
+    }
+    // U = au * chol.matrixU()  (mvnormal.cpp:83)
+    double *U = a.LambdaU;
+    for (int e = tid; e < KK; e += T) {
+        const int i = e % K, j = e / K;
+        double s = 0.0;
+        if (i <= j)
+            for (int k = i; k <= j; ++k) s += au[i + k * K] * L[j + k * K];
+        U[e] = s;
+    }
+    __syncthreads();
+    // mu = U \ z / sqrt(kappa_c) + mu_c  (mvnormal.cpp:58-60), column-oriented back substitution
+    for (int j = K - 1; j >= 0; --j) {
+        if (tid == 0) zv[j] = zv[j] / U[j + j * K];
+        __syncthreads();
+        const double bj = zv[j];
+        for (int i = tid; i < j; i += T) zv[i] = zv[i] - U[i + j * K] * bj;
+        __syncthreads();
+    }
+    const double sk = sqrt(kappa_c);
+    for (int i = tid; i < K; i += T) a.mu[i] = (zv[i] / sk) + mu_c[i];
+    // LambdaF = U^T U  (bpmf.h:101)
+    for (int e = tid; e < KK; e += T) {
+        const int i = e % K, j = e / K;
+        const int kmax = min(i, j);
+        double s = 0.0;
+        for (int k = 0; k <= kmax; ++k) s += U[k + i * K] * U[k + j * K];
+        a.LambdaF[e] = s;
+    }
+}
+
+cudaError_t launch_hyper(bpmf_gpu_ctx *c, int side, uint32_t iter, const double *d_sum, const double *d_cov)
+{
+    SideDev &s = c->side[side];
+    HyperArgs a;
+    a.K = c->K; a.N = s.num; a.nblk = c->hs.nblk; a.iter = iter;
+    a.sum = d_sum; a.cov = d_cov;
+    a.words = c->hs.words; a.acc = c->hs.acc; a.rank = c->hs.rank; a.pos_of_rank = c->hs.pos_of_rank;
+    a.row_start = c->hs.row_start; a.row_cls = c->hs.row_cls; a.piv = c->hs.piv;
+    a.mats = c->hs.mats; a.vecs = c->hs.vecs;
+    a.mu = s.hp.mu; a.LambdaU = s.hp.LambdaU; a.LambdaF = s.hp.LambdaF;
+    a.err = c->d_err;
+    hyper_kernel<<<1, 1024, 0, c->stream>>>(a);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+// =================================================================================================
+// Per-item conditional update, reference order, any K: one CTA per item
+// =================================================================================================
+struct ItemArgs {
+    int K, from, to;
+    uint32_t iter;
+    double alpha, mean_rating;
+    const int64_t *colptr;
+    const int32_t *rowidx;
+    const double *val;
+    const double *other;   // K x num_other
+    double *items;         // K x num
+    int npeers;
+    double *const *peers;
+    const double *mu, *LambdaF;
+    unsigned int *work_counter;
+    unsigned long long *err;
+};
+
+constexpr int EXACT_TILE = 16;  // ratings staged per step
+
+size_t exact_items_smem_bytes(int K) { return sizeof(double) * ((size_t)K * K + 3 * (size_t)K + (size_t)EXACT_TILE * K + EXACT_TILE); }
+
+__global__ void items_exact_kernel(ItemArgs p)
+{
+    extern __shared__ double sm[];
+    const int K = p.K, KK = K * K, tid = threadIdx.x, T = blockDim.x;
+    double *MM = sm;
+    double *rr = MM + KK;
+    double *z = rr + K;
+    double *ytile = z + K;
+    double *w = ytile + EXACT_TILE * K;
+    __shared__ int s_item;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = p.from + (int)atomicAdd(p.work_counter, 1u);
+        __syncthreads();
+        const int idx = s_item;
+        if (idx >= p.to) break;
+        // rng_set_pos((idx+1) * num_latent * (iter+1))  (sample.cpp:266), uint32 truncation
+        const uint32_t c = (uint32_t)(((long long)idx + 1) * (long long)K * ((long long)p.iter + 1));
+        if (tid < 32) warp_randn(c, K, z);
+        // rr = LambdaF * hp.mu (sample.cpp:285); MM = 0
+        for (int a = tid; a < K; a += T) {
+            double s = 0.0;
+            for (int j = 0; j < K; ++j) s += p.LambdaF[a + j * K] * p.mu[j];
+            rr[a] = s;
+        }
+        for (int e = tid; e < KK; e += T) MM[e] = 0.0;
+        __syncthreads();
+        // computeMuLambda (sample.cpp:251-257), entries of the upper triangle accumulate in rating order
+        const int64_t ps = p.colptr[idx], pe = p.colptr[idx + 1];
+        for (int64_t t0 = ps; t0 < pe; t0 += EXACT_TILE) {
+            const int nr = (int)min((int64_t)EXACT_TILE, pe - t0);
+            for (int e = tid; e < nr * K; e += T) {
+                const int r = e / K, a = e - r * K;
+                ytile[e] = p.other[(size_t)p.rowidx[t0 + r] * K + a];
+            }
+            for (int r = tid; r < nr; r += T) w[r] = (p.val[t0 + r] - p.mean_rating) * p.alpha;
+            __syncthreads();
+            for (int e = tid; e < KK; e += T) {
+                const int a = e % K, b = e / K;
+                if (a <= b) {
+                    double acc = MM[e];
+                    for (int r = 0; r < nr; ++r) acc += ytile[r * K + a] * ytile[r * K + b];
+                    MM[e] = acc;
+                }
+            }
+            for (int a = tid; a < K; a += T) {
+                double acc = rr[a];
+                for (int r = 0; r < nr; ++r) acc += ytile[r * K + a] * w[r];
+                rr[a] = acc;
+            }
+            __syncthreads();
+        }
+        // lower triangle of MM = LambdaF + alpha * MM (sample.cpp:297-298); the LLT only reads the lower part
+        for (int e = tid; e < KK; e += T) {
+            const int a = e % K, b = e / K;
+            if (a >= b) MM[a + b * K] = p.LambdaF[a + b * K] + p.alpha * MM[b + a * K];
+        }
+        __syncthreads();
+        // chol.compute(MM) (sample.cpp:306): right-looking, per-element update order j = 0..k-1 as in the oracle
+        bool failed = false;
+        for (int k = 0; k < K; ++k) {
+            const double x = MM[k + k * K];
+            if (x <= 0.0) { failed = true; break; }
+            const double sx = sqrt(x);
+            for (int i = k + 1 + tid; i < K; i += T) MM[i + k * K] = MM[i + k * K] / sx;
+            __syncthreads();
+            if (tid == 0) MM[k + k * K] = sx;
+            const int m = K - k - 1;
+            for (int e = tid; e < m * m; e += T) {
+                const int i = k + 1 + e % m, cc = k + 1 + e / m;
+                if (i >= cc) MM[i + cc * K] = MM[i + cc * K] - MM[i + k * K] * MM[cc + k * K];
+            }
+            __syncthreads();
+        }
+        if (failed) {  // THROWERROR("Cholesky failed") (sample.cpp:308): reported through the error word
+            if (tid == 0) atomicMax(p.err, ERR_CHOLESKY | (unsigned)idx);
+            continue;
+        }
+        // chol.matrixL().solveInPlace(rr) (sample.cpp:321)
+        for (int j = 0; j < K; ++j) {
+            if (tid == 0) rr[j] = rr[j] / MM[j + j * K];
+            __syncthreads();
+            const double bj = rr[j];
+            for (int i = j + 1 + tid; i < K; i += T) rr[i] = rr[i] - MM[i + j * K] * bj;
+            __syncthreads();
+        }
+        // rr += nrandn(K) (sample.cpp:322)
+        for (int a = tid; a < K; a += T) rr[a] = rr[a] + z[a];
+        __syncthreads();
+        // chol.matrixU().solveInPlace(rr) (sample.cpp:323)
+        for (int j = K - 1; j >= 0; --j) {
+            if (tid == 0) rr[j] = rr[j] / MM[j + j * K];
+            __syncthreads();
+            const double bj = rr[j];
+            for (int i = tid; i < j; i += T) rr[i] = rr[i] - MM[j + i * K] * bj;
+            __syncthreads();
+        }
+        // items().col(idx) = rr (sample.cpp:324) — and into every peer replica (replaces send_item)
+        for (int a = tid; a < K; a += T) {
+            const double v = rr[a];
+            p.items[(size_t)idx * K + a] = v;
+            for (int q = 0; q < p.npeers; ++q)
+                if (p.peers[q] && p.peers[q] != p.items) p.peers[q][(size_t)idx * K + a] = v;
+        }
+    }
+}
+
+cudaError_t launch_items_exact(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha)
+{
+    SideDev &s = c->side[side];
+    const SideDev &o = c->side[1 - side];
+    ItemArgs p;
+    p.K = c->K; p.from = s.from; p.to = s.to; p.iter = iter; p.alpha = alpha; p.mean_rating = s.mean_rating;
+    p.colptr = s.colptr; p.rowidx = s.rowidx; p.val = s.val;
+    p.other = o.items; p.items = s.items;
+    p.npeers = s.npeers; p.peers = s.peers_dev;
+    p.mu = s.hp.mu; p.LambdaF = s.hp.LambdaF;
+    p.work_counter = s.work_counter; p.err = c->d_err;
+    cudaError_t e = cudaMemsetAsync(s.work_counter, 0, sizeof(unsigned int), c->stream);
+    if (e != cudaSuccess) return e;
+    const size_t smem = exact_items_smem_bytes(c->K);
+    const int threads = c->K <= 48 ? 128 : 256;
+    e = cudaFuncSetAttribute(items_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, items_exact_kernel, threads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    long long n = (long long)s.to - s.from;
+    long long grid = (long long)c->sm_count * per_sm;
+    if (grid > n) grid = n;
+    if (grid < 1) return cudaSuccess;
+    items_exact_kernel<<<(unsigned)grid, threads, smem, c->stream>>>(p);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+// =================================================================================================
+// Sweep reductions: sum, prod (outer products), norm over ALL items, then cov (sample.cpp:359-362,379-384)
+// =================================================================================================
+template <int NE>
+__global__ void __launch_bounds__(256) stats_partial_kernel(const double *__restrict__ items, int N, int K, double *__restrict__ partials)
+{
+    constexpr int TILE = 32;
+    extern __shared__ double sm[];  // TILE * K
+    const int tid = threadIdx.x, T = blockDim.x, KK = K * K;
+    const int chunk = (N + gridDim.x - 1) / gridDim.x;
+    const int i0 = min(N, (int)blockIdx.x * chunk), i1 = min(N, i0 + chunk);
+    double acc[NE];
+    int ea[NE], eb[NE];
+#pragma unroll
+    for (int n = 0; n < NE; ++n) {
+        acc[n] = 0.0;
+        const int e = tid + n * T;
+        ea[n] = e < KK ? e % K : -1;
+        eb[n] = e < KK ? e / K : 0;
+    }
+    double s1 = 0.0, s2 = 0.0;  // for tid < K: sum of x[tid], sum of x[tid]^2
+    for (int t0 = i0; t0 < i1; t0 += TILE) {
+        const int nt = min(TILE, i1 - t0);
+        __syncthreads();
+        for (int e = tid; e < nt * K; e += T) sm[e] = items[(size_t)t0 * K + e];
+        __syncthreads();
+        for (int t = 0; t < nt; ++t) {
+            const double *x = sm + t * K;
+#pragma unroll
+            for (int n = 0; n < NE; ++n)
+                if (ea[n] >= 0) acc[n] += x[ea[n]] * x[eb[n]];
+            if (tid < K) { const double v = x[tid]; s1 += v; s2 += v * v; }
+        }
+    }
+    double *out = partials + (size_t)blockIdx.x * (KK + K + 1);
+#pragma unroll
+    for (int n = 0; n < NE; ++n)
+        if (ea[n] >= 0) out[tid + n * T] = acc[n];
+    __syncthreads();
+    for (int a = tid; a < K; a += T) { out[KK + a] = s1; sm[a] = s2; }  // (K <= 256 = T)
+    __syncthreads();
+    if (tid == 0) {
+        double nn = 0.0;
+        for (int a = 0; a < K; ++a) nn += sm[a];
+        out[KK + K] = nn;
+    }
+}
+
+__global__ void __launch_bounds__(256) stats_final_kernel(const double *__restrict__ partials, int nblocks, int N, int K, double *sum,
+                                                           double *prod, double *cov, double *norm)
+{
+    const int KK = K * K, W = KK + K + 1;
+    for (int e = threadIdx.x; e < W; e += blockDim.x) {
+        double s = 0.0;
+        for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * W + e];
+        if (e < KK) prod[e] = s;
+        else if (e < KK + K) sum[e - KK] = s;
+        else *norm = s;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < KK; e += blockDim.x) {
+        const int a = e % K, b = e / K;
+        cov[e] = (prod[e] - (sum[a] * sum[b] / N)) / (N - 1);
+    }
+}
+
+cudaError_t launch_stats(bpmf_gpu_ctx *c, int side)
+{
+    SideDev &s = c->side[side];
+    const int K = c->K, KK = K * K;
+    const int ne = (KK + 255) / 256;
+    const size_t smem = sizeof(double) * 32 * K;
+    const int nb = STATS_BLOCKS;
+#define BPMF_STATS_CASE(NE) stats_partial_kernel<NE><<<nb, 256, smem, c->stream>>>(s.items, s.num, K, s.partials)
+    if (ne <= 1) BPMF_STATS_CASE(1);
+    else if (ne <= 2) BPMF_STATS_CASE(2);
+    else if (ne <= 4) BPMF_STATS_CASE(4);
+    else if (ne <= 8) BPMF_STATS_CASE(8);
+    else if (ne <= 16) BPMF_STATS_CASE(16);
+    else if (ne <= 32) BPMF_STATS_CASE(32);
+    else if (ne <= 64) BPMF_STATS_CASE(64);
+    else return cudaErrorInvalidValue;
+#undef BPMF_STATS_CASE
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    stats_final_kernel<<<1, 256, 0, c->stream>>>(s.partials, nb, s.num, K, s.sum, s.prod, s.cov, s.norm);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+// =================================================================================================
+// Sys::predict (sample.cpp:48-96): one thread per test entry, Welford update of Pavg/Pm2 (quirk Q4 kept)
+// =================================================================================================
+__global__ void __launch_bounds__(256) predict_kernel(int K, int64_t nnz, int n, double mean_rating, const int32_t *__restrict__ t_col,
+                                                      const int32_t *__restrict__ t_row, const double *__restrict__ t_val,
+                                                      const double *__restrict__ items, const double *__restrict__ other, double *pavg,
+                                                      double *pm2, double *partials)
+{
+    double se = 0.0, se_avg = 0.0;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x) {
+        const double *m = items + (size_t)t_col[p] * K;
+        const double *u = other + (size_t)t_row[p] * K;
+        double d = 0.0;
+        for (int a = 0; a < K; ++a) d += m[a] * u[a];
+        const double pred = d + mean_rating;
+        const double r = t_val[p];
+        se += (r - pred) * (r - pred);
+        double avg = pavg[p];
+        const double delta = pred - avg;
+        avg = (n == 0) ? pred : (avg + delta / n);
+        pavg[p] = avg;
+        pm2[p] = (n == 0) ? 0.0 : pm2[p] + delta * (pred - avg);
+        se_avg += (r - avg) * (r - avg);
+    }
+    __shared__ double s0[256], s1[256];
+    s0[threadIdx.x] = se; s1[threadIdx.x] = se_avg;
+    __syncthreads();
+    for (int off = 128; off; off >>= 1) {
+        if ((int)threadIdx.x < off) { s0[threadIdx.x] += s0[threadIdx.x + off]; s1[threadIdx.x] += s1[threadIdx.x + off]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { partials[2 * blockIdx.x] = s0[0]; partials[2 * blockIdx.x + 1] = s1[0]; }
+}
+__global__ void predict_final_kernel(const double *partials, int nb, double *out)
+{
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int i = 0; i < nb; ++i) { a += partials[2 * i]; b += partials[2 * i + 1]; }
+        out[0] = a; out[1] = b;
+    }
+}
+
+cudaError_t launch_predict(bpmf_gpu_ctx *c, int side, int n)
+{
+    SideDev &s = c->side[side];
+    const SideDev &o = c->side[1 - side];
+    if (s.nnz_test == 0) return cudaSuccess;
+    long long nb = (s.nnz_test + 255) / 256;
+    if (nb > s.pred_blocks) nb = s.pred_blocks;
+    predict_kernel<<<(unsigned)nb, 256, 0, c->stream>>>(c->K, s.nnz_test, n, s.mean_rating, s.t_col, s.t_rowidx, s.t_val, s.items,
+                                                         o.items, s.pavg, s.pm2, s.pred_partials);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    predict_final_kernel<<<1, 32, 0, c->stream>>>(s.pred_partials, (int)nb, s.pred_partials + 2 * (size_t)s.pred_blocks);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+// =================================================================================================
+// RNG probe
+// =================================================================================================
+__global__ void debug_randn_kernel(uint32_t c, int n, double *out)
+{
+    extern __shared__ double sm[];
+    warp_randn(c, n, sm);
+    __syncwarp();
+    for (int i = threadIdx.x; i < n; i += 32) out[i] = sm[i];
+}
+cudaError_t launch_debug_randn(bpmf_gpu_ctx *c, uint32_t seed, int n, double *d_out)
+{
+    debug_randn_kernel<<<1, 32, sizeof(double) * n, c->stream>>>(seed, n, d_out);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace bpmf

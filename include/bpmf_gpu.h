@@ -1,0 +1,122 @@
+/* bpmf_gpu.h — C ABI of libbpmf_b200.so: the B200 (sm_100a) implementation of the BPMF Gibbs sweep.
+ *
+ * This is the drop-in boundary for the reference's communication-backend plug-in point
+ * (a header that defines `SYS` and a `struct X_Sys : Sys`, selected in c++/bpmf.cpp:19-39 the way
+ * c++/nocomm.h:6-37 does for NO_COMM). A `CUDA_Sys : Sys` backend calls exactly these entry points
+ * from `alloc_and_init()` and from its override of `virtual void Sys::sample(Sys &in)`
+ * (c++/bpmf.h:144,216,219); INTEGRATION.md shows that binding.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every function returns 0 on success or a BPMF_GPU_E* code and
+ *     never throws. bpmf_gpu_last_error() gives the message of the last failure on that context.
+ *   - "side" 0 = movies (columns of the input file), 1 = users (rows), as in c++/bpmf.cpp:131-132.
+ *   - all dense K x K matrices are column-major, latent matrices are item-major K-vectors
+ *     (item i at ptr + i*K), exactly `Sys::items_ptr` (c++/bpmf.h:193-194).
+ *   - host pointers are borrowed for the duration of the call only. Pointers named dev_* are CUDA
+ *     device pointers on the context's device.
+ *   - one context drives one GPU; all calls of a context must come from one host thread at a time
+ *     (the reference enters Sys::sample from the main thread, c++/bpmf.cpp:184-185).
+ *   - work is enqueued on the context's stream (bpmf_gpu_set_stream); calls that return host data
+ *     synchronise that stream, the others are asynchronous.
+ */
+#ifndef BPMF_GPU_H
+#define BPMF_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BPMF_GPU_OK 0
+#define BPMF_GPU_EINVAL 1      /* bad argument / call order                                   */
+#define BPMF_GPU_ECUDA 2       /* a CUDA runtime call or kernel failed                         */
+#define BPMF_GPU_ECHOLESKY 3   /* "Cholesky failed" (c++/sample.cpp:308): pivot <= 0 for an item */
+#define BPMF_GPU_ERNG 4        /* hyper-parameter draw ran out of pre-generated Philox blocks  */
+#define BPMF_GPU_ENODEVICE 5   /* no usable sm_100 device (there is NO CPU fallback)           */
+
+#define BPMF_GPU_MOVIES 0
+#define BPMF_GPU_USERS 1
+
+/* kernel variants of the per-item conditional update */
+#define BPMF_GPU_KERNEL_AUTO 0   /* fastest available for this K                                          */
+#define BPMF_GPU_KERNEL_EXACT 1  /* any K; reference summation order, no FMA contraction (debug / fallback) */
+#define BPMF_GPU_KERNEL_DMMA 2   /* K == 32: warp per item, fp64 tensor-core (DMMA) Gram, registers         */
+
+typedef struct bpmf_gpu_ctx bpmf_gpu_ctx;
+
+/* ---- life cycle: Sys::Init / Sys::Finalize (c++/nocomm.h:19-27) ------------------------------ */
+int bpmf_gpu_create(bpmf_gpu_ctx **out, int device, int num_latent);
+int bpmf_gpu_destroy(bpmf_gpu_ctx *ctx);
+const char *bpmf_gpu_last_error(const bpmf_gpu_ctx *ctx); /* ctx may be NULL: last create() failure */
+int bpmf_gpu_num_latent(const bpmf_gpu_ctx *ctx);
+/* cudaStream_t to enqueue on (NULL = legacy default stream). */
+int bpmf_gpu_set_stream(bpmf_gpu_ctx *ctx, void *cuda_stream);
+/* Sys::sync (c++/nocomm.h:35): wait for everything enqueued so far, report deferred kernel errors. */
+int bpmf_gpu_sync(bpmf_gpu_ctx *ctx);
+
+/* ---- data: the Sys constructors + Sys::init (c++/sample.cpp:112-137,179-190) ------------------
+ * Train matrix of one side in compressed-column form: column i = item i of this side, rowidx =
+ * indices into the OTHER side ascending, explicit zeros kept (Eigen::SparseMatrix<double>, int32
+ * inner indices, c++/bpmf.h:55). mean_rating is Sys::mean_rating (c++/sample.cpp:183). Items are
+ * zeroed, iter = -1, cov = 0, norm = 0, range = [0, num_items). */
+int bpmf_gpu_load_side(bpmf_gpu_ctx *ctx, int side, int num_items, int num_other, const int64_t *colptr,
+                       const int32_t *rowidx, const double *val, double mean_rating);
+/* Test matrix T of one side, same layout; Pavg = Pm2 = T (c++/sample.cpp:123). */
+int bpmf_gpu_load_test(bpmf_gpu_ctx *ctx, int side, const int64_t *colptr, const int32_t *rowidx, const double *val);
+/* Sys::from()/to() (c++/bpmf.h:171-172): the items this context samples; others are left to peers. */
+int bpmf_gpu_set_range(bpmf_gpu_ctx *ctx, int side, int from, int to);
+/* Use caller-owned device storage (K * num_items doubles) for a side's latent matrix, e.g. a
+ * torch tensor that NCCL all-gathers into; the current contents are copied over. NULL = go back
+ * to internal storage. */
+int bpmf_gpu_bind_items(bpmf_gpu_ctx *ctx, int side, double *dev_items);
+/* Multi-GPU push: device pointers (peer-mapped, one per rank, NULL entries skipped) to every
+ * replica of this side's latent matrix; the item kernel stores each fresh K-vector into all of
+ * them as it is produced (replaces Sys::send_item, c++/bpmf.h:216). npeers = 0 turns it off. */
+int bpmf_gpu_set_peers(bpmf_gpu_ctx *ctx, int side, int npeers, double *const *dev_peer_items);
+int bpmf_gpu_items_device_ptr(bpmf_gpu_ctx *ctx, int side, double **dev_items);
+
+int bpmf_gpu_set_items(bpmf_gpu_ctx *ctx, int side, const double *host_items);
+int bpmf_gpu_get_items(bpmf_gpu_ctx *ctx, int side, double *host_items); /* synchronises */
+int bpmf_gpu_get_iter(bpmf_gpu_ctx *ctx, int side, int *iter);
+int bpmf_gpu_set_iter(bpmf_gpu_ctx *ctx, int side, int iter);
+
+/* ---- the hot path ---------------------------------------------------------------------------
+ * bpmf_gpu_sample == Sys::sample(Sys &other) of NO_COMM (c++/sample.cpp:341-385): iter++, seed,
+ * hp.sample(num, sum (always 0), cov), every item in [from,to) drawn by the
+ * fused kernel, then sum / prod / norm reduced over ALL items and cov updated on the device. */
+int bpmf_gpu_sample(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_variant);
+
+/* The stages of bpmf_gpu_sample, individually callable (multi-GPU hosts put the exchange of the
+ * fresh columns between _sample_items and _reduce_stats; tests probe each stage). */
+/* rng_set_pos(iter); hp.sample(N, sum, cov)  (c++/sample.cpp:349-350, c++/bpmf.h:98-103,
+ * c++/mvnormal.cpp:56-135). host_sum may be NULL (= zeros, what the reference always passes);
+ * host_cov NULL = the side's device-resident cov from the last _reduce_stats. */
+int bpmf_gpu_sample_hyper(bpmf_gpu_ctx *ctx, int side, uint32_t iter, const double *host_sum, const double *host_cov);
+/* override the hyper-parameters (tests) / read them back: mu[K], LambdaU[K*K], LambdaF[K*K] */
+int bpmf_gpu_set_hyper(bpmf_gpu_ctx *ctx, int side, const double *mu, const double *LambdaF);
+int bpmf_gpu_get_hyper(bpmf_gpu_ctx *ctx, int side, double *mu, double *LambdaU, double *LambdaF);
+/* Sys::sample(long idx, Sys &in) for idx in [from,to) (c++/sample.cpp:263-336, 248-258) with the
+ * side's current hyper-parameters; `iter` is the value the reference's Sys::iter has inside the call. */
+int bpmf_gpu_sample_items(bpmf_gpu_ctx *ctx, int side, uint32_t iter, double alpha, int kernel_variant);
+/* sums.combine()/prods.combine()/norms.combine() + cov (c++/sample.cpp:359-362,379-384) over all items */
+int bpmf_gpu_reduce_stats(bpmf_gpu_ctx *ctx, int side);
+/* any of the out pointers may be NULL. sum[K], prod[K*K], cov[K*K], norm scalar. synchronises. */
+int bpmf_gpu_get_stats(bpmf_gpu_ctx *ctx, int side, double *sum, double *prod, double *cov, double *norm);
+
+/* ---- Sys::predict (c++/sample.cpp:48-96) on the device, over all test entries ------------------ */
+int bpmf_gpu_predict(bpmf_gpu_ctx *ctx, int side, int burnin, double *rmse, double *rmse_avg, int64_t *num_predict);
+int bpmf_gpu_get_predictions(bpmf_gpu_ctx *ctx, int side, double *pavg, double *pm2);
+
+/* ---- introspection --------------------------------------------------------------------------- */
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t bpmf_gpu_launch_count(const bpmf_gpu_ctx *ctx);
+/* milliseconds the last bpmf_gpu_sample_items kernel took, from CUDA events on the context's stream */
+int bpmf_gpu_last_items_kernel_ms(bpmf_gpu_ctx *ctx, float *ms);
+/* device RNG probes for known-answer tests: n normals of the stream rng_set_pos(c) */
+int bpmf_gpu_debug_randn(bpmf_gpu_ctx *ctx, uint32_t c, int n, double *host_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BPMF_GPU_H */

@@ -136,11 +136,14 @@ inline void solve_lower_inplace(const double *A, int K, double *b)
         b[i] = s / A[i + i * K];
     }
 }
+// (terms are subtracted in the order the unknowns become available, j = K-1 down to i+1: the
+//  column-oriented form. Eigen's own order inside its blocked triangular solver is not reproducible
+//  without Eigen; any order is the same algorithm up to round-off.)
 inline void solve_lower_transposed_inplace(const double *A, int K, double *b)
 {
     for (int i = K - 1; i >= 0; --i) {
         double s = b[i];
-        for (int j = i + 1; j < K; ++j) s -= A[j + i * K] * b[j];
+        for (int j = K - 1; j > i; --j) s -= A[j + i * K] * b[j];
         b[i] = s / A[i + i * K];
     }
 }
@@ -149,7 +152,7 @@ inline void solve_upper_inplace(const double *U, int K, double *b)
 {
     for (int i = K - 1; i >= 0; --i) {
         double s = b[i];
-        for (int j = i + 1; j < K; ++j) s -= U[i + j * K] * b[j];
+        for (int j = K - 1; j > i; --j) s -= U[i + j * K] * b[j];
         b[i] = s / U[i + i * K];
     }
 }

@@ -1,0 +1,249 @@
+"""GPU parity tests: every stage of the CUDA path, called through the C ABI (libbpmf_b200.so), against the CPU
+oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): 1e-10 on latent vectors / per-iteration column means, 1e-6 on RMSE.
+The EXACT kernel variant (reference summation order, no FMA) is held to a far tighter bound, which pins the
+RNG stream logic: only log() (<= 1 ulp vs glibc) may differ.
+"""
+import numpy as np
+import pytest
+
+import util
+from util import MOVIES, USERS
+
+pytestmark = pytest.mark.gpu
+
+TOL_ITEMS = 1e-10
+TOL_RMSE = 1e-6
+TOL_EXACT = 2e-12
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import bpmf_b200
+    bpmf_b200.load_library()
+    return bpmf_b200
+
+
+def test_library_is_the_cuda_one(gpu):
+    # the product path must be the in-tree .so; no fallback module exists
+    import os
+    assert os.path.exists(gpu.SO_PATH)
+    ctx = gpu.Context(32)
+    assert ctx.launch_count() == 0
+    ctx.close()
+
+
+@pytest.mark.parametrize("c", [0, 10, 32, 12345, 0xFFFFFFF0])
+def test_device_randn_matches_libstdcxx_stream(gpu, oracle_lib, c):
+    ctx = gpu.Context(32)
+    for n in (1, 6, 32, 128, 1000):
+        got = ctx.debug_randn(c, n)
+        ref = oracle_lib.randn(c, n)
+        np.testing.assert_allclose(got, ref, rtol=4e-16 * 8, atol=0)
+    ctx.close()
+
+
+@pytest.mark.parametrize("K,N,it", [(10, 4, 0), (10, 2, 3), (16, 1000, 1), (32, 943, 7), (32, 1000000, 19), (64, 5000, 2),
+                                    (128, 200000, 5)])
+def test_hyper_draw(gpu, oracle_lib, K, N, it):
+    cov = util.random_spd(K, 100 + K + it, scale=0.3)
+    mu_o, LU_o, LF_o = oracle_lib.hyper(K, N, it, cov.T.copy())
+    ctx = gpu.Context(K)
+    # a side with N items: give it an empty pattern
+    ctx.load_side(MOVIES, N, 8, np.zeros(N + 1, np.int64), np.zeros(0, np.int32), np.zeros(0), 0.0)
+    ctx.sample_hyper(MOVIES, it, None, cov.T.copy().reshape(-1))
+    mu, LU, LF = ctx.get_hyper(MOVIES)
+    scale = np.abs(LF_o).max()
+    assert np.abs(LU - LU_o).max() <= 1e-11 * np.abs(LU_o).max()
+    assert np.abs(LF - LF_o).max() <= 1e-11 * scale
+    assert np.abs(mu - mu_o).max() <= 1e-11 * max(1.0, np.abs(mu_o).max())
+    ctx.close()
+
+
+def test_hyper_draw_zero_cov_first_sweep(gpu, oracle_lib):
+    # sweep 0: cov == 0 -> X = I (quirk Q6)
+    K, N = 32, 1682
+    mu_o, LU_o, LF_o = oracle_lib.hyper(K, N, 0, np.zeros((K, K)))
+    ctx = gpu.Context(K)
+    ctx.load_side(MOVIES, N, 8, np.zeros(N + 1, np.int64), np.zeros(0, np.int32), np.zeros(0), 0.0)
+    ctx.sample_hyper(MOVIES, 0)
+    mu, LU, LF = ctx.get_hyper(MOVIES)
+    np.testing.assert_allclose(LF, LF_o, rtol=0, atol=1e-11 * np.abs(LF_o).max())
+    np.testing.assert_allclose(mu, mu_o, rtol=0, atol=1e-12)
+    ctx.close()
+
+
+def _prime(orc, ctx, K, seed):
+    """Put identical non-trivial latents and hyper-parameters into oracle and GPU."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    for side in (MOVIES, USERS):
+        x = rng.normal(0, 0.7, size=(orc.num(side), K))
+        orc.set_items(side, x)
+        ctx.set_items(side, x)
+        LF = util.random_spd(K, seed + 10 + side, scale=2.0) + np.eye(K)
+        mu = rng.normal(0, 0.3, size=K)
+        orc.set_hyper(side, mu, LF)
+        ctx.set_hyper(side, mu, LF)
+
+
+CASES = [
+    # K, rows, cols, nnz, kwargs
+    (10, 40, 30, 300, {}),
+    (32, 300, 200, 6000, {}),
+    (32, 500, 64, 4000, dict(skew=1.2, empty_rows=40, heavy_col=450)),   # empty rows, a hot column > 32*k
+    (16, 120, 90, 1500, {}),
+    (64, 90, 70, 2500, {}),
+]
+
+
+@pytest.mark.parametrize("K,nr,nc,nnz,kw", CASES)
+@pytest.mark.parametrize("variant", ["exact", "dmma"])
+def test_item_update_one_sweep(gpu, K, nr, nc, nnz, kw, variant):
+    if variant == "dmma" and K != 32:
+        pytest.skip("DMMA kernel is K == 32")
+    v = gpu.KERNEL_EXACT if variant == "exact" else gpu.KERNEL_DMMA
+    tol = TOL_EXACT if variant == "exact" else TOL_ITEMS
+    train, test = util.synth_ratings(nr, nc, nnz, 7 + K, **kw)
+    orc = util.make_oracle(K, train, test)
+    ctx = util.make_gpu_from_oracle(orc, K)
+    _prime(orc, ctx, K, 99)
+    for side, it in ((MOVIES, 3), (USERS, 3), (MOVIES, 4)):
+        orc.set_iter(side, it)
+        orc.sample_range(side, 0, orc.num(side))
+        ctx.sample_items(side, it, 2.0, v)
+        got, ref = ctx.get_items(side), orc.items(side)
+        assert np.abs(got - ref).max() <= tol * max(1.0, np.abs(ref).max()), (side, it)
+        # keep both in lock-step for the next sweep
+        ctx.set_items(side, ref)
+    ctx.close()
+
+
+def test_stats_and_cov(gpu):
+    K = 32
+    train, test = util.synth_ratings(700, 333, 5000, 3)
+    orc = util.make_oracle(K, train, test)
+    ctx = util.make_gpu_from_oracle(orc, K)
+    orc.sweep(MOVIES)
+    ctx.set_items(MOVIES, orc.items(MOVIES))
+    ctx.reduce_stats(MOVIES)
+    s, p, c, n = ctx.get_stats(MOVIES)
+    so, po, co, no = orc.stats(MOVIES)
+    np.testing.assert_allclose(s, so, rtol=0, atol=1e-11 * max(1, np.abs(so).max()))
+    np.testing.assert_allclose(p, po, rtol=0, atol=1e-11 * np.abs(po).max())
+    np.testing.assert_allclose(c, co, rtol=0, atol=1e-11 * np.abs(co).max())
+    assert abs(n - no) <= 1e-11 * no
+    ctx.close()
+
+
+def _run_both(gpu, K, train, test, iters, burnin, variant, alpha=2.0):
+    orc = util.make_oracle(K, train, test, alpha=alpha, burnin=burnin)
+    ctx = util.make_gpu_from_oracle(orc, K)
+    worst = 0.0
+    for i in range(iters):
+        orc.iterate()
+        ctx.sample(MOVIES, alpha, variant)
+        ctx.sample(USERS, alpha, variant)
+        rm = ctx.predict(MOVIES, burnin)
+        ru = ctx.predict(USERS, burnin)
+        for side in (MOVIES, USERS):
+            got, ref = ctx.get_items(side), orc.items(side)
+            d = np.abs(got - ref).max()
+            worst = max(worst, d)
+            assert d <= TOL_ITEMS * max(1.0, np.abs(ref).max()), (i, side, d)
+            # per-iteration posterior column means (the north-star gate)
+            assert np.abs(got.mean(0) - ref.mean(0)).max() <= TOL_ITEMS
+        ro = orc.rmse(MOVIES)
+        assert abs(rm[0] - ro[0]) <= TOL_RMSE and abs(rm[1] - ro[1]) <= TOL_RMSE and rm[2] == ro[2], (i, rm, ro)
+        rou = orc.rmse(USERS)
+        assert abs(ru[0] - rou[0]) <= TOL_RMSE and abs(ru[1] - rou[1]) <= TOL_RMSE
+        assert abs(np.sqrt(ctx.get_stats(USERS)[3]) - np.sqrt(orc.stats(USERS)[3])) <= 1e-9
+    # final predict (quirk Q4: bpmf.cpp:225|242 re-applies the last sample)
+    orc.finish()
+    rm = ctx.predict(MOVIES, burnin)
+    assert abs(rm[1] - orc.rmse(MOVIES)[1]) <= TOL_RMSE
+    pa, pm = ctx.get_predictions(MOVIES)
+    pao, pmo = orc.pred(MOVIES)
+    np.testing.assert_allclose(pa, pao, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(pm, pmo, rtol=0, atol=1e-8)
+    ctx.close()
+    return worst
+
+
+def test_full_run_tiny_k10(gpu):
+    # BASELINE.json configs[0]: data/tiny, K=10; run_test.sh uses -i 9 -b 0
+    _run_both(gpu, 10, util.TINY_TRAIN, util.TINY_TEST, 9, 0, gpu.KERNEL_AUTO)
+    _run_both(gpu, 10, util.TINY_TRAIN, util.TINY_TEST, 20, 5, gpu.KERNEL_EXACT)
+
+
+@pytest.mark.parametrize("variant", ["exact", "dmma"])
+def test_full_run_movielens_shaped_k32(gpu, variant):
+    # ML-100K-shaped synthetic (943 x 1682, ~80k train / 20k test), K=32, 20 iterations, burn-in 5
+    v = gpu.KERNEL_EXACT if variant == "exact" else gpu.KERNEL_DMMA
+    train, test = util.synth_ratings(943, 1682, 110000, 2026, rank=10, skew=0.7, test_frac=0.2)
+    worst = _run_both(gpu, 32, train, test, 20, 5, v)
+    print("worst latent deviation over 20 iterations (%s): %.3e" % (variant, worst))
+
+
+def test_full_run_chembl_shaped_k32(gpu):
+    # skewed like ChEMBL: many near-empty rows, empty rows, one very hot column
+    train, test = util.synth_ratings(6000, 300, 14000, 77, rank=6, skew=1.1, empty_rows=800, heavy_col=3000)
+    _run_both(gpu, 32, train, test, 8, 3, gpu.KERNEL_AUTO)
+
+
+def test_range_and_peer_push(gpu):
+    # two "ranks" on one GPU: each samples half of the items and pushes into the other's replica
+    K = 32
+    train, test = util.synth_ratings(400, 300, 9000, 11)
+    orc = util.make_oracle(K, train, test)
+    a = util.make_gpu_from_oracle(orc, K)
+    b = util.make_gpu_from_oracle(orc, K)
+    _prime(orc, a, K, 5)
+    _prime(orc, b, K, 5)
+    n = orc.num(MOVIES)
+    half = n // 2 + 3
+    pa, pb = a.items_device_ptr(MOVIES), b.items_device_ptr(MOVIES)
+    for ctx, (lo, hi) in ((a, (0, half)), (b, (half, n))):
+        ctx.set_range(MOVIES, lo, hi)
+        ctx.set_peers(MOVIES, [pa, pb])
+    orc.set_iter(MOVIES, 2)
+    orc.sample_range(MOVIES, 0, n)
+    a.sample_items(MOVIES, 2, 2.0, gpu.KERNEL_DMMA)
+    b.sample_items(MOVIES, 2, 2.0, gpu.KERNEL_EXACT)
+    a.sync(); b.sync()
+    ref = orc.items(MOVIES)
+    for ctx in (a, b):
+        assert np.abs(ctx.get_items(MOVIES) - ref).max() <= TOL_ITEMS * np.abs(ref).max()
+    a.close(); b.close()
+
+
+def test_cholesky_failure_is_reported(gpu):
+    K = 32
+    train, test = util.synth_ratings(50, 40, 600, 1)
+    orc = util.make_oracle(K, train, test)
+    for v in (gpu.KERNEL_EXACT, gpu.KERNEL_DMMA):
+        ctx = util.make_gpu_from_oracle(orc, K)
+        ctx.set_hyper(MOVIES, np.zeros(K), -np.eye(K))   # not positive definite -> "Cholesky failed" (sample.cpp:308)
+        ctx.sample_items(MOVIES, 0, 2.0, v)
+        with pytest.raises(gpu.BpmfGpuError) as ei:
+            ctx.sync()
+        assert ei.value.code == 3 and "Cholesky failed" in str(ei.value)
+        ctx.close()
+
+
+def test_bind_external_items_storage(gpu):
+    torch = pytest.importorskip("torch")
+    K = 32
+    train, test = util.synth_ratings(100, 80, 1500, 4)
+    orc = util.make_oracle(K, train, test)
+    ctx = util.make_gpu_from_oracle(orc, K)
+    _prime(orc, ctx, K, 8)
+    ext = torch.zeros(orc.num(MOVIES), K, dtype=torch.float64, device="cuda")
+    ctx.bind_items(MOVIES, ext.data_ptr())
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    orc.set_iter(MOVIES, 1)
+    orc.sample_range(MOVIES, 0, orc.num(MOVIES))
+    ctx.sample_items(MOVIES, 1, 2.0, gpu.KERNEL_AUTO)
+    ctx.sync()
+    assert np.abs(ext.cpu().numpy() - orc.items(MOVIES)).max() <= TOL_ITEMS * 10
+    ctx.close()
