@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — latent-vector samples/sec of the BPMF Gibbs sweep pair (movies sweep + users sweep) at K=32.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME] [--exchange allgather|push]
+
+A "step" = movies.sample(users); users.sample(movies)  (c++/bpmf.cpp:184-185) over the whole synthetic rating matrix:
+hyper-parameter draw + fused per-item kernel + exchange (N > 1) + sweep reductions, per side.
+`value`   = (N_users + N_movies) * steps / time, CUDA events, max over ranks, latents resident in HBM.
+`e2e`     = the same through the C ABI with HOST-resident latent matrices (the reference's Sys::sample(Sys &other)
+            reads other.items() from host memory and leaves items() in host memory): per sweep the other side is
+            uploaded from pinned host memory and the fresh side downloaded, inside the timed region.
+`roofline`= fused item kernel: nnz * K * 8 algorithmic gather bytes per launch / its CUDA-event duration, against
+            MEASURED_PEAKS.json:hbm_gbs.
+`cpu_baseline` = the CPU oracle (restated reference, OpenMP over items like sample.cpp:352) on a bounded row sample of
+            the same matrix, on this box's host cores (N=1, rank 0 only).
+--impl reference times only that CPU path (the reference itself cannot be built: no Eigen3/Random123).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "latent-vector samples/sec (U+V sweep) at K=32"
+UNIT = "samples/s"
+DEFAULT_WORKLOAD = "synthA-1Mx1M-100Mnnz-K32"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.1] or [r for (_, r) in self.rows[-3:]]
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[6]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json:hbm_gbs"
+        except (KeyError, ValueError):
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle on a bounded sample of the same matrix
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_baseline(ratings, K, alpha, budget_s=12.0, threads=0, max_rows=None):
+    """Times the oracle's per-item loop (sample.cpp:352-372: OpenMP over items, schedule(guided)) on the first S user
+    rows and the first S movie columns of the workload, the other side's full-size latent matrix resident in host
+    memory, so every item does exactly the work it does in the full job. Returns samples/s and what was sampled."""
+    from oracle import oracle as o
+    ncores = o.lib().bpmf_oracle_max_threads() if threads <= 0 else threads
+    rng = np.random.Generator(np.random.PCG64(7))
+
+    def sub_model(side, S):
+        # users sample: rows [0,S) of R against all movies; movies sample: columns [0,S) of R against all users
+        n, n_other, ptr, idx, val = ratings.side(side)
+        S = min(S, n)
+        e = int(ptr[S])
+        own = np.repeat(np.arange(S, dtype=np.int32), np.diff(ptr[:S + 1]))
+        oth = np.asarray(idx[:e], np.int32)
+        v = np.asarray(val[:e], np.float64)
+        if side == 1:     # users are file rows
+            shape, rows, cols = (S, n_other), own, oth
+        else:
+            shape, rows, cols = (n_other, S), oth, own
+        m = o.Oracle(K, shape, rows, cols, v, shape, rows[:1], cols[:1], v[:1], alpha=alpha, burnin=0, nthreads=threads)
+        m.set_items(1 - side, rng.normal(0, 0.3, size=(m.num(1 - side), K)))
+        m.set_hyper(side, rng.normal(0, 0.1, size=K), np.eye(K) * 2.0)
+        m.set_iter(side, 3)
+        return m, S, e
+
+    def timed(S):
+        tot, items, nnz = 0.0, 0, 0
+        for side in (0, 1):
+            m, s, e = sub_model(side, S)
+            t0 = time.perf_counter()
+            m.sample_range(side, 0, s)
+            tot += time.perf_counter() - t0
+            items += s; nnz += e
+            del m
+        return tot, items, nnz
+
+    S = 4000
+    t, items, nnz = timed(S)                  # calibration pass (also warms the OpenMP team)
+    rate = items / t
+    S = int(max(S, min(rate * budget_s / 2, max_rows or 10**9, max(ratings.nrows, ratings.ncols))))
+    t, items, nnz = timed(S)
+    return {"value": items / t, "unit": UNIT, "cores": int(ncores), "kind": "port",
+            "sample": "first %d user rows + first %d movie columns of the workload (%d ratings), per-item loop of the "
+                      "restated reference (oracle/, OpenMP schedule(guided), %d threads), other side's full latent matrix "
+                      "in host memory; %.1f s of CPU time" % (min(S, ratings.nrows), min(S, ratings.ncols), nnz, ncores, t),
+            "seconds": t}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--exchange", default="allgather", choices=["allgather", "push"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "exact", "dmma"])
+    ap.add_argument("--alpha", type=float, default=2.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cache-dir", default="/dev/shm")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from bpmf_b200 import synthetic
+    nrows, ncols, mean_nnz, K, seed = synthetic.WORKLOADS[args.workload]
+    config = {"workload": args.workload, "users": nrows, "movies": ncols, "num_latent": K, "alpha": args.alpha,
+              "generator": "bpmf_b200/synthetic.py seed %d: Poisson(%g) ratings per user row, uniform distinct movies, "
+                           "planted rank-16 values" % (seed, mean_nnz),
+              "l2": "inputs larger than L2: per sweep %.0f MB of latent vectors gathered at random + %.0f MB of CSR"
+                    % (max(nrows, ncols) * K * 8 / 1e6, nrows * mean_nnz * 12 / 1e6)}
+
+    # ---------------------------------------------------------------- reference arm: CPU only, rank 0 only
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        ratings, K = synthetic.workload(args.workload, cache_dir=args.cache_dir, verbose=True)
+        config["nnz"] = int(ratings.nnz)
+        vals = []
+        per_step_budget = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
+        base = None
+        for i in range(args.warmup + args.steps):
+            base = cpu_baseline(ratings, K, args.alpha, budget_s=per_step_budget)
+            log("reference step %d: %.0f samples/s (%s)" % (i, base["value"], base["sample"][:60]))
+            if i >= args.warmup:
+                vals.append(base)
+        tot_items = sum(b["value"] * b["seconds"] for b in vals)
+        tot_s = sum(b["seconds"] for b in vals)
+        v = tot_items / tot_s
+        base["value"] = v
+        out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": 1e3 * (nrows + ncols) / v, "higher_is_better": True, "scaling": "strong",
+               "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "cpu_baseline": base,
+               "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+               "note": "restated reference (oracle/, kind=port): the reference needs Eigen3 + Random123, absent here; "
+                       "ms_per_step is extrapolated from the bounded sample to the whole matrix"}
+        print(json.dumps(out), flush=True)
+        return 0
+
+    # ---------------------------------------------------------------- B200 arm
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import bpmf_b200
+    from bpmf_b200.sampler import GibbsSampler, MOVIES, USERS
+
+    t_gen = time.time()
+    if world > 1:
+        if rank == 0:
+            ratings, K = synthetic.workload(args.workload, cache_dir=args.cache_dir, verbose=True)
+        dist.barrier(device_ids=[local_rank])
+        if rank != 0:
+            ratings, K = synthetic.workload(args.workload, cache_dir=args.cache_dir)
+    else:
+        ratings, K = synthetic.workload(args.workload, cache_dir=args.cache_dir, verbose=True)
+    config["nnz"] = int(ratings.nnz)
+    if rank == 0:
+        log("workload %s ready in %.1fs (nnz %d)" % (args.workload, time.time() - t_gen, ratings.nnz))
+    variant = {"auto": bpmf_b200.KERNEL_AUTO, "exact": bpmf_b200.KERNEL_EXACT, "dmma": bpmf_b200.KERNEL_DMMA}[args.variant]
+    gs = GibbsSampler(ratings, K, device=local_rank, alpha=args.alpha, variant=variant, exchange=args.exchange, with_test=True)
+    config["parallelism"] = "1 gpu" if world == 1 else "items of both factors split over %d gpus, %s exchange" % (world, gs.exchange)
+    n_samples = nrows + ncols
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    def timed_region(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident sweep pairs
+    for _ in range(args.warmup):
+        gs.step()
+    gs.ctx.sync()
+    gs.ctx.items_kernel_time()                       # drop the warm-up launches
+    launches0 = gs.ctx.launch_count()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.25)
+    t0 = time.time()
+    ms = timed_region(gs.step, args.steps)
+    t1 = time.time()
+    gs.ctx.sync()                                    # surfaces "Cholesky failed" etc.
+    launches = gs.ctx.launch_count() - launches0
+    k_ms, k_n = gs.ctx.items_kernel_time()
+    clk = clocks.stop(t0, t1) if clocks else None
+    value = n_samples * args.steps / (ms / 1e3)
+    rmse = gs.predict(burnin=args.warmup)[0]
+
+    # ---- roofline of the fused item kernel (both sides' launches averaged)
+    peak, peak_src = measured_peaks()
+    bytes_per_launch = ratings.nnz / world * K * 8.0          # nnz * K * 8 per sweep, this rank's share
+    k_avg_ms = k_ms / max(1, k_n)
+    achieved = bytes_per_launch / (k_avg_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "items_dmma32_kernel" if K == 32 and args.variant != "exact" else "items_exact_kernel",
+                "kernel_ms_avg": k_avg_ms, "kernel_launches_timed": k_n, "kernel_share_of_step": k_ms / ms,
+                "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src + " (of measured, burst)"}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get(args.workload, {}).get("dram_bytes_per_launch")
+        except ValueError:
+            pass
+
+    # ---- end to end with host-resident latent matrices
+    e2e = None
+    if not args.no_e2e:
+        host = [torch.empty(gs.num[s], K, dtype=torch.float64).pin_memory() for s in (MOVIES, USERS)]
+        for s in (MOVIES, USERS):
+            host[s].copy_(gs.items[s][: gs.num[s]])
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            for side in (MOVIES, USERS):
+                if world == 1:
+                    gs.ctx.sample_host(side, host[1 - side].data_ptr(), host[side].data_ptr(), args.alpha, variant)
+                else:
+                    gs.ctx.set_items_ptr(1 - side, host[1 - side].data_ptr())
+                    gs.sample(side)
+                    gs.ctx.get_items_ptr(side, host[side].data_ptr())
+
+        # iteration counters continue; the latents uploaded are the ones just downloaded, so the chain is unchanged
+        e2e_step()
+        e_steps = max(2, min(args.steps, 5))
+        e_ms = timed_region(e2e_step, e_steps)
+        hb = (gs.num[MOVIES] + gs.num[USERS]) * K * 8
+        e2e = {"value": n_samples * e_steps / (e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": hb * world,
+               "d2h_bytes_per_step": hb * world, "ms_per_step": e_ms / e_steps, "steps": e_steps,
+               "api": "bpmf_gpu_sample_host (C ABI) with pinned host latent matrices" if world == 1 else
+                      "bpmf_gpu_set_items / sample stages / bpmf_gpu_get_items per rank with pinned host latent matrices"}
+
+    total_launches = launches
+    if world > 1:
+        t = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        total_launches = int(t.item())
+
+    if rank == 0:
+        base = None
+        if world == 1 and not args.no_cpu_baseline:
+            base = cpu_baseline(ratings, K, args.alpha)
+            base.pop("seconds", None)
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f64", "data": "synthetic", "config": config, "roofline": roofline, "cpu_baseline": base, "e2e": e2e,
+               "gpu_launches": total_launches, "clocks": clk,
+               "rmse_after_run": rmse[0], "ratings_per_s": 2.0 * ratings.nnz * args.steps / (ms / 1e3)}
+        print(json.dumps(out), flush=True)
+    gs.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

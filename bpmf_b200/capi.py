@@ -32,11 +32,12 @@ SYMBOLS = {
     "bpmf_gpu_bind_items": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "bpmf_gpu_set_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "bpmf_gpu_items_device_ptr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
-    "bpmf_gpu_set_items": (C.c_int, [C.c_void_p, C.c_int, _f64p]),
-    "bpmf_gpu_get_items": (C.c_int, [C.c_void_p, C.c_int, _f64p]),
+    "bpmf_gpu_set_items": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "bpmf_gpu_get_items": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "bpmf_gpu_get_iter": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "bpmf_gpu_set_iter": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "bpmf_gpu_sample": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int]),
+    "bpmf_gpu_sample_host": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
     "bpmf_gpu_sample_hyper": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, _opt, _opt]),
     "bpmf_gpu_set_hyper": (C.c_int, [C.c_void_p, C.c_int, _f64p, _f64p]),
     "bpmf_gpu_get_hyper": (C.c_int, [C.c_void_p, C.c_int, _f64p, _f64p, _f64p]),
@@ -48,6 +49,7 @@ SYMBOLS = {
     "bpmf_gpu_get_predictions": (C.c_int, [C.c_void_p, C.c_int, _f64p, _f64p]),
     "bpmf_gpu_launch_count": (C.c_int64, [C.c_void_p]),
     "bpmf_gpu_last_items_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "bpmf_gpu_items_kernel_time": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "bpmf_gpu_debug_randn": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, _f64p]),
 }
 
@@ -142,11 +144,18 @@ class Context:
     def set_items(self, side, a):
         a = np.ascontiguousarray(a, np.float64)
         assert a.size == self.K * self.num[side]
-        self._ck(self.L.bpmf_gpu_set_items(self.h, side, a.reshape(-1)))
+        self._ck(self.L.bpmf_gpu_set_items(self.h, side, C.c_void_p(a.ctypes.data)))
+
+    def set_items_ptr(self, side, host_ptr):
+        """upload K * num doubles from a raw host address (e.g. a pinned torch tensor's data_ptr())"""
+        self._ck(self.L.bpmf_gpu_set_items(self.h, side, C.c_void_p(host_ptr)))
+
+    def get_items_ptr(self, side, host_ptr):
+        self._ck(self.L.bpmf_gpu_get_items(self.h, side, C.c_void_p(host_ptr)))
 
     def get_items(self, side):
         out = np.empty((self.num[side], self.K), np.float64)
-        self._ck(self.L.bpmf_gpu_get_items(self.h, side, out.reshape(-1)))
+        self._ck(self.L.bpmf_gpu_get_items(self.h, side, C.c_void_p(out.ctypes.data)))
         return out
 
     def get_iter(self, side):
@@ -158,6 +167,11 @@ class Context:
 
     # ---- hot path
     def sample(self, side, alpha=2.0, variant=KERNEL_AUTO): self._ck(self.L.bpmf_gpu_sample(self.h, side, alpha, variant))
+
+    def sample_host(self, side, host_other_ptr, host_items_ptr, alpha=2.0, variant=KERNEL_AUTO):
+        """Sys::sample(other) with host-resident items on both sides; arguments are raw host addresses (or None)."""
+        self._ck(self.L.bpmf_gpu_sample_host(self.h, side, alpha, variant, C.c_void_p(host_other_ptr),
+                                             C.c_void_p(host_items_ptr)))
 
     def sample_hyper(self, side, it, sum_=None, cov=None):
         s = None if sum_ is None else np.ascontiguousarray(sum_, np.float64)
@@ -201,6 +215,12 @@ class Context:
         ms = C.c_float()
         self._ck(self.L.bpmf_gpu_last_items_kernel_ms(self.h, C.byref(ms)))
         return ms.value
+
+    def items_kernel_time(self):
+        """(total ms, count) of the item kernels launched since the last call."""
+        t, n = C.c_double(), C.c_int()
+        self._ck(self.L.bpmf_gpu_items_kernel_time(self.h, C.byref(t), C.byref(n)))
+        return t.value, n.value
 
     def debug_randn(self, c, n):
         out = np.empty(n)

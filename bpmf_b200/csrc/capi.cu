@@ -110,8 +110,10 @@ int bpmf_gpu_create(bpmf_gpu_ctx **out, int device, int num_latent)
     if ((e = cudaMemset(ctx->d_err, 0, sizeof(unsigned long long))) != cudaSuccess) return bail(e);
     if ((e = cudaMallocHost(&ctx->h_err, sizeof(unsigned long long))) != cudaSuccess) return bail(e);
     if ((e = cudaMallocHost(&ctx->h_pinned, sizeof(double) * (KK + K + 8))) != cudaSuccess) return bail(e);
-    if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e);
-    if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e);
+    for (int i = 0; i < bpmf_gpu_ctx::EV_RING; ++i) {
+        if ((e = cudaEventCreate(&ctx->ev0[i])) != cudaSuccess) return bail(e);
+        if ((e = cudaEventCreate(&ctx->ev1[i])) != cudaSuccess) return bail(e);
+    }
     HyperScratch &h = ctx->hs;
     // expected consumption is 1.27 (K^2+K) + K/2 blocks; 2 (K^2+4K) + 64 is > 40 standard deviations above it
     h.nblk = 2 * (KK + 4 * K) + 64;
@@ -141,8 +143,10 @@ int bpmf_gpu_destroy(bpmf_gpu_ctx *ctx)
     dfree(ctx->d_err);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (int i = 0; i < bpmf_gpu_ctx::EV_RING; ++i) {
+        if (ctx->ev0[i]) cudaEventDestroy(ctx->ev0[i]);
+        if (ctx->ev1[i]) cudaEventDestroy(ctx->ev1[i]);
+    }
     delete ctx;
     return BPMF_GPU_OK;
 }
@@ -396,14 +400,15 @@ int bpmf_gpu_sample_items(bpmf_gpu_ctx *ctx, int side, uint32_t iter, double alp
     if (s.num_other != o.num) return fail(ctx, BPMF_GPU_EINVAL, "sides disagree on dimensions");
     CU(cudaSetDevice(ctx->device));
     const int v = pick_variant(ctx, kernel_variant);
-    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    const int slot = (int)(ctx->ev_count % bpmf_gpu_ctx::EV_RING);
+    CU(cudaEventRecord(ctx->ev0[slot], ctx->stream));
     if (v == BPMF_GPU_KERNEL_EXACT) CU(launch_items_exact(ctx, side, iter, alpha));
     else if (v == BPMF_GPU_KERNEL_DMMA) {
         if (ctx->K != 32) return fail(ctx, BPMF_GPU_EINVAL, "the DMMA kernel is built for num_latent == 32");
         CU(launch_items_dmma32(ctx, side, iter, alpha));
     } else return fail(ctx, BPMF_GPU_EINVAL, "unknown kernel variant");
-    CU(cudaEventRecord(ctx->ev1, ctx->stream));
-    ctx->have_item_timing = true;
+    CU(cudaEventRecord(ctx->ev1[slot], ctx->stream));
+    ctx->ev_count++;
     return BPMF_GPU_OK;
 }
 
@@ -482,11 +487,50 @@ int64_t bpmf_gpu_launch_count(const bpmf_gpu_ctx *ctx) { return ctx ? ctx->launc
 int bpmf_gpu_last_items_kernel_ms(bpmf_gpu_ctx *ctx, float *ms)
 {
     if (!ctx || !ms) return BPMF_GPU_EINVAL;
-    if (!ctx->have_item_timing) return fail(ctx, BPMF_GPU_EINVAL, "no item kernel has run yet");
+    if (!ctx->ev_count) return fail(ctx, BPMF_GPU_EINVAL, "no item kernel has run yet");
     CU(cudaSetDevice(ctx->device));
-    CU(cudaEventSynchronize(ctx->ev1));
-    CU(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    const int slot = (int)((ctx->ev_count - 1) % bpmf_gpu_ctx::EV_RING);
+    CU(cudaEventSynchronize(ctx->ev1[slot]));
+    CU(cudaEventElapsedTime(ms, ctx->ev0[slot], ctx->ev1[slot]));
     return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_items_kernel_time(bpmf_gpu_ctx *ctx, double *total_ms, int *count)
+{
+    if (!ctx || !total_ms || !count) return BPMF_GPU_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    long long first = ctx->ev_read;
+    if (ctx->ev_count - first > bpmf_gpu_ctx::EV_RING) first = ctx->ev_count - bpmf_gpu_ctx::EV_RING;  // older ones were overwritten
+    double tot = 0.0;
+    int n = 0;
+    for (long long i = first; i < ctx->ev_count; ++i) {
+        const int slot = (int)(i % bpmf_gpu_ctx::EV_RING);
+        float ms = 0.f;
+        CU(cudaEventSynchronize(ctx->ev1[slot]));
+        CU(cudaEventElapsedTime(&ms, ctx->ev0[slot], ctx->ev1[slot]));
+        tot += ms; ++n;
+    }
+    ctx->ev_read = ctx->ev_count;
+    *total_ms = tot; *count = n;
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_sample_host(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_variant, const double *host_other_items,
+                         double *host_items)
+{
+    if (!ctx || !side_ok(side)) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    SideDev &o = ctx->side[1 - side];
+    if (!s.loaded || !o.loaded) return fail(ctx, BPMF_GPU_EINVAL, "both sides must be loaded");
+    CU(cudaSetDevice(ctx->device));
+    const size_t K = (size_t)ctx->K;
+    if (host_other_items)   // other.items() lives in host memory in the reference (bpmf.h:193-194)
+        CU(cudaMemcpyAsync(o.items, host_other_items, sizeof(double) * K * o.num, cudaMemcpyHostToDevice, ctx->stream));
+    const int rc = bpmf_gpu_sample(ctx, side, alpha, kernel_variant);
+    if (rc) return rc;
+    if (host_items)
+        CU(cudaMemcpyAsync(host_items, s.items, sizeof(double) * K * s.num, cudaMemcpyDeviceToHost, ctx->stream));
+    return check_device_error(ctx);   // synchronises the stream
 }
 
 int bpmf_gpu_debug_randn(bpmf_gpu_ctx *ctx, uint32_t c, int n, double *host_out)

@@ -75,8 +75,11 @@ struct bpmf_gpu_ctx {
     unsigned long long *d_err = nullptr;  // device error word
     unsigned long long *h_err = nullptr;  // pinned host copy
     double *h_pinned = nullptr;           // small pinned staging (K*K + K + 8 doubles)
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool have_item_timing = false;
+    // ring of CUDA-event pairs around the item kernels (bench.py reads the per-launch durations from it)
+    static constexpr int EV_RING = 128;
+    cudaEvent_t ev0[EV_RING] = {}, ev1[EV_RING] = {};
+    long long ev_count = 0;      // item-kernel launches timed so far
+    long long ev_read = 0;       // launches already returned by bpmf_gpu_items_kernel_time
     long long launches = 0;
     std::string err;
 };

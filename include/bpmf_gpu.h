@@ -87,6 +87,14 @@ int bpmf_gpu_set_iter(bpmf_gpu_ctx *ctx, int side, int iter);
  * fused kernel, then sum / prod / norm reduced over ALL items and cov updated on the device. */
 int bpmf_gpu_sample(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_variant);
 
+/* The same call with HOST-resident latent matrices on both sides, which is literally the reference's
+ * Sys::sample(Sys &other): other.items() is read from host memory (host_other_items, K * num_other doubles,
+ * uploaded first; NULL = the device copy is current) and this side's fresh items() are written back to
+ * host_items (K * num_items doubles; NULL = leave them on the device). Pinned host memory makes both copies
+ * asynchronous to the host; the call returns after the download has finished. */
+int bpmf_gpu_sample_host(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_variant, const double *host_other_items,
+                         double *host_items);
+
 /* The stages of bpmf_gpu_sample, individually callable (multi-GPU hosts put the exchange of the
  * fresh columns between _sample_items and _reduce_stats; tests probe each stage). */
 /* rng_set_pos(iter); hp.sample(N, sum, cov)  (c++/sample.cpp:349-350, c++/bpmf.h:98-103,
@@ -113,6 +121,9 @@ int bpmf_gpu_get_predictions(bpmf_gpu_ctx *ctx, int side, double *pavg, double *
 int64_t bpmf_gpu_launch_count(const bpmf_gpu_ctx *ctx);
 /* milliseconds the last bpmf_gpu_sample_items kernel took, from CUDA events on the context's stream */
 int bpmf_gpu_last_items_kernel_ms(bpmf_gpu_ctx *ctx, float *ms);
+/* sum of the CUDA-event durations (ms) of the bpmf_gpu_sample_items kernels launched since the previous call
+ * of this function, and how many there were (at most the last 128 are kept). Synchronises on them. */
+int bpmf_gpu_items_kernel_time(bpmf_gpu_ctx *ctx, double *total_ms, int *count);
 /* device RNG probes for known-answer tests: n normals of the stream rng_set_pos(c) */
 int bpmf_gpu_debug_randn(bpmf_gpu_ctx *ctx, uint32_t c, int n, double *host_out);
 
