@@ -20,6 +20,7 @@ UNITS = [
     ("capi.cu", []),
     ("exact_kernels.cu", ["-fmad=false"]),
     ("fast_kernels.cu", []),
+    ("stream_kernel.cu", []),
 ]
 HEADERS = ["common.cuh", "rng.cuh", os.path.join(ROOT, "include", "bpmf_gpu.h")]
 

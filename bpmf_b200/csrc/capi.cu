@@ -72,7 +72,7 @@ int check_device_error(bpmf_gpu_ctx *ctx)
 
 int pick_variant(const bpmf_gpu_ctx *ctx, int v)
 {
-    if (v == BPMF_GPU_KERNEL_AUTO) return ctx->K == 32 ? BPMF_GPU_KERNEL_DMMA : BPMF_GPU_KERNEL_EXACT;
+    if (v == BPMF_GPU_KERNEL_AUTO) return ctx->K == 32 ? BPMF_GPU_KERNEL_STREAM : BPMF_GPU_KERNEL_EXACT;
     return v;
 }
 
@@ -406,6 +406,9 @@ int bpmf_gpu_sample_items(bpmf_gpu_ctx *ctx, int side, uint32_t iter, double alp
     else if (v == BPMF_GPU_KERNEL_DMMA) {
         if (ctx->K != 32) return fail(ctx, BPMF_GPU_EINVAL, "the DMMA kernel is built for num_latent == 32");
         CU(launch_items_dmma32(ctx, side, iter, alpha));
+    } else if (v == BPMF_GPU_KERNEL_STREAM) {
+        if (ctx->K != 32) return fail(ctx, BPMF_GPU_EINVAL, "the stream kernel is built for num_latent == 32");
+        CU(launch_items_stream32(ctx, side, iter, alpha));
     } else return fail(ctx, BPMF_GPU_EINVAL, "unknown kernel variant");
     CU(cudaEventRecord(ctx->ev1[slot], ctx->stream));
     ctx->ev_count++;

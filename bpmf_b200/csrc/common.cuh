@@ -95,4 +95,6 @@ cudaError_t launch_debug_randn(bpmf_gpu_ctx *c, uint32_t seed, int n, double *d_
 size_t exact_items_smem_bytes(int K);
 // fast_kernels.cu
 cudaError_t launch_items_dmma32(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha);
+// stream_kernel.cu
+cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha);
 }  // namespace bpmf

@@ -1,0 +1,375 @@
+// stream_kernel.cu — the fused per-item conditional update for num_latent == 32 on sm_100a, version 2
+// ("stream" variant): c++/sample.cpp:263-336 + 248-258 as ONE persistent kernel, one warp per item.
+//
+//   gather   Every warp owns a ring of NS shared-memory stages of SR latent rows (256 B each, padded to 288 B).
+//            The rows of the other factor named by the item's CSR entries are copied global -> shared with
+//            cp.async (LDGSTS.128, L1-bypassing, zero-fill for the ragged end), NS-1 stages ahead of the
+//            arithmetic and ACROSS item boundaries, so the HBM/L2 latency of the random 256-byte gathers is
+//            overlapped with the tensor-core work and with the Cholesky/solve tail of the previous item.
+//            Consecutive items are claimed CLAIM at a time from a global counter: their ratings are contiguous in
+//            the CSR arrays, so indices and values stream in coalesced 32-entry batches, one batch ahead.
+//   Gram     fp64 tensor cores: mma.sync.m8n8k4 (DMMA). Lane 4g+t holds f[a] = y_t[8a+g] of rating t of a group of
+//            four; f[I] is the A fragment and f[J] the B fragment of block (I,J), so ten DMMAs update the lower
+//            triangle of 8x8 blocks and every gathered value is read from shared memory exactly once. The 288-byte
+//            row stride makes those fragment loads bank-conflict free. rr += y * w is 4 DFMAs per group.
+//   tail     MM = LambdaF + alpha * G stays in the DMMA accumulator layout (20 registers per lane): blocked
+//            right-looking Cholesky, 8x8 diagonal blocks factored with warp shuffles, panel columns scaled in the
+//            same step, trailing blocks updated with DMMAs again. L is then scattered (packed, 4.1 KB) to shared
+//            memory for the two triangular solves in "lane j owns row j" form; K normals from Philox4x32-10 (rng.cuh).
+//
+// Roofline: nnz * 256 B gathered per sweep against HBM; 2.5 DMMA (1280 flop) per rating against the fp64
+// tensor pipe (37 TFLOP/s measured): at K = 32 the two are co-limiting (3.9 ms vs 3.5 ms for 100M ratings).
+#include "common.cuh"
+#include "rng.cuh"
+
+namespace bpmf {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int SR = 8;                       // ratings (latent rows) per stage
+constexpr int NS = 4;                       // stages per warp
+constexpr int ROWB = 288;                   // bytes per staged row: 256 + 32 pad
+constexpr int STAGE_BYTES = SR * ROWB + SR * 8 + 16;   // rows, weights, meta {n, item, first, last}
+constexpr int LPACK = 528;                  // packed lower triangle, column-major
+constexpr int WARP_BYTES = NS * STAGE_BYTES + LPACK * 8 + 32 * 8 + 32 * 8;   // + z + b
+constexpr int LFS = 34;                     // row stride (doubles) of LambdaF in shared memory
+constexpr int SHARED_BYTES = 32 * LFS * 8 + 32 * 8;
+constexpr int NW = 15;                      // warps per CTA, one CTA per SM
+constexpr int CLAIM = 16;                   // consecutive items claimed per atomic
+
+static_assert(STAGE_BYTES % 16 == 0 && WARP_BYTES % 16 == 0 && SHARED_BYTES % 16 == 0, "16-byte alignment for cp.async");
+static_assert(NW * WARP_BYTES + SHARED_BYTES <= 227 * 1024, "shared memory budget");
+
+struct StreamArgs {
+    int from, to;
+    uint32_t iter;
+    double alpha, mean_rating;
+    const int64_t *colptr;
+    const int32_t *rowidx;
+    const double *val;
+    const double *other;
+    double *items;
+    int npeers;
+    double *const *peers;
+    const double *mu, *LambdaF;
+    unsigned int *work_counter;
+    unsigned long long *err;
+};
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+// 16-byte global -> shared copy; src_bytes == 0 writes zeros without touching global memory
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ int64_t shfl64(int64_t v, int src)
+{
+    const int lo = __shfl_sync(FULL, (int)(v & 0xffffffffll), src);
+    const int hi = __shfl_sync(FULL, (int)(v >> 32), src);
+    return ((int64_t)hi << 32) | (uint32_t)lo;
+}
+
+constexpr __host__ __device__ int blk(int I, int J) { return I * (I + 1) / 2 + J; }
+__device__ __forceinline__ int col_off(int k) { return 32 * k - ((k * (k - 1)) >> 1); }
+
+// One block column KB of the right-looking blocked Cholesky on the accumulator layout (bench_micro/emulate_block_chol.py
+// is the lane-level model of this function).
+template <int KB>
+__device__ __forceinline__ void chol_block_column(double (&c)[10][2], double &myrs, bool &ok, int lane, int t)
+{
+    constexpr int D = blk(KB, KB);
+#pragma unroll 1
+    for (int k2 = 0; k2 < 4; ++k2) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int k = 2 * k2 + e;
+            const double p = __shfl_sync(FULL, c[D][e], 4 * k + k2);       // pivot: lane (g = k, t = k2), register e
+            if (!(p > 0.0)) ok = false;                                     // Eigen LLT: pivot <= 0 -> "Cholesky failed"
+            const double rs = rsqrt(p);
+            if (lane == 8 * KB + k) myrs = rs;
+            const bool own = (t == k2);
+#pragma unroll
+            for (int I = KB; I < 4; ++I)
+                if (own) c[blk(I, KB)][e] *= rs;                            // column k of L (diagonal entry becomes sqrt(p))
+            const double bl0 = __shfl_sync(FULL, c[D][e], 4 * (2 * t) + k2);       // L[2t][k]
+            const double bl1 = __shfl_sync(FULL, c[D][e], 4 * (2 * t + 1) + k2);   // L[2t+1][k]
+#pragma unroll
+            for (int I = KB; I < 4; ++I) {
+                const double a = __shfl_sync(FULL, c[blk(I, KB)][e], (lane & ~3) | k2);   // L[8I+g][k]
+                if (2 * t > k) c[blk(I, KB)][0] = fma(-a, bl0, c[blk(I, KB)][0]);
+                if (2 * t + 1 > k) c[blk(I, KB)][1] = fma(-a, bl1, c[blk(I, KB)][1]);
+            }
+        }
+    }
+    // trailing update A(I,J) -= L(I,KB) L(J,KB)^T for KB < J <= I on the tensor cores
+    if (KB < 3) {
+        double fr[4][2];
+#pragma unroll
+        for (int I = KB + 1; I < 4; ++I)
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                const int src = (lane & ~3) | (2 * kk + (t >> 1));
+                const double v0 = __shfl_sync(FULL, c[blk(I, KB)][0], src);
+                const double v1 = __shfl_sync(FULL, c[blk(I, KB)][1], src);
+                fr[I][kk] = (t & 1) ? v1 : v0;                              // L(I,KB)[g][4kk + t]
+            }
+#pragma unroll
+        for (int I = KB + 1; I < 4; ++I)
+#pragma unroll
+            for (int J = KB + 1; J <= I; ++J)
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) dmma884(c[blk(I, J)][0], c[blk(I, J)][1], -fr[I][kk], fr[J][kk]);
+    }
+}
+
+__global__ void __launch_bounds__(NW * 32, 1) items_stream32_kernel(StreamArgs p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    double *sLF = reinterpret_cast<double *>(smem_raw);            // LambdaF(i,k) at sLF[k * LFS + i]
+    double *srr0 = sLF + 32 * LFS;                                 // LambdaF * mu
+    unsigned char *wbase = smem_raw + SHARED_BYTES + (size_t)warp * WARP_BYTES;
+    double *Lp = reinterpret_cast<double *>(wbase + NS * STAGE_BYTES);
+    double *wz = Lp + LPACK;
+    double *wb = wz + 32;
+    const uint32_t wbase_s = (uint32_t)__cvta_generic_to_shared(wbase);
+
+    for (int e = tid; e < 1024; e += NW * 32) sLF[(e >> 5) * LFS + (e & 31)] = p.LambdaF[e];
+    __syncthreads();
+    if (tid < 32) {
+        double s = 0.0;
+        for (int j = 0; j < 32; ++j) s += sLF[j * LFS + tid] * p.mu[j];   // rr = LambdaF * hp.mu (sample.cpp:285)
+        srr0[tid] = s;
+    }
+    __syncthreads();
+
+    // ---------------- fetch-side state (warp-uniform unless noted) ----------------
+    int g_base = 0, g_n = 0, f_it = 0;
+    int64_t cp = 0;                       // per lane: colptr[g_base + lane]
+    int64_t f_pos = 0, f_end = 0, f_start = 0, g_end = 0, b_base = 0;
+    int32_t b_idx = 0, nb_idx = 0;        // per lane: index of stream position b_base + lane / b_base + 32 + lane
+    double b_w = 0.0, nb_w = 0.0;         // per lane: (val - mean_rating) * alpha of the same positions
+    bool f_done = false;
+
+    auto load_batch = [&](int64_t base, int32_t &idx, double &w) {
+        const int64_t q = base + lane;
+        idx = 0; w = 0.0;
+        if (q < g_end) {
+            idx = __ldg(p.rowidx + q);
+            w = (__ldg(p.val + q) - p.mean_rating) * p.alpha;
+        }
+    };
+    auto claim = [&]() {
+        int base = 0;
+        if (lane == 0) base = p.from + (int)atomicAdd(p.work_counter, (unsigned)CLAIM);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= p.to) { f_done = true; return; }
+        g_base = base;
+        g_n = min(CLAIM, p.to - base);
+        cp = (lane <= g_n) ? __ldg(p.colptr + base + lane) : 0;
+        f_it = 0;
+        f_start = f_pos = shfl64(cp, 0);
+        f_end = shfl64(cp, 1);
+        g_end = shfl64(cp, g_n);
+        b_base = f_pos;
+        load_batch(b_base, b_idx, b_w);
+        load_batch(b_base + 32, nb_idx, nb_w);
+    };
+    // fill ring slot `slot` with the next (at most SR) ratings of the stream; exactly one commit_group per call
+    auto issue_stage = [&](int slot) {
+        const uint32_t st = wbase_s + slot * STAGE_BYTES;
+        unsigned char *stg = wbase + slot * STAGE_BYTES;
+        if (f_done) {
+            if (lane == 0) *reinterpret_cast<int4 *>(stg + SR * ROWB + SR * 8) = make_int4(-1, 0, 0, 0);
+            cp_async_commit();
+            return;
+        }
+        if (f_pos >= b_base + 32) {       // rotate to the prefetched batch and start fetching the one after it
+            b_base += 32;
+            b_idx = nb_idx; b_w = nb_w;
+            load_batch(b_base + 32, nb_idx, nb_w);
+        }
+        const int off = (int)(f_pos - b_base);
+        const int n = (int)min((int64_t)SR, min(f_end - f_pos, b_base + 32 - f_pos));
+#pragma unroll
+        for (int i = 0; i < SR / 2; ++i) {
+            const int r = 2 * i + (lane >> 4);
+            const int j = __shfl_sync(FULL, b_idx, (off + r) & 31);
+            const bool valid = r < n;
+            const double *src = p.other + (valid ? (size_t)j * 32 : 0) + (lane & 15) * 2;
+            cp_async16(st + r * ROWB + (lane & 15) * 16, src, valid ? 16 : 0);
+        }
+        const double wv = __shfl_sync(FULL, b_w, (off + lane) & 31);
+        if (lane < SR) reinterpret_cast<double *>(stg + SR * ROWB)[lane] = (lane < n) ? wv : 0.0;
+        const int first = (f_pos == f_start), last = (f_pos + n == f_end);
+        if (lane == 0) *reinterpret_cast<int4 *>(stg + SR * ROWB + SR * 8) = make_int4(n, g_base + f_it, first, last);
+        cp_async_commit();
+        f_pos += n;
+        if (last) {
+            ++f_it;
+            if (f_it >= g_n) claim();
+            else { f_start = f_pos = f_end; f_end = shfl64(cp, f_it + 1); }
+        }
+    };
+
+    claim();
+#pragma unroll 1
+    for (int s = 0; s < NS; ++s) issue_stage(s);
+
+    double c[10][2];
+    double rrp[4];
+#pragma unroll
+    for (int b = 0; b < 10; ++b) { c[b][0] = 0.0; c[b][1] = 0.0; }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) rrp[a] = 0.0;
+
+    int h = 0;
+#pragma unroll 1
+    for (;;) {
+        cp_async_wait<NS - 1>();
+        __syncwarp();
+        unsigned char *stg = wbase + h * STAGE_BYTES;
+        const int4 meta = *reinterpret_cast<const int4 *>(stg + SR * ROWB + SR * 8);
+        if (meta.x < 0) break;
+        // ---------------- Gram + rhs of this stage (computeMuLambda, sample.cpp:251-257) ----------------
+        const int ngroups = (meta.x + 3) >> 2;
+#pragma unroll 1
+        for (int q = 0; q < ngroups; ++q) {
+            const unsigned char *row = stg + (4 * q + t) * ROWB + g * 8;
+            double f[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) f[a] = *reinterpret_cast<const double *>(row + a * 64);
+            const double w = reinterpret_cast<const double *>(stg + SR * ROWB)[4 * q + t];
+#pragma unroll
+            for (int I = 0; I < 4; ++I)
+#pragma unroll
+                for (int J = 0; J <= I; ++J) dmma884(c[blk(I, J)][0], c[blk(I, J)][1], f[I], f[J]);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) rrp[a] = fma(f[a], w, rrp[a]);
+        }
+        __syncwarp();                     // every lane is done reading slot h
+        issue_stage(h);                   // refill it: this prefetch overlaps the tail below
+        h = (h + 1 == NS) ? 0 : h + 1;
+        if (!meta.w) continue;            // more stages of this item to come
+
+        // ---------------- tail: one item's Gram is complete ----------------
+        const int idx = meta.y;
+        // the K normals of this item: rng_set_pos((idx+1)*K*(iter+1)) (sample.cpp:266)
+        warp_randn((uint32_t)(((long long)idx + 1) * 32ll * ((long long)p.iter + 1)), 32, wz);
+        // rr = LambdaF*mu + sum over the quad's four ratings-of-a-group
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            rrp[a] += __shfl_xor_sync(FULL, rrp[a], 1);
+            rrp[a] += __shfl_xor_sync(FULL, rrp[a], 2);
+        }
+        if (t == 0) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) wb[8 * a + g] = srr0[8 * a + g] + rrp[a];
+        }
+        // MM = LambdaF + alpha * G (sample.cpp:297-298), in place in the accumulator layout
+#pragma unroll
+        for (int I = 0; I < 4; ++I)
+#pragma unroll
+            for (int J = 0; J <= I; ++J)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    c[blk(I, J)][e] = fma(p.alpha, c[blk(I, J)][e], sLF[(8 * J + 2 * t + e) * LFS + 8 * I + g]);   // LambdaF(i,k), i >= k
+        // chol.compute(MM) (sample.cpp:306)
+        double myrs = 0.0;
+        bool ok = true;
+        chol_block_column<0>(c, myrs, ok, lane, t);
+        chol_block_column<1>(c, myrs, ok, lane, t);
+        chol_block_column<2>(c, myrs, ok, lane, t);
+        chol_block_column<3>(c, myrs, ok, lane, t);
+        // L -> shared memory, packed by columns: element (i,k), i >= k, at col_off(k) + i - k
+#pragma unroll
+        for (int I = 0; I < 4; ++I)
+#pragma unroll
+            for (int J = 0; J <= I; ++J)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int i = 8 * I + g, k = 8 * J + 2 * t + e;
+                    if (i >= k) Lp[col_off(k) + i - k] = c[blk(I, J)][e];
+                }
+        // reset the accumulators for the next item (its first stage may already be waiting)
+#pragma unroll
+        for (int b = 0; b < 10; ++b) { c[b][0] = 0.0; c[b][1] = 0.0; }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) rrp[a] = 0.0;
+        __syncwarp();
+        if (!ok) {   // THROWERROR("Cholesky failed") (sample.cpp:308): reported through the error word
+            if (lane == 0) atomicMax(p.err, ERR_CHOLESKY | (unsigned)idx);
+            continue;
+        }
+        // chol.matrixL().solveInPlace(rr); rr += nrandn(); chol.matrixU().solveInPlace(rr) (sample.cpp:321-323)
+        double bb = wb[lane];
+        const double z = wz[lane];
+        double yv = 0.0;
+#pragma unroll 4
+        for (int k = 0; k < 32; ++k) {
+            const double yk = __shfl_sync(FULL, bb * myrs, k);
+            if (lane == k) yv = yk;
+            const double l = (lane > k) ? Lp[col_off(k) + lane - k] : 0.0;
+            bb = fma(-l, yk, bb);
+        }
+        yv += z;
+        double xv = 0.0;
+        const int myoff = col_off(lane) - lane;
+#pragma unroll 4
+        for (int i = 31; i >= 0; --i) {
+            const double xi = __shfl_sync(FULL, yv * myrs, i);
+            if (lane == i) xv = xi;
+            const double l = (lane < i) ? Lp[myoff + i] : 0.0;
+            yv = fma(-l, xi, yv);
+        }
+        // items().col(idx) = rr (sample.cpp:324); push to the peer replicas (replaces send_item, :370)
+        p.items[(size_t)idx * 32 + lane] = xv;
+        for (int pr = 0; pr < p.npeers; ++pr) {
+            double *dst = p.peers[pr];
+            if (dst && dst != p.items) dst[(size_t)idx * 32 + lane] = xv;
+        }
+        __syncwarp();                     // wb / wz / Lp are free again
+    }
+    cp_async_wait<0>();
+}
+
+}  // namespace
+
+cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha)
+{
+    SideDev &s = c->side[side];
+    const SideDev &o = c->side[1 - side];
+    StreamArgs p;
+    p.from = s.from; p.to = s.to; p.iter = iter; p.alpha = alpha; p.mean_rating = s.mean_rating;
+    p.colptr = s.colptr; p.rowidx = s.rowidx; p.val = s.val;
+    p.other = o.items; p.items = s.items;
+    p.npeers = s.npeers; p.peers = s.peers_dev;
+    p.mu = s.hp.mu; p.LambdaF = s.hp.LambdaF;
+    p.work_counter = s.work_counter; p.err = c->d_err;
+    cudaError_t e = cudaMemsetAsync(s.work_counter, 0, sizeof(unsigned int), c->stream);
+    if (e != cudaSuccess) return e;
+    const size_t smem = (size_t)NW * WARP_BYTES + SHARED_BYTES;
+    e = cudaFuncSetAttribute(items_stream32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long n = (long long)s.to - s.from;
+    if (n < 1) return cudaSuccess;
+    long long grid = c->sm_count;                              // persistent: one CTA per SM
+    const long long need = (n + (long long)NW * CLAIM - 1) / ((long long)NW * CLAIM);
+    if (grid > need) grid = need;
+    items_stream32_kernel<<<(unsigned)grid, NW * 32, smem, c->stream>>>(p);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace bpmf

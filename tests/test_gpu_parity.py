@@ -97,12 +97,15 @@ CASES = [
 ]
 
 
+VARIANTS = {"exact": 1, "dmma": 2, "stream": 3}
+
+
 @pytest.mark.parametrize("K,nr,nc,nnz,kw", CASES)
-@pytest.mark.parametrize("variant", ["exact", "dmma"])
+@pytest.mark.parametrize("variant", ["exact", "dmma", "stream"])
 def test_item_update_one_sweep(gpu, K, nr, nc, nnz, kw, variant):
-    if variant == "dmma" and K != 32:
-        pytest.skip("DMMA kernel is K == 32")
-    v = gpu.KERNEL_EXACT if variant == "exact" else gpu.KERNEL_DMMA
+    if variant != "exact" and K != 32:
+        pytest.skip("the tensor-core kernels are K == 32")
+    v = VARIANTS[variant]
     tol = TOL_EXACT if variant == "exact" else TOL_ITEMS
     train, test = util.synth_ratings(nr, nc, nnz, 7 + K, **kw)
     orc = util.make_oracle(K, train, test)
@@ -176,10 +179,10 @@ def test_full_run_tiny_k10(gpu):
     _run_both(gpu, 10, util.TINY_TRAIN, util.TINY_TEST, 20, 5, gpu.KERNEL_EXACT)
 
 
-@pytest.mark.parametrize("variant", ["exact", "dmma"])
+@pytest.mark.parametrize("variant", ["exact", "dmma", "stream"])
 def test_full_run_movielens_shaped_k32(gpu, variant):
     # ML-100K-shaped synthetic (943 x 1682, ~80k train / 20k test), K=32, 20 iterations, burn-in 5
-    v = gpu.KERNEL_EXACT if variant == "exact" else gpu.KERNEL_DMMA
+    v = VARIANTS[variant]
     train, test = util.synth_ratings(943, 1682, 110000, 2026, rank=10, skew=0.7, test_frac=0.2)
     worst = _run_both(gpu, 32, train, test, 20, 5, v)
     print("worst latent deviation over 20 iterations (%s): %.3e" % (variant, worst))
@@ -208,7 +211,7 @@ def test_range_and_peer_push(gpu):
         ctx.set_peers(MOVIES, [pa, pb])
     orc.set_iter(MOVIES, 2)
     orc.sample_range(MOVIES, 0, n)
-    a.sample_items(MOVIES, 2, 2.0, gpu.KERNEL_DMMA)
+    a.sample_items(MOVIES, 2, 2.0, gpu.KERNEL_STREAM)
     b.sample_items(MOVIES, 2, 2.0, gpu.KERNEL_EXACT)
     a.sync(); b.sync()
     ref = orc.items(MOVIES)
@@ -221,7 +224,7 @@ def test_cholesky_failure_is_reported(gpu):
     K = 32
     train, test = util.synth_ratings(50, 40, 600, 1)
     orc = util.make_oracle(K, train, test)
-    for v in (gpu.KERNEL_EXACT, gpu.KERNEL_DMMA):
+    for v in (gpu.KERNEL_EXACT, gpu.KERNEL_DMMA, gpu.KERNEL_STREAM):
         ctx = util.make_gpu_from_oracle(orc, K)
         ctx.set_hyper(MOVIES, np.zeros(K), -np.eye(K))   # not positive definite -> "Cholesky failed" (sample.cpp:308)
         ctx.sample_items(MOVIES, 0, 2.0, v)
