@@ -22,24 +22,28 @@
 #include "common.cuh"
 #include "rng.cuh"
 
+#include <cstdlib>
+
 namespace bpmf {
 
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int SR = 8;                       // ratings (latent rows) per stage
-constexpr int NS = 4;                       // stages per warp
+constexpr int SR = 16;                      // ratings (latent rows) per stage: four groups of four
 constexpr int ROWB = 288;                   // bytes per staged row: 256 + 32 pad
-constexpr int STAGE_BYTES = SR * ROWB + SR * 8 + 16;   // rows, weights, meta {n, item, first, last}
+constexpr int W_OFF = SR * ROWB;            // weights (SR doubles)
+constexpr int META_OFF = W_OFF + SR * 8;    // int4 {n, item, first, last}
+constexpr int STAGE_BYTES = META_OFF + 16;
 constexpr int LPACK = 528;                  // packed lower triangle, column-major
-constexpr int WARP_BYTES = NS * STAGE_BYTES + LPACK * 8 + 32 * 8 + 32 * 8;   // + z + b
+// the tail re-uses the stage it has just consumed as scratch: L (packed) | or, before that, zy, zr, b
+constexpr int ZY_OFF = 0, ZR_OFF = 256, B_OFF = 512;
 constexpr int LFS = 34;                     // row stride (doubles) of LambdaF in shared memory
 constexpr int SHARED_BYTES = 32 * LFS * 8 + 32 * 8;
-constexpr int NW = 15;                      // warps per CTA, one CTA per SM
 constexpr int CLAIM = 16;                   // consecutive items claimed per atomic
-
-static_assert(STAGE_BYTES % 16 == 0 && WARP_BYTES % 16 == 0 && SHARED_BYTES % 16 == 0, "16-byte alignment for cp.async");
-static_assert(NW * WARP_BYTES + SHARED_BYTES <= 227 * 1024, "shared memory budget");
+// NS = stages per warp, NW = warps per CTA (one CTA per SM)
+template <int NS> constexpr __host__ __device__ int warp_bytes() { return NS * STAGE_BYTES; }
+static_assert(STAGE_BYTES % 16 == 0 && SHARED_BYTES % 16 == 0, "16-byte alignment for cp.async");
+static_assert(LPACK * 8 <= STAGE_BYTES && B_OFF + 256 <= STAGE_BYTES, "tail scratch must fit in one stage");
 
 struct StreamArgs {
     int from, to;
@@ -72,15 +76,8 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ int64_t shfl64(int64_t v, int src)
-{
-    const int lo = __shfl_sync(FULL, (int)(v & 0xffffffffll), src);
-    const int hi = __shfl_sync(FULL, (int)(v >> 32), src);
-    return ((int64_t)hi << 32) | (uint32_t)lo;
-}
-
 constexpr __host__ __device__ int blk(int I, int J) { return I * (I + 1) / 2 + J; }
-__device__ __forceinline__ int col_off(int k) { return 32 * k - ((k * (k - 1)) >> 1); }
+constexpr __host__ __device__ int col_off(int k) { return 32 * k - ((k * (k - 1)) / 2); }
 
 // One block column KB of the right-looking blocked Cholesky on the accumulator layout (bench_micro/emulate_block_chol.py
 // is the lane-level model of this function).
@@ -90,6 +87,8 @@ __device__ __forceinline__ void chol_block_column(double (&c)[10][2], double &my
     constexpr int D = blk(KB, KB);
 #pragma unroll 1
     for (int k2 = 0; k2 < 4; ++k2) {
+        const bool own = (t == k2);
+        const int qsrc = (lane & ~3) | k2;
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int k = 2 * k2 + e;
@@ -97,17 +96,19 @@ __device__ __forceinline__ void chol_block_column(double (&c)[10][2], double &my
             if (!(p > 0.0)) ok = false;                                     // Eigen LLT: pivot <= 0 -> "Cholesky failed"
             const double rs = rsqrt(p);
             if (lane == 8 * KB + k) myrs = rs;
-            const bool own = (t == k2);
+            const double sc = own ? rs : 1.0;
 #pragma unroll
-            for (int I = KB; I < 4; ++I)
-                if (own) c[blk(I, KB)][e] *= rs;                            // column k of L (diagonal entry becomes sqrt(p))
-            const double bl0 = __shfl_sync(FULL, c[D][e], 4 * (2 * t) + k2);       // L[2t][k]
-            const double bl1 = __shfl_sync(FULL, c[D][e], 4 * (2 * t + 1) + k2);   // L[2t+1][k]
+            for (int I = KB; I < 4; ++I) c[blk(I, KB)][e] *= sc;            // column k of L (diagonal entry becomes sqrt(p))
+            // L[2t][k], L[2t+1][k]; zeroed where this lane's column is not right of k, so the updates need no predicate
+            double bl0 = __shfl_sync(FULL, c[D][e], 4 * (2 * t) + k2);
+            double bl1 = __shfl_sync(FULL, c[D][e], 4 * (2 * t + 1) + k2);
+            bl0 = (2 * t > k) ? -bl0 : 0.0;
+            bl1 = (2 * t + 1 > k) ? -bl1 : 0.0;
 #pragma unroll
             for (int I = KB; I < 4; ++I) {
-                const double a = __shfl_sync(FULL, c[blk(I, KB)][e], (lane & ~3) | k2);   // L[8I+g][k]
-                if (2 * t > k) c[blk(I, KB)][0] = fma(-a, bl0, c[blk(I, KB)][0]);
-                if (2 * t + 1 > k) c[blk(I, KB)][1] = fma(-a, bl1, c[blk(I, KB)][1]);
+                const double a = __shfl_sync(FULL, c[blk(I, KB)][e], qsrc);   // L[8I+g][k]
+                c[blk(I, KB)][0] = fma(a, bl0, c[blk(I, KB)][0]);
+                c[blk(I, KB)][1] = fma(a, bl1, c[blk(I, KB)][1]);
             }
         }
     }
@@ -132,17 +133,31 @@ __device__ __forceinline__ void chol_block_column(double (&c)[10][2], double &my
     }
 }
 
+// one group of four staged ratings: 10 DMMAs on the lower triangle of blocks + the rhs
+__device__ __forceinline__ void gram_group(double (&c)[10][2], double (&rrp)[4], const unsigned char *row, const double *wq)
+{
+    double f[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) f[a] = *reinterpret_cast<const double *>(row + a * 64);
+    const double w = *wq;
+#pragma unroll
+    for (int I = 0; I < 4; ++I)
+#pragma unroll
+        for (int J = 0; J <= I; ++J) dmma884(c[blk(I, J)][0], c[blk(I, J)][1], f[I], f[J]);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) rrp[a] = fma(f[a], w, rrp[a]);
+}
+
+template <int NS, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) items_stream32_kernel(StreamArgs p)
 {
+    constexpr int WARP_BYTES = warp_bytes<NS>();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     double *sLF = reinterpret_cast<double *>(smem_raw);            // LambdaF(i,k) at sLF[k * LFS + i]
     double *srr0 = sLF + 32 * LFS;                                 // LambdaF * mu
     unsigned char *wbase = smem_raw + SHARED_BYTES + (size_t)warp * WARP_BYTES;
-    double *Lp = reinterpret_cast<double *>(wbase + NS * STAGE_BYTES);
-    double *wz = Lp + LPACK;
-    double *wb = wz + 32;
     const uint32_t wbase_s = (uint32_t)__cvta_generic_to_shared(wbase);
 
     for (int e = tid; e < 1024; e += NW * 32) sLF[(e >> 5) * LFS + (e & 31)] = p.LambdaF[e];
@@ -154,20 +169,24 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32_kernel(StreamArgs p
     }
     __syncthreads();
 
-    // ---------------- fetch-side state (warp-uniform unless noted) ----------------
+    // ---------------- fetch-side state (warp-uniform unless noted); positions are relative to the group's first rating
     int g_base = 0, g_n = 0, f_it = 0;
-    int64_t cp = 0;                       // per lane: colptr[g_base + lane]
-    int64_t f_pos = 0, f_end = 0, f_start = 0, g_end = 0, b_base = 0;
+    int cpr = 0;                          // per lane: colptr[g_base + lane] - colptr[g_base]
+    int f_pos = 0, f_end = 0, f_start = 0, g_end = 0, b_base = 0;
+    const int32_t *g_idx = p.rowidx;      // rowidx / val at the group's first rating
+    const double *g_val = p.val;
     int32_t b_idx = 0, nb_idx = 0;        // per lane: index of stream position b_base + lane / b_base + 32 + lane
     double b_w = 0.0, nb_w = 0.0;         // per lane: (val - mean_rating) * alpha of the same positions
     bool f_done = false;
+    const unsigned char *src_lane = reinterpret_cast<const unsigned char *>(p.other) + (lane & 15) * 16;   // this lane's 16 B of a row
+    const uint32_t dst_lane = wbase_s + (lane >> 4) * ROWB + (lane & 15) * 16;
 
-    auto load_batch = [&](int64_t base, int32_t &idx, double &w) {
-        const int64_t q = base + lane;
+    auto load_batch = [&](int base, int32_t &idx, double &w) {
+        const int q = base + lane;
         idx = 0; w = 0.0;
         if (q < g_end) {
-            idx = __ldg(p.rowidx + q);
-            w = (__ldg(p.val + q) - p.mean_rating) * p.alpha;
+            idx = __ldg(g_idx + q);
+            w = (__ldg(g_val + q) - p.mean_rating) * p.alpha;
         }
     };
     auto claim = [&]() {
@@ -177,49 +196,57 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32_kernel(StreamArgs p
         if (base >= p.to) { f_done = true; return; }
         g_base = base;
         g_n = min(CLAIM, p.to - base);
-        cp = (lane <= g_n) ? __ldg(p.colptr + base + lane) : 0;
+        const int64_t c0 = __ldg(p.colptr + base);
+        cpr = (lane <= g_n) ? (int)(__ldg(p.colptr + base + lane) - c0) : 0;
+        g_idx = p.rowidx + c0;
+        g_val = p.val + c0;
         f_it = 0;
-        f_start = f_pos = shfl64(cp, 0);
-        f_end = shfl64(cp, 1);
-        g_end = shfl64(cp, g_n);
-        b_base = f_pos;
-        load_batch(b_base, b_idx, b_w);
-        load_batch(b_base + 32, nb_idx, nb_w);
+        f_start = f_pos = 0;
+        f_end = __shfl_sync(FULL, cpr, 1);
+        g_end = __shfl_sync(FULL, cpr, g_n);
+        b_base = 0;
+        load_batch(0, b_idx, b_w);
+        load_batch(32, nb_idx, nb_w);
     };
-    // fill ring slot `slot` with the next (at most SR) ratings of the stream; exactly one commit_group per call
+    // fill ring slot `slot` with the next (at most SR) ratings of the current item; exactly one commit_group per call
     auto issue_stage = [&](int slot) {
-        const uint32_t st = wbase_s + slot * STAGE_BYTES;
+        const uint32_t st = dst_lane + slot * STAGE_BYTES;
         unsigned char *stg = wbase + slot * STAGE_BYTES;
         if (f_done) {
-            if (lane == 0) *reinterpret_cast<int4 *>(stg + SR * ROWB + SR * 8) = make_int4(-1, 0, 0, 0);
+            if (lane == 0) *reinterpret_cast<int4 *>(stg + META_OFF) = make_int4(-1, 0, 0, 0);
             cp_async_commit();
             return;
         }
-        if (f_pos >= b_base + 32) {       // rotate to the prefetched batch and start fetching the one after it
+        const int off = f_pos - b_base;                  // 0..31: the stage may run into the prefetched batch
+        const int n = min(SR, f_end - f_pos);
+#pragma unroll
+        for (int i = 0; i < SR / 2; ++i) {
+            const int q = off + 2 * i + (lane >> 4);
+            const int j0 = __shfl_sync(FULL, b_idx, q & 31);
+            const int j1 = __shfl_sync(FULL, nb_idx, q & 31);
+            const unsigned j = (unsigned)((q < 32) ? j0 : j1);
+            // rows past the item's end are zero-filled (src-size 0 reads nothing; j is still a valid row)
+            cp_async16(st + 2 * i * ROWB, src_lane + (size_t)j * 256, (2 * i + (lane >> 4) < n) ? 16 : 0);
+        }
+        {
+            const int q = off + lane;
+            const double w0 = __shfl_sync(FULL, b_w, q & 31);
+            const double w1 = __shfl_sync(FULL, nb_w, q & 31);
+            if (lane < SR) reinterpret_cast<double *>(stg + W_OFF)[lane] = (lane < n) ? ((q < 32) ? w0 : w1) : 0.0;
+        }
+        const int last = (f_pos + n == f_end);
+        if (lane == 0) *reinterpret_cast<int4 *>(stg + META_OFF) = make_int4(n, g_base + f_it, f_pos == f_start, last);
+        cp_async_commit();
+        f_pos += n;
+        if (f_pos - b_base >= 32) {       // rotate to the prefetched batch and start fetching the one after it
             b_base += 32;
             b_idx = nb_idx; b_w = nb_w;
             load_batch(b_base + 32, nb_idx, nb_w);
         }
-        const int off = (int)(f_pos - b_base);
-        const int n = (int)min((int64_t)SR, min(f_end - f_pos, b_base + 32 - f_pos));
-#pragma unroll
-        for (int i = 0; i < SR / 2; ++i) {
-            const int r = 2 * i + (lane >> 4);
-            const int j = __shfl_sync(FULL, b_idx, (off + r) & 31);
-            const bool valid = r < n;
-            const double *src = p.other + (valid ? (size_t)j * 32 : 0) + (lane & 15) * 2;
-            cp_async16(st + r * ROWB + (lane & 15) * 16, src, valid ? 16 : 0);
-        }
-        const double wv = __shfl_sync(FULL, b_w, (off + lane) & 31);
-        if (lane < SR) reinterpret_cast<double *>(stg + SR * ROWB)[lane] = (lane < n) ? wv : 0.0;
-        const int first = (f_pos == f_start), last = (f_pos + n == f_end);
-        if (lane == 0) *reinterpret_cast<int4 *>(stg + SR * ROWB + SR * 8) = make_int4(n, g_base + f_it, first, last);
-        cp_async_commit();
-        f_pos += n;
         if (last) {
             ++f_it;
             if (f_it >= g_n) claim();
-            else { f_start = f_pos = f_end; f_end = shfl64(cp, f_it + 1); }
+            else { f_start = f_end; f_end = __shfl_sync(FULL, cpr, f_it + 1); }
         }
     };
 
@@ -240,33 +267,41 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32_kernel(StreamArgs p
         cp_async_wait<NS - 1>();
         __syncwarp();
         unsigned char *stg = wbase + h * STAGE_BYTES;
-        const int4 meta = *reinterpret_cast<const int4 *>(stg + SR * ROWB + SR * 8);
+        const int4 meta = *reinterpret_cast<const int4 *>(stg + META_OFF);
         if (meta.x < 0) break;
         // ---------------- Gram + rhs of this stage (computeMuLambda, sample.cpp:251-257) ----------------
-        const int ngroups = (meta.x + 3) >> 2;
-#pragma unroll 1
-        for (int q = 0; q < ngroups; ++q) {
-            const unsigned char *row = stg + (4 * q + t) * ROWB + g * 8;
-            double f[4];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) f[a] = *reinterpret_cast<const double *>(row + a * 64);
-            const double w = reinterpret_cast<const double *>(stg + SR * ROWB)[4 * q + t];
-#pragma unroll
-            for (int I = 0; I < 4; ++I)
-#pragma unroll
-                for (int J = 0; J <= I; ++J) dmma884(c[blk(I, J)][0], c[blk(I, J)][1], f[I], f[J]);
-#pragma unroll
-            for (int a = 0; a < 4; ++a) rrp[a] = fma(f[a], w, rrp[a]);
+        {
+            const unsigned char *row = stg + t * ROWB + g * 8;
+            const double *wq = reinterpret_cast<const double *>(stg + W_OFF) + t;
+            if (meta.x > 0) gram_group(c, rrp, row, wq);
+            if (meta.x > 4) gram_group(c, rrp, row + 4 * ROWB, wq + 4);
+            if (meta.x > 8) gram_group(c, rrp, row + 8 * ROWB, wq + 8);
+            if (meta.x > 12) gram_group(c, rrp, row + 12 * ROWB, wq + 12);
         }
         __syncwarp();                     // every lane is done reading slot h
-        issue_stage(h);                   // refill it: this prefetch overlaps the tail below
-        h = (h + 1 == NS) ? 0 : h + 1;
-        if (!meta.w) continue;            // more stages of this item to come
-
-        // ---------------- tail: one item's Gram is complete ----------------
+        if (!meta.w) {                    // more stages of this item to come: refill the slot and go on
+            issue_stage(h);
+            h = (h + 1 == NS) ? 0 : h + 1;
+            continue;
+        }
+        // ---------------- tail: one item's Gram is complete; slot h is its scratch until the refill at the end ---------
         const int idx = meta.y;
-        // the K normals of this item: rng_set_pos((idx+1)*K*(iter+1)) (sample.cpp:266)
-        warp_randn((uint32_t)(((long long)idx + 1) * 32ll * ((long long)p.iter + 1)), 32, wz);
+        double *zy = reinterpret_cast<double *>(stg + ZY_OFF), *zr = reinterpret_cast<double *>(stg + ZR_OFF);
+        double *wb = reinterpret_cast<double *>(stg + B_OFF), *Lp = reinterpret_cast<double *>(stg);
+        // the K normals of this item: rng_set_pos((idx+1)*K*(iter+1)) (sample.cpp:266). Accepted polar attempts are numbered
+        // by ballot; lane n then finishes normal n (one log / sqrt / divide per lane instead of one per attempt).
+        {
+            const uint32_t seed = (uint32_t)(((long long)idx + 1) * 32ll * ((long long)p.iter + 1));
+            int have = 0;
+            for (uint32_t base = 0; have < 32; base += 32) {
+                const U4 bk = stream_block(seed, base + lane);
+                const Polar pa = polar_attempt(bk.v[3], bk.v[2], bk.v[1], bk.v[0]);
+                const unsigned m = __ballot_sync(FULL, pa.ok);
+                const int n = have + __popc(m & ((1u << lane) - 1u));
+                if (pa.ok && n < 32) { zy[n] = pa.y; zr[n] = pa.r2; }
+                have += __popc(m);
+            }
+        }
         // rr = LambdaF*mu + sum over the quad's four ratings-of-a-group
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
@@ -277,6 +312,9 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32_kernel(StreamArgs p
 #pragma unroll
             for (int a = 0; a < 4; ++a) wb[8 * a + g] = srr0[8 * a + g] + rrp[a];
         }
+        __syncwarp();
+        const double z = __dmul_rn(zy[lane], polar_mult(zr[lane]));
+        double bb = wb[lane];
         // MM = LambdaF + alpha * G (sample.cpp:297-298), in place in the accumulator layout
 #pragma unroll
         for (int I = 0; I < 4; ++I)
@@ -292,56 +330,75 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32_kernel(StreamArgs p
         chol_block_column<1>(c, myrs, ok, lane, t);
         chol_block_column<2>(c, myrs, ok, lane, t);
         chol_block_column<3>(c, myrs, ok, lane, t);
+        __syncwarp();                     // zy / zr / wb have been read by everyone: L may overwrite them
         // L -> shared memory, packed by columns: element (i,k), i >= k, at col_off(k) + i - k
+        {
+            double *lq = Lp + g - 2 * t;                    // + col_off(k) + 8 (I - J) - e per element
 #pragma unroll
-        for (int I = 0; I < 4; ++I)
+            for (int I = 0; I < 4; ++I)
 #pragma unroll
-            for (int J = 0; J <= I; ++J)
+                for (int J = 0; J <= I; ++J)
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int i = 8 * I + g, k = 8 * J + 2 * t + e;
-                    if (i >= k) Lp[col_off(k) + i - k] = c[blk(I, J)][e];
-                }
-        // reset the accumulators for the next item (its first stage may already be waiting)
+                    for (int e = 0; e < 2; ++e) {
+                        const int k = 8 * J + 2 * t + e;
+                        if (I > J || g >= 2 * t + e) lq[(32 * k - ((k * (k - 1)) >> 1)) + 8 * (I - J) - e] = c[blk(I, J)][e];
+                    }
+        }
+        // reset the accumulators for the next item
 #pragma unroll
         for (int b = 0; b < 10; ++b) { c[b][0] = 0.0; c[b][1] = 0.0; }
 #pragma unroll
         for (int a = 0; a < 4; ++a) rrp[a] = 0.0;
         __syncwarp();
-        if (!ok) {   // THROWERROR("Cholesky failed") (sample.cpp:308): reported through the error word
-            if (lane == 0) atomicMax(p.err, ERR_CHOLESKY | (unsigned)idx);
-            continue;
+        if (ok) {
+            // chol.matrixL().solveInPlace(rr); rr += nrandn(); chol.matrixU().solveInPlace(rr) (sample.cpp:321-323):
+            // lane j owns row j; one broadcast per step. Lanes that are already solved are simply not updated.
+            {
+                const double *lf = Lp + lane;              // element (lane, k) at lf[col_off(k) - k]
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    const double yk = __shfl_sync(FULL, bb * myrs, k);
+                    if (lane > k) bb = fma(-lf[col_off(k) - k], yk, bb);
+                }
+            }
+            double yv = fma(bb, myrs, z);                  // y + z
+            {
+                const double *lb = Lp + (32 * lane - ((lane * (lane - 1)) >> 1)) - lane;   // element (i, lane) at lb[i]
+#pragma unroll
+                for (int i = 31; i >= 0; --i) {
+                    const double xi = __shfl_sync(FULL, yv * myrs, i);
+                    if (lane < i) yv = fma(-lb[i], xi, yv);
+                }
+            }
+            const double xv = yv * myrs;
+            // items().col(idx) = rr (sample.cpp:324); push to the peer replicas (replaces send_item, :370)
+            p.items[(size_t)idx * 32 + lane] = xv;
+            for (int pr = 0; pr < p.npeers; ++pr) {
+                double *dst = p.peers[pr];
+                if (dst && dst != p.items) dst[(size_t)idx * 32 + lane] = xv;
+            }
+        } else if (lane == 0) {           // THROWERROR("Cholesky failed") (sample.cpp:308): reported through the error word
+            atomicMax(p.err, ERR_CHOLESKY | (unsigned)idx);
         }
-        // chol.matrixL().solveInPlace(rr); rr += nrandn(); chol.matrixU().solveInPlace(rr) (sample.cpp:321-323)
-        double bb = wb[lane];
-        const double z = wz[lane];
-        double yv = 0.0;
-#pragma unroll 4
-        for (int k = 0; k < 32; ++k) {
-            const double yk = __shfl_sync(FULL, bb * myrs, k);
-            if (lane == k) yv = yk;
-            const double l = (lane > k) ? Lp[col_off(k) + lane - k] : 0.0;
-            bb = fma(-l, yk, bb);
-        }
-        yv += z;
-        double xv = 0.0;
-        const int myoff = col_off(lane) - lane;
-#pragma unroll 4
-        for (int i = 31; i >= 0; --i) {
-            const double xi = __shfl_sync(FULL, yv * myrs, i);
-            if (lane == i) xv = xi;
-            const double l = (lane < i) ? Lp[myoff + i] : 0.0;
-            yv = fma(-l, xi, yv);
-        }
-        // items().col(idx) = rr (sample.cpp:324); push to the peer replicas (replaces send_item, :370)
-        p.items[(size_t)idx * 32 + lane] = xv;
-        for (int pr = 0; pr < p.npeers; ++pr) {
-            double *dst = p.peers[pr];
-            if (dst && dst != p.items) dst[(size_t)idx * 32 + lane] = xv;
-        }
-        __syncwarp();                     // wb / wz / Lp are free again
+        __syncwarp();                     // the scratch is free again
+        issue_stage(h);
+        h = (h + 1 == NS) ? 0 : h + 1;
     }
     cp_async_wait<0>();
+}
+
+template <int NS, int NW>
+cudaError_t launch_cfg(bpmf_gpu_ctx *c, const StreamArgs &p, long long n)
+{
+    constexpr size_t smem = (size_t)NW * warp_bytes<NS>() + SHARED_BYTES;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    cudaError_t e = cudaFuncSetAttribute(items_stream32_kernel<NS, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    long long grid = c->sm_count;                              // persistent: one CTA per SM
+    const long long need = (n + (long long)NW * CLAIM - 1) / ((long long)NW * CLAIM);
+    if (grid > need) grid = need;
+    items_stream32_kernel<NS, NW><<<(unsigned)grid, NW * 32, smem, c->stream>>>(p);
+    return cudaGetLastError();
 }
 
 }  // namespace
@@ -359,17 +416,18 @@ cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, doub
     p.work_counter = s.work_counter; p.err = c->d_err;
     cudaError_t e = cudaMemsetAsync(s.work_counter, 0, sizeof(unsigned int), c->stream);
     if (e != cudaSuccess) return e;
-    const size_t smem = (size_t)NW * WARP_BYTES + SHARED_BYTES;
-    e = cudaFuncSetAttribute(items_stream32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     const long long n = (long long)s.to - s.from;
     if (n < 1) return cudaSuccess;
-    long long grid = c->sm_count;                              // persistent: one CTA per SM
-    const long long need = (n + (long long)NW * CLAIM - 1) / ((long long)NW * CLAIM);
-    if (grid > need) grid = need;
-    items_stream32_kernel<<<(unsigned)grid, NW * 32, smem, c->stream>>>(p);
+    // tuning knob (bench only): BPMF_STREAM_CFG = "<stages><warps>" e.g. "315"; default 3 stages x 15 warps
+    static const int cfg = [] { const char *v = getenv("BPMF_STREAM_CFG"); return v ? atoi(v) : 315; }();
+    switch (cfg) {
+    case 216: e = launch_cfg<2, 16>(c, p, n); break;
+    case 411: e = launch_cfg<4, 11>(c, p, n); break;
+    case 314: e = launch_cfg<3, 14>(c, p, n); break;
+    default: e = launch_cfg<3, 15>(c, p, n); break;
+    }
     c->launches++;
-    return cudaGetLastError();
+    return e;
 }
 
 }  // namespace bpmf
