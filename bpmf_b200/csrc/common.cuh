@@ -97,4 +97,5 @@ size_t exact_items_smem_bytes(int K);
 cudaError_t launch_items_dmma32(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha);
 // stream_kernel.cu
 cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha);
+cudaError_t launch_stats_partial32(bpmf_gpu_ctx *c, int side);
 }  // namespace bpmf

@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(256) stats_partial_kernel(const double *__rest
     }
 }
 
-__global__ void __launch_bounds__(256) stats_final_kernel(const double *__restrict__ partials, int nblocks, int N, int K, double *sum,
+__global__ void __launch_bounds__(1024) stats_final_kernel(const double *__restrict__ partials, int nblocks, int N, int K, double *sum,
                                                            double *prod, double *cov, double *norm)
 {
     const int KK = K * K, W = KK + K + 1;
@@ -542,7 +542,11 @@ cudaError_t launch_stats(bpmf_gpu_ctx *c, int side)
     const size_t smem = sizeof(double) * 32 * K;
     const int nb = STATS_BLOCKS;
 #define BPMF_STATS_CASE(NE) stats_partial_kernel<NE><<<nb, 256, smem, c->stream>>>(s.items, s.num, K, s.partials)
-    if (ne <= 1) BPMF_STATS_CASE(1);
+    if (K == 32) {   // tensor-core version, same partial layout (stream_kernel.cu)
+        cudaError_t e32 = launch_stats_partial32(c, side);
+        if (e32 != cudaSuccess) return e32;
+        c->launches--;   // counted once below
+    } else if (ne <= 1) BPMF_STATS_CASE(1);
     else if (ne <= 2) BPMF_STATS_CASE(2);
     else if (ne <= 4) BPMF_STATS_CASE(4);
     else if (ne <= 8) BPMF_STATS_CASE(8);
@@ -554,7 +558,7 @@ cudaError_t launch_stats(bpmf_gpu_ctx *c, int side)
     c->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    stats_final_kernel<<<1, 256, 0, c->stream>>>(s.partials, nb, s.num, K, s.sum, s.prod, s.cov, s.norm);
+    stats_final_kernel<<<1, 1024, 0, c->stream>>>(s.partials, nb, s.num, K, s.sum, s.prod, s.cov, s.norm);
     c->launches++;
     return cudaGetLastError();
 }

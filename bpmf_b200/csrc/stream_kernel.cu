@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32_kernel(StreamArgs p
     const int32_t *g_idx = p.rowidx;      // rowidx / val at the group's first rating
     const double *g_val = p.val;
     int32_t b_idx = 0, nb_idx = 0;        // per lane: index of stream position b_base + lane / b_base + 32 + lane
-    double b_w = 0.0, nb_w = 0.0;         // per lane: (val - mean_rating) * alpha of the same positions
+    double b_w = 0.0, nb_w = 0.0;         // per lane: the rating values of the same positions (used long after the load)
     bool f_done = false;
     const unsigned char *src_lane = reinterpret_cast<const unsigned char *>(p.other) + (lane & 15) * 16;   // this lane's 16 B of a row
     const uint32_t dst_lane = wbase_s + (lane >> 4) * ROWB + (lane & 15) * 16;
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32_kernel(StreamArgs p
         idx = 0; w = 0.0;
         if (q < g_end) {
             idx = __ldg(g_idx + q);
-            w = (__ldg(g_val + q) - p.mean_rating) * p.alpha;
+            w = __ldg(g_val + q);         // raw: any arithmetic here would wait for the load right away
         }
     };
     auto claim = [&]() {
@@ -232,7 +232,8 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32_kernel(StreamArgs p
             const int q = off + lane;
             const double w0 = __shfl_sync(FULL, b_w, q & 31);
             const double w1 = __shfl_sync(FULL, nb_w, q & 31);
-            if (lane < SR) reinterpret_cast<double *>(stg + W_OFF)[lane] = (lane < n) ? ((q < 32) ? w0 : w1) : 0.0;
+            // rr weight (v - mean_rating) * alpha (sample.cpp:255)
+            if (lane < SR) reinterpret_cast<double *>(stg + W_OFF)[lane] = (lane < n) ? (((q < 32) ? w0 : w1) - p.mean_rating) * p.alpha : 0.0;
         }
         const int last = (f_pos + n == f_end);
         if (lane == 0) *reinterpret_cast<int4 *>(stg + META_OFF) = make_int4(n, g_base + f_it, f_pos == f_start, last);
@@ -401,7 +402,90 @@ cudaError_t launch_cfg(bpmf_gpu_ctx *c, const StreamArgs &p, long long n)
     return cudaGetLastError();
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Sweep reductions for K = 32 (sample.cpp:359-362,379-381): sum of x x^T on the fp64 tensor cores, sum of x, and
+// norm = trace. Fixed decomposition (STATS_BLOCKS x 8 warps, contiguous item chunks) and fixed summation order, so
+// the result does not depend on how items were scheduled in the sweep, nor on the number of GPUs.
+// Writes the same per-block partial layout as stats_partial_kernel (exact_kernels.cu): prod[K*K] | sum[K] | norm.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SW = 8;   // warps per stats block
+
+__global__ void __launch_bounds__(SW * 32) stats_partial32_kernel(const double *__restrict__ items, int N, double *__restrict__ partials)
+{
+    __shared__ double sp[SW][10 * 64 + 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const long long nw = (long long)gridDim.x * SW, w = (long long)blockIdx.x * SW + warp;
+    long long chunk = (N + nw - 1) / nw;
+    chunk = (chunk + 3) & ~3ll;
+    const long long i0 = min((long long)N, w * chunk), i1 = min((long long)N, i0 + chunk);
+    double c[10][2], sx[4];
+#pragma unroll
+    for (int b = 0; b < 10; ++b) { c[b][0] = 0.0; c[b][1] = 0.0; }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) sx[a] = 0.0;
+    for (long long i = i0; i < i1; i += 4) {
+        double f[4];
+        const bool valid = i + t < i1;
+        const double *row = items + (size_t)(i + t) * 32 + g;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) f[a] = valid ? __ldg(row + 8 * a) : 0.0;
+#pragma unroll
+        for (int I = 0; I < 4; ++I)
+#pragma unroll
+            for (int J = 0; J <= I; ++J) dmma884(c[blk(I, J)][0], c[blk(I, J)][1], f[I], f[J]);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) sx[a] += f[a];
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        sx[a] += __shfl_xor_sync(FULL, sx[a], 1);
+        sx[a] += __shfl_xor_sync(FULL, sx[a], 2);
+    }
+#pragma unroll
+    for (int b = 0; b < 10; ++b) {
+        sp[warp][b * 64 + g * 8 + 2 * t] = c[b][0];        // block b, element (g, 2t + e)
+        sp[warp][b * 64 + g * 8 + 2 * t + 1] = c[b][1];
+    }
+    if (t == 0) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) sp[warp][640 + 8 * a + g] = sx[a];
+    }
+    __syncthreads();
+    double *out = partials + (size_t)blockIdx.x * (1024 + 32 + 1);
+    for (int e = tid; e < 1024; e += SW * 32) {
+        int i = e & 31, k = e >> 5;                          // prod(i,k), column-major
+        if (i < k) { const int x = i; i = k; k = x; }        // mirror of the lower triangle
+        const int I = i >> 3, J = k >> 3;
+        const int off = blk(I, J) * 64 + (i & 7) * 8 + (k & 7);
+        double acc = 0.0;
+#pragma unroll
+        for (int ww = 0; ww < SW; ++ww) acc += sp[ww][off];
+        out[e] = acc;
+    }
+    if (tid < 32) {
+        double acc = 0.0;
+#pragma unroll
+        for (int ww = 0; ww < SW; ++ww) acc += sp[ww][640 + tid];
+        out[1024 + tid] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) {   // norm = sum of squared norms = trace of the outer-product sum
+        double nn = 0.0;
+        for (int d = 0; d < 32; ++d) nn += out[d * 33];
+        out[1024 + 32] = nn;
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_stats_partial32(bpmf_gpu_ctx *c, int side)
+{
+    SideDev &s = c->side[side];
+    stats_partial32_kernel<<<STATS_BLOCKS, SW * 32, 0, c->stream>>>(s.items, s.num, s.partials);
+    c->launches++;
+    return cudaGetLastError();
+}
 
 cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha)
 {
@@ -418,13 +502,13 @@ cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, doub
     if (e != cudaSuccess) return e;
     const long long n = (long long)s.to - s.from;
     if (n < 1) return cudaSuccess;
-    // tuning knob (bench only): BPMF_STREAM_CFG = "<stages><warps>" e.g. "315"; default 3 stages x 15 warps
-    static const int cfg = [] { const char *v = getenv("BPMF_STREAM_CFG"); return v ? atoi(v) : 315; }();
+    // tuning knob (bench only): BPMF_STREAM_CFG = "<stages><warps>" e.g. "216"; default 2 stages x 16 warps
+    static const int cfg = [] { const char *v = getenv("BPMF_STREAM_CFG"); return v ? atoi(v) : 216; }();
     switch (cfg) {
-    case 216: e = launch_cfg<2, 16>(c, p, n); break;
-    case 411: e = launch_cfg<4, 11>(c, p, n); break;
-    case 314: e = launch_cfg<3, 14>(c, p, n); break;
-    default: e = launch_cfg<3, 15>(c, p, n); break;
+    case 315: e = launch_cfg<3, 15>(c, p, n); break;
+    case 218: e = launch_cfg<2, 18>(c, p, n); break;
+    case 220: e = launch_cfg<2, 20>(c, p, n); break;
+    default: e = launch_cfg<2, 16>(c, p, n); break;
     }
     c->launches++;
     return e;
