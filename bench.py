@@ -281,7 +281,7 @@ def main():
     if not args.no_e2e:
         host = [torch.empty(gs.num[s], K, dtype=torch.float64).pin_memory() for s in (MOVIES, USERS)]
         for s in (MOVIES, USERS):
-            host[s].copy_(gs.items[s][: gs.num[s]])
+            gs.ctx.get_items_ptr(s, host[s].data_ptr())
         torch.cuda.synchronize()
 
         def e2e_step():

@@ -32,6 +32,11 @@ SYMBOLS = {
     "bpmf_gpu_bind_items": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "bpmf_gpu_set_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "bpmf_gpu_items_device_ptr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "bpmf_gpu_ipc_export": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p]),
+    "bpmf_gpu_ipc_open": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "bpmf_gpu_enable_peer_access": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bpmf_gpu_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
+    "bpmf_gpu_host_free": (C.c_int, [C.c_void_p]),
     "bpmf_gpu_set_items": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "bpmf_gpu_get_items": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "bpmf_gpu_get_iter": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
@@ -140,6 +145,18 @@ class Context:
         p = C.c_void_p()
         self._ck(self.L.bpmf_gpu_items_device_ptr(self.h, side, C.byref(p)))
         return p.value
+
+    def ipc_export(self, side):
+        buf = C.create_string_buffer(64)
+        self._ck(self.L.bpmf_gpu_ipc_export(self.h, side, buf))
+        return buf.raw
+
+    def ipc_open(self, handle):
+        p = C.c_void_p()
+        self._ck(self.L.bpmf_gpu_ipc_open(self.h, handle, C.byref(p)))
+        return p.value
+
+    def enable_peer_access(self, peer): self._ck(self.L.bpmf_gpu_enable_peer_access(self.h, peer.h))
 
     def set_items(self, side, a):
         a = np.ascontiguousarray(a, np.float64)

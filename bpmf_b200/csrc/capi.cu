@@ -137,6 +137,8 @@ int bpmf_gpu_destroy(bpmf_gpu_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     free_side(ctx->side[0]); free_side(ctx->side[1]);
+    for (void *m : ctx->ipc_mapped) cudaIpcCloseMemHandle(m);
+    ctx->ipc_mapped.clear();
     HyperScratch &h = ctx->hs;
     dfree(h.words); dfree(h.acc); dfree(h.rank); dfree(h.pos_of_rank); dfree(h.row_start); dfree(h.row_cls);
     dfree(h.mats); dfree(h.vecs); dfree(h.piv); dfree(h.host_in);
@@ -304,6 +306,54 @@ int bpmf_gpu_items_device_ptr(bpmf_gpu_ctx *ctx, int side, double **dev_items)
     *dev_items = ctx->side[side].items;
     return BPMF_GPU_OK;
 }
+
+int bpmf_gpu_ipc_export(bpmf_gpu_ctx *ctx, int side, unsigned char handle[BPMF_GPU_IPC_HANDLE_BYTES])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == BPMF_GPU_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+    if (!ctx || !side_ok(side) || !handle) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
+    if (s.items != s.items_own) return fail(ctx, BPMF_GPU_EINVAL, "externally bound latent storage cannot be exported");
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, s.items_own));
+    memcpy(handle, &h, sizeof h);
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_ipc_open(bpmf_gpu_ctx *ctx, const unsigned char handle[BPMF_GPU_IPC_HANDLE_BYTES], double **dev_items)
+{
+    if (!ctx || !handle || !dev_items) return BPMF_GPU_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    void *p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->ipc_mapped.push_back(p);
+    *dev_items = static_cast<double *>(p);
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_enable_peer_access(bpmf_gpu_ctx *ctx, const bpmf_gpu_ctx *peer)
+{
+    if (!ctx || !peer) return BPMF_GPU_EINVAL;
+    if (ctx->device == peer->device) return BPMF_GPU_OK;
+    CU(cudaSetDevice(ctx->device));
+    int can = 0;
+    CU(cudaDeviceCanAccessPeer(&can, ctx->device, peer->device));
+    if (!can) return fail(ctx, BPMF_GPU_ECUDA, "devices are not peer-accessible");
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ctx->err = cudaGetErrorString(e); return BPMF_GPU_ECUDA; }
+    (void)cudaGetLastError();
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_host_alloc(void **host_ptr, uint64_t bytes)
+{
+    if (!host_ptr) return BPMF_GPU_EINVAL;
+    return cudaMallocHost(host_ptr, bytes ? bytes : 1) == cudaSuccess ? BPMF_GPU_OK : BPMF_GPU_ECUDA;
+}
+int bpmf_gpu_host_free(void *host_ptr) { return cudaFreeHost(host_ptr) == cudaSuccess ? BPMF_GPU_OK : BPMF_GPU_ECUDA; }
 
 int bpmf_gpu_set_items(bpmf_gpu_ctx *ctx, int side, const double *host_items)
 {

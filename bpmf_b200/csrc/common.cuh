@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <vector>
 #include <cuda_runtime.h>
 
 namespace bpmf {
@@ -82,6 +83,7 @@ struct bpmf_gpu_ctx {
     long long ev_read = 0;       // launches already returned by bpmf_gpu_items_kernel_time
     long long launches = 0;
     std::string err;
+    std::vector<void *> ipc_mapped;       // peer allocations opened with cudaIpcOpenMemHandle
 };
 
 // ---- launchers implemented in the kernel translation units ------------------------------------

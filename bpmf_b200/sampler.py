@@ -9,15 +9,9 @@ Nothing here computes on the CPU; without the CUDA library or a GPU the construc
 import numpy as np
 
 from . import capi
+from .partition import allgather_slices, balanced_ranges, split_range
 
 MOVIES, USERS = capi.MOVIES, capi.USERS
-
-
-def split_range(n, world, rank):
-    """Equal-count contiguous slices, ceil(n / world) each (the last ones may be short or empty)."""
-    chunk = (n + world - 1) // world
-    lo = min(n, rank * chunk)
-    return lo, min(n, lo + chunk), chunk
 
 
 class GibbsSampler:
@@ -40,17 +34,30 @@ class GibbsSampler:
         self.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
         self.num = [0, 0]
         self.range = [None, None]
-        self.items = [None, None]     # torch tensors the library's latent matrices are bound to (padded to chunk * world)
+        self.items = [None, None]     # allgather mode: torch tensors the latent matrices are bound to (padded to chunk * world)
+        self._tiny = torch.zeros(1, device="cuda:%d" % device)
         for side in (MOVIES, USERS):
             n, n_other, ptr, idx, val = ratings.side(side)
             self.num[side] = n
             self.ctx.load_side(side, n, n_other, ptr, idx, val, ratings.mean_rating)
-            lo, hi, chunk = split_range(n, self.world, self.rank)
+            if self.exchange == "push":
+                # ragged, work-balanced ranges; the library's own (cudaMalloc) storage is what CUDA IPC can export
+                b = balanced_ranges(ptr, self.world)
+                lo, hi, chunk = int(b[self.rank]), int(b[self.rank + 1]), 0
+            else:
+                lo, hi, chunk = split_range(n, self.world, self.rank)
+                buf = torch.zeros(chunk * self.world, K, dtype=torch.float64, device="cuda:%d" % device)
+                self.ctx.bind_items(side, buf.data_ptr())
+                self.items[side] = buf
             self.range[side] = (lo, hi, chunk)
             self.ctx.set_range(side, lo, hi)
-            buf = torch.zeros(chunk * self.world, K, dtype=torch.float64, device="cuda:%d" % device)
-            self.ctx.bind_items(side, buf.data_ptr())
-            self.items[side] = buf
+        if self.exchange == "push":
+            for side in (MOVIES, USERS):
+                handles = [None] * self.world
+                dist.all_gather_object(handles, self.ctx.ipc_export(side))
+                ptrs = [self.ctx.items_device_ptr(side) if r == self.rank else self.ctx.ipc_open(handles[r])
+                        for r in range(self.world)]
+                self.ctx.set_peers(side, ptrs)
         if with_test:
             for side in (MOVIES, USERS):
                 self.ctx.load_test(side, *ratings.test_side(side))
@@ -69,13 +76,13 @@ class GibbsSampler:
     def _exchange(self, side):
         if self.world == 1:
             return
-        lo, hi, chunk = self.range[side]
-        buf = self.items[side]
         if self.exchange == "allgather":
-            self.dist.all_gather_into_tensor(buf, buf[self.rank * chunk:(self.rank + 1) * chunk])
+            allgather_slices(self.dist, self.items[side], self.rank, self.world)
         elif self.exchange == "push":
-            # the kernel already wrote into the peers; a barrier makes every rank's stores visible everywhere
-            self.dist.barrier(device_ids=[self.device])
+            # the item kernel already stored every fresh column into all replicas over NVLink; a one-element
+            # all-reduce on the stream orders the next kernel after EVERY rank's item kernel (stores are visible
+            # system-wide once the storing kernel has completed)
+            self.dist.all_reduce(self._tiny)
         else:
             raise ValueError(self.exchange)
 
@@ -88,7 +95,11 @@ class GibbsSampler:
         return self.ctx.predict(MOVIES, burnin), self.ctx.predict(USERS, burnin)
 
     def items_host(self, side):
-        return self.items[side][: self.num[side]].cpu().numpy()
+        return self.ctx.get_items(side)
+
+    def items_view(self, side):
+        """device tensor of the bound latent matrix (allgather mode) or None (push mode: library-owned storage)"""
+        return None if self.items[side] is None else self.items[side][: self.num[side]]
 
     def close(self):
         self.ctx.close()

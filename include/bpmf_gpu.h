@@ -76,6 +76,18 @@ int bpmf_gpu_bind_items(bpmf_gpu_ctx *ctx, int side, double *dev_items);
  * them as it is produced (replaces Sys::send_item, c++/bpmf.h:216). npeers = 0 turns it off. */
 int bpmf_gpu_set_peers(bpmf_gpu_ctx *ctx, int side, int npeers, double *const *dev_peer_items);
 int bpmf_gpu_items_device_ptr(bpmf_gpu_ctx *ctx, int side, double **dev_items);
+/* One process per GPU: export this context's OWN latent storage of a side as a 64-byte CUDA IPC handle, and map a
+ * peer process's handle into this process (the result goes into bpmf_gpu_set_peers). Handles of externally bound
+ * storage (bpmf_gpu_bind_items) cannot be exported. bpmf_gpu_destroy unmaps what _ipc_open mapped. */
+#define BPMF_GPU_IPC_HANDLE_BYTES 64
+int bpmf_gpu_ipc_export(bpmf_gpu_ctx *ctx, int side, unsigned char handle[BPMF_GPU_IPC_HANDLE_BYTES]);
+int bpmf_gpu_ipc_open(bpmf_gpu_ctx *ctx, const unsigned char handle[BPMF_GPU_IPC_HANDLE_BYTES], double **dev_items);
+/* One process, several GPUs: let this context's device read/write `peer`'s device memory directly, so that
+ * bpmf_gpu_items_device_ptr(peer, ...) can be passed to bpmf_gpu_set_peers(ctx, ...). */
+int bpmf_gpu_enable_peer_access(bpmf_gpu_ctx *ctx, const bpmf_gpu_ctx *peer);
+/* pinned (page-locked) host memory for Sys::items_ptr, so the per-sweep copies run at PCIe speed */
+int bpmf_gpu_host_alloc(void **host_ptr, uint64_t bytes);
+int bpmf_gpu_host_free(void *host_ptr);
 
 int bpmf_gpu_set_items(bpmf_gpu_ctx *ctx, int side, const double *host_items);
 int bpmf_gpu_get_items(bpmf_gpu_ctx *ctx, int side, double *host_items); /* synchronises */

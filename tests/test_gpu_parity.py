@@ -250,3 +250,19 @@ def test_bind_external_items_storage(gpu):
     ctx.sync()
     assert np.abs(ext.cpu().numpy() - orc.items(MOVIES)).max() <= TOL_ITEMS * 10
     ctx.close()
+
+
+@pytest.mark.parametrize("mode", ["allgather", "push"])
+def test_two_gpus_match_one(gpu, mode):
+    torch = pytest.importorskip("torch")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tests", "multi_gpu_worker.py"), mode]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "identical to single GPU" in r.stdout
