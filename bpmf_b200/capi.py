@@ -52,6 +52,9 @@ SYMBOLS = {
     "bpmf_gpu_predict": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                    C.POINTER(C.c_int64)]),
     "bpmf_gpu_get_predictions": (C.c_int, [C.c_void_p, C.c_int, _f64p, _f64p]),
+    "bpmf_gpu_enable_aggregation": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "bpmf_gpu_aggregate": (C.c_int, [C.c_void_p, C.c_int]),
+    "bpmf_gpu_get_aggregates": (C.c_int, [C.c_void_p, C.c_int, _f64p, _f64p]),
     "bpmf_gpu_launch_count": (C.c_int64, [C.c_void_p]),
     "bpmf_gpu_last_items_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "bpmf_gpu_items_kernel_time": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
@@ -227,6 +230,15 @@ class Context:
         a, b = np.empty(n), np.empty(n)
         self._ck(self.L.bpmf_gpu_get_predictions(self.h, side, a, b))
         return a, b
+
+    def enable_aggregation(self, side, burnin): self._ck(self.L.bpmf_gpu_enable_aggregation(self.h, side, burnin))
+    def aggregate(self, side): self._ck(self.L.bpmf_gpu_aggregate(self.h, side))
+
+    def get_aggregates(self, side):
+        K, n = self.K, self.num[side]
+        mu, lam = np.empty((n, K)), np.empty((n, K * K))
+        self._ck(self.L.bpmf_gpu_get_aggregates(self.h, side, mu.reshape(-1), lam.reshape(-1)))
+        return mu, lam
 
     def last_items_kernel_ms(self):
         ms = C.c_float()

@@ -47,7 +47,7 @@ void free_side(SideDev &s)
     dfree(s.peers_dev);
     dfree(s.hp.mu); dfree(s.hp.LambdaU); dfree(s.hp.LambdaF);
     dfree(s.sum); dfree(s.prod); dfree(s.cov); dfree(s.norm); dfree(s.partials); dfree(s.pred_partials);
-    dfree(s.work_counter);
+    dfree(s.work_counter); dfree(s.aggrMu); dfree(s.aggrLambda);
     s = SideDev();
 }
 
@@ -499,7 +499,50 @@ int bpmf_gpu_sample(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_varian
     if (rc) return rc;
     rc = bpmf_gpu_sample_items(ctx, side, (uint32_t)s.iter, alpha, kernel_variant);  // :352-373
     if (rc) return rc;
+    if (s.aggrMu && s.iter >= s.aggr_burnin) {                            // :364-368
+        rc = bpmf_gpu_aggregate(ctx, side);
+        if (rc) return rc;
+    }
     return bpmf_gpu_reduce_stats(ctx, side);                              // :379-384
+}
+
+int bpmf_gpu_enable_aggregation(bpmf_gpu_ctx *ctx, int side, int burnin)
+{
+    if (!ctx || !side_ok(side)) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    dfree(s.aggrMu); dfree(s.aggrLambda);
+    const size_t K = (size_t)ctx->K, n = (size_t)(s.num > 0 ? s.num : 1);
+    CU(cudaMalloc(&s.aggrMu, sizeof(double) * K * n));
+    CU(cudaMalloc(&s.aggrLambda, sizeof(double) * K * K * n));
+    CU(cudaMemset(s.aggrMu, 0, sizeof(double) * K * n));               // sample.cpp:198-199
+    CU(cudaMemset(s.aggrLambda, 0, sizeof(double) * K * K * n));
+    s.aggr_burnin = burnin;
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_aggregate(bpmf_gpu_ctx *ctx, int side)
+{
+    if (!ctx || !side_ok(side)) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded || !s.aggrMu) return fail(ctx, BPMF_GPU_EINVAL, "aggregation is not enabled for this side");
+    CU(cudaSetDevice(ctx->device));
+    CU(launch_aggregate(ctx, side));
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_get_aggregates(bpmf_gpu_ctx *ctx, int side, double *aggrMu, double *aggrLambda)
+{
+    if (!ctx || !side_ok(side)) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded || !s.aggrMu) return fail(ctx, BPMF_GPU_EINVAL, "aggregation is not enabled for this side");
+    CU(cudaSetDevice(ctx->device));
+    const size_t K = (size_t)ctx->K;
+    if (aggrMu) CU(cudaMemcpyAsync(aggrMu, s.aggrMu, sizeof(double) * K * s.num, cudaMemcpyDeviceToHost, ctx->stream));
+    if (aggrLambda) CU(cudaMemcpyAsync(aggrLambda, s.aggrLambda, sizeof(double) * K * K * s.num, cudaMemcpyDeviceToHost, ctx->stream));
+    return check_device_error(ctx);
 }
 
 int bpmf_gpu_predict(bpmf_gpu_ctx *ctx, int side, int burnin, double *rmse, double *rmse_avg, int64_t *num_predict)

@@ -46,6 +46,9 @@ struct SideDev {          // the device mirror of one Sys (c++/bpmf.h:112-239)
     double *partials = nullptr;     // STATS_BLOCKS x (K*K + K + 1)
     double *pred_partials = nullptr;
     int pred_blocks = 0;
+    // posterior aggregation (-o): K x num and K*K x num, allocated by bpmf_gpu_enable_aggregation
+    double *aggrMu = nullptr, *aggrLambda = nullptr;
+    int aggr_burnin = 0;
     // dynamic work counter for the item kernels
     unsigned int *work_counter = nullptr;
 };
@@ -93,6 +96,7 @@ cudaError_t launch_hyper(bpmf_gpu_ctx *c, int side, uint32_t iter, const double 
 cudaError_t launch_items_exact(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha);
 cudaError_t launch_stats(bpmf_gpu_ctx *c, int side);
 cudaError_t launch_predict(bpmf_gpu_ctx *c, int side, int n);
+cudaError_t launch_aggregate(bpmf_gpu_ctx *c, int side);
 cudaError_t launch_debug_randn(bpmf_gpu_ctx *c, uint32_t seed, int n, double *d_out);
 size_t exact_items_smem_bytes(int K);
 // fast_kernels.cu

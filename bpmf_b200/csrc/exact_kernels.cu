@@ -623,6 +623,38 @@ cudaError_t launch_predict(bpmf_gpu_ctx *c, int side, int n)
 }
 
 // =================================================================================================
+// Posterior aggregation of -o (sample.cpp:364-368): aggrMu.col(i) += r; aggrLambda.col(i) += vec(r r^T)
+// One thread per element of the K x K outer product, items of [from, to).
+// =================================================================================================
+__global__ void __launch_bounds__(256) aggregate_kernel(int K, int from, int to, const double *__restrict__ items, double *aggrMu,
+                                                        double *aggrLambda)
+{
+    const int KK = K * K;
+    const int64_t total = (int64_t)(to - from) * KK;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = from + q / KK;
+        const int e = (int)(q % KK), a = e % K, b = e / K;
+        const double *r = items + (size_t)i * K;
+        const double ra = r[a], rb = r[b];
+        aggrLambda[(size_t)i * KK + e] += ra * rb;
+        if (b == 0) aggrMu[(size_t)i * K + a] += ra;
+    }
+}
+
+cudaError_t launch_aggregate(bpmf_gpu_ctx *c, int side)
+{
+    SideDev &s = c->side[side];
+    const int64_t total = (int64_t)(s.to - s.from) * c->K * c->K;
+    if (total <= 0) return cudaSuccess;
+    int64_t nb = (total + 255) / 256;
+    const int64_t cap = (int64_t)c->sm_count * 16;
+    if (nb > cap) nb = cap;
+    aggregate_kernel<<<(unsigned)nb, 256, 0, c->stream>>>(c->K, s.from, s.to, s.items, s.aggrMu, s.aggrLambda);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+// =================================================================================================
 // RNG probe
 // =================================================================================================
 __global__ void debug_randn_kernel(uint32_t c, int n, double *out)

@@ -129,6 +129,14 @@ int bpmf_gpu_get_stats(bpmf_gpu_ctx *ctx, int side, double *sum, double *prod, d
 int bpmf_gpu_predict(bpmf_gpu_ctx *ctx, int side, int burnin, double *rmse, double *rmse_avg, int64_t *num_predict);
 int bpmf_gpu_get_predictions(bpmf_gpu_ctx *ctx, int side, double *pavg, double *pm2);
 
+/* ---- posterior aggregation of -o (c++/sample.cpp:195-199,364-368; read back for c++/bpmf.cpp:229-239) ----
+ * After _enable_aggregation, every bpmf_gpu_sample whose iteration is >= burnin adds r to aggrMu.col(i) and
+ * vec(r r^T) to aggrLambda.col(i) for the items of [from,to) (K*num + K*K*num doubles of device memory).
+ * bpmf_gpu_aggregate is that stage on its own, for hosts that drive the stages individually. */
+int bpmf_gpu_enable_aggregation(bpmf_gpu_ctx *ctx, int side, int burnin);
+int bpmf_gpu_aggregate(bpmf_gpu_ctx *ctx, int side);
+int bpmf_gpu_get_aggregates(bpmf_gpu_ctx *ctx, int side, double *aggrMu, double *aggrLambda); /* synchronises */
+
 /* ---- introspection --------------------------------------------------------------------------- */
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t bpmf_gpu_launch_count(const bpmf_gpu_ctx *ctx);
