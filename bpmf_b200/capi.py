@@ -58,6 +58,7 @@ SYMBOLS = {
     "bpmf_gpu_launch_count": (C.c_int64, [C.c_void_p]),
     "bpmf_gpu_last_items_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "bpmf_gpu_items_kernel_time": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "bpmf_gpu_debug_set_tuning": (C.c_int, [C.c_void_p, C.c_int]),
     "bpmf_gpu_debug_randn": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, _f64p]),
 }
 
@@ -250,6 +251,8 @@ class Context:
         t, n = C.c_double(), C.c_int()
         self._ck(self.L.bpmf_gpu_items_kernel_time(self.h, C.byref(t), C.byref(n)))
         return t.value, n.value
+
+    def set_tuning(self, cfg): self._ck(self.L.bpmf_gpu_debug_set_tuning(self.h, cfg))
 
     def debug_randn(self, c, n):
         out = np.empty(n)

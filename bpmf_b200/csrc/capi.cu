@@ -629,6 +629,13 @@ int bpmf_gpu_sample_host(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_v
     return check_device_error(ctx);   // synchronises the stream
 }
 
+int bpmf_gpu_debug_set_tuning(bpmf_gpu_ctx *ctx, int stream_cfg)
+{
+    if (!ctx) return BPMF_GPU_EINVAL;
+    ctx->stream_cfg = stream_cfg;
+    return BPMF_GPU_OK;
+}
+
 int bpmf_gpu_debug_randn(bpmf_gpu_ctx *ctx, uint32_t c, int n, double *host_out)
 {
     if (!ctx || n < 1 || n > 4096 || !host_out) return BPMF_GPU_EINVAL;

@@ -85,6 +85,7 @@ struct bpmf_gpu_ctx {
     long long ev_count = 0;      // item-kernel launches timed so far
     long long ev_read = 0;       // launches already returned by bpmf_gpu_items_kernel_time
     long long launches = 0;
+    int stream_cfg = 0;                   // 0 = default; see launch_items_stream32
     std::string err;
     std::vector<void *> ipc_mapped;       // peer allocations opened with cudaIpcOpenMemHandle
 };

@@ -388,17 +388,347 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32_kernel(StreamArgs p
     cp_async_wait<0>();
 }
 
-template <int NS, int NW>
+// =====================================================================================================================
+// Version 3 of the same kernel. Two changes, both aimed at the fp64 pipe, which DMMA and scalar DFMA/DMUL share: a DMMA
+// holds it for 16 cycles per scheduler, so every DEPENDENT scalar fp64 instruction of another warp's tail queues behind
+// the Gram DMMAs, and the tail is one long dependent chain.
+//   fetch   Index / value loads are aligned to the stage (one coalesced load of the next stage's <= 16 entries, issued a
+//           whole stage ahead), so issuing a stage is 8 x (shuffle, address, cp.async) and little else.
+//   tail    Square-root-free blocked LDL^T instead of LL^T: per column the chain is pivot shuffle -> reciprocal ->
+//           multiply -> FMA (no rsqrt, no column scaling before the broadcasts); the unit-lower factor goes to shared
+//           memory already divided by the pivots, which turns both triangular solves into pure shuffle + FMA chains:
+//               A = Lu D Lu^T, L = Lu D^(1/2):  x = L^-T (L^-1 b + z) = Lu^-T (D^-1 Lu^-1 b + D^(-1/2) z)
+//           One rsqrt per item (all 32 pivots at once, lane k owns d_k) instead of 32 serial ones.
+//           bench_micro/emulate_block_ldlt.py is the lane-level model of chol3_block_column / the scatter / the solves.
+// =====================================================================================================================
+constexpr int LPACK1 = 496;                  // strictly lower triangle, column-major packed
+constexpr int V3_ZY_OFF = LPACK1 * 8, V3_ZR_OFF = V3_ZY_OFF + 256, V3_B_OFF = V3_ZR_OFF + 256;
+static_assert(V3_B_OFF + 256 <= STAGE_BYTES, "v3 tail scratch must fit in one stage");
+constexpr __host__ __device__ int col_off1(int k) { return 31 * k - ((k * (k - 1)) / 2); }
+
+// 1 / p for a positive normal p: MUFU.RCP64H seed (about 20 bits) + one cubic step. Relative error ~1e-17.
+__device__ __forceinline__ double fast_rcp(double p)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(p));
+    const double e = fma(-p, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
+}
+
+template <int KB>
+__device__ __forceinline__ void chol3_block_column(double (&c)[10][2], double &myd, double &myrinv, bool &ok, int lane, int t)
+{
+    constexpr int D = blk(KB, KB);
+#pragma unroll 1
+    for (int k2 = 0; k2 < 4; ++k2) {
+        const int qsrc = (lane & ~3) | k2;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int k = 2 * k2 + e;
+            const double p = __shfl_sync(FULL, c[D][e], 4 * k + k2);       // pivot d_k: lane (g = k, t = k2), register e
+            // a[2t][k], a[2t+1][k] (unscaled) and the column itself do not wait for the reciprocal
+            double bl0 = __shfl_sync(FULL, c[D][e], 4 * (2 * t) + k2);
+            double bl1 = __shfl_sync(FULL, c[D][e], 4 * (2 * t + 1) + k2);
+            double a[4];
+#pragma unroll
+            for (int I = KB; I < 4; ++I) a[I] = __shfl_sync(FULL, c[blk(I, KB)][e], qsrc);   // a[8I+g][k]
+            if (!(p > 0.0)) ok = false;                                     // Eigen LLT: pivot <= 0 -> "Cholesky failed"
+            const double rinv = fast_rcp(p);
+            if (lane == 8 * KB + k) { myd = p; myrinv = rinv; }
+            bl0 = (2 * t > k) ? -(bl0 * rinv) : 0.0;                        // zero where this lane's column is not right of k
+            bl1 = (2 * t + 1 > k) ? -(bl1 * rinv) : 0.0;
+#pragma unroll
+            for (int I = KB; I < 4; ++I) {
+                c[blk(I, KB)][0] = fma(a[I], bl0, c[blk(I, KB)][0]);
+                c[blk(I, KB)][1] = fma(a[I], bl1, c[blk(I, KB)][1]);
+            }
+        }
+    }
+    // trailing update A(I,J) -= A~(I,KB) D^-1 A~(J,KB)^T for KB < J <= I on the tensor cores
+    if (KB < 3) {
+        double fr[4][2], rv[2];
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) rv[kk] = __shfl_sync(FULL, myrinv, 8 * KB + 4 * kk + t);
+#pragma unroll
+        for (int I = KB + 1; I < 4; ++I)
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                const int src = (lane & ~3) | (2 * kk + (t >> 1));
+                const double v0 = __shfl_sync(FULL, c[blk(I, KB)][0], src);
+                const double v1 = __shfl_sync(FULL, c[blk(I, KB)][1], src);
+                fr[I][kk] = (t & 1) ? v1 : v0;                              // A~(I,KB)[g][4kk + t]
+            }
+#pragma unroll
+        for (int I = KB + 1; I < 4; ++I)
+#pragma unroll
+            for (int J = KB + 1; J <= I; ++J)
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) dmma884(c[blk(I, J)][0], c[blk(I, J)][1], -fr[I][kk], fr[J][kk] * rv[kk]);
+    }
+}
+
+// DBG (bench_micro/tune_stream.py only) is a bit mask: 0 = the product; 1 = no tail (Gram only); 2 = no Gram DMMAs;
+// 4 = no gather (Gram on whatever the stage holds); 8 = no normals; 16 = no factorization; 32 = no triangular solves.
+// Anything but 0 produces garbage: the probes exist to time the parts of the kernel.
+template <int NS, int NW, int DBG>
+__global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs p)
+{
+    constexpr int WARP_BYTES = warp_bytes<NS>();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    double *sLF = reinterpret_cast<double *>(smem_raw);            // LambdaF(i,k) at sLF[k * LFS + i]
+    double *srr0 = sLF + 32 * LFS;                                 // LambdaF * mu
+    unsigned char *wbase = smem_raw + SHARED_BYTES + (size_t)warp * WARP_BYTES;
+    const uint32_t wbase_s = (uint32_t)__cvta_generic_to_shared(wbase);
+
+    for (int e = tid; e < 1024; e += NW * 32) sLF[(e >> 5) * LFS + (e & 31)] = p.LambdaF[e];
+    __syncthreads();
+    if (tid < 32) {
+        double s = 0.0;
+        for (int j = 0; j < 32; ++j) s += sLF[j * LFS + tid] * p.mu[j];   // rr = LambdaF * hp.mu (sample.cpp:285)
+        srr0[tid] = s;
+    }
+    __syncthreads();
+
+    // ---------------- fetch-side state (warp-uniform unless noted); positions are relative to the group's first rating
+    int g_base = 0, g_n = 0, f_it = 0;
+    int cpr = 0;                          // per lane: colptr[g_base + lane] - colptr[g_base]
+    int f_pos = 0, f_end = 0, f_start = 0, g_end = 0;
+    const int32_t *g_idx = p.rowidx;      // rowidx / val at the group's first rating
+    const double *g_val = p.val;
+    int32_t n_idx = 0;                    // per lane: index / value of stream position f_pos + (lane & 15): the NEXT stage's
+    double n_w = 0.0;
+    bool f_done = false;
+    const unsigned char *src_lane = reinterpret_cast<const unsigned char *>(p.other) + (lane & 15) * 16;   // this lane's 16 B of a row
+    const uint32_t dst_lane = wbase_s + (lane >> 4) * ROWB + (lane & 15) * 16;
+    const int half = lane >> 4;
+
+    auto load_next = [&]() {
+        const int q = f_pos + (lane & 15);
+        n_idx = 0; n_w = 0.0;
+        if (q < g_end) {                  // entries past the item's end but inside the group are loaded and never used
+            n_idx = __ldg(g_idx + q);
+            n_w = __ldg(g_val + q);
+        }
+    };
+    auto claim = [&]() {
+        int base = 0;
+        if (lane == 0) base = p.from + (int)atomicAdd(p.work_counter, (unsigned)CLAIM);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= p.to) { f_done = true; return; }
+        g_base = base;
+        g_n = min(CLAIM, p.to - base);
+        const int64_t c0 = __ldg(p.colptr + base);
+        cpr = (lane <= g_n) ? (int)(__ldg(p.colptr + base + lane) - c0) : 0;
+        g_idx = p.rowidx + c0;
+        g_val = p.val + c0;
+        f_it = 0;
+        f_start = f_pos = 0;
+        f_end = __shfl_sync(FULL, cpr, 1);
+        g_end = __shfl_sync(FULL, cpr, g_n);
+    };
+    // fill ring slot `slot` with the next (at most SR) ratings of the current item; exactly one commit_group per call
+    auto issue_stage = [&](int slot) {
+        const uint32_t st = dst_lane + slot * STAGE_BYTES;
+        unsigned char *stg = wbase + slot * STAGE_BYTES;
+        if (f_done) {
+            if (lane == 0) *reinterpret_cast<int4 *>(stg + META_OFF) = make_int4(-1, 0, 0, 0);
+            cp_async_commit();
+            return;
+        }
+        const int n = min(SR, f_end - f_pos);
+        const int nn = n - half;
+#pragma unroll
+        for (int i = 0; i < SR / 2; ++i) {
+            const unsigned j = (unsigned)__shfl_sync(FULL, n_idx, 2 * i + half);
+            // rows past the item's end are zero-filled (src-size 0 reads nothing; j is still a valid row)
+            if (!(DBG & 4)) cp_async16(st + 2 * i * ROWB, src_lane + (size_t)j * 256, (2 * i < nn) ? 16 : 0);
+        }
+        // rr weight (v - mean_rating) * alpha (sample.cpp:255)
+        if (lane < SR) reinterpret_cast<double *>(stg + W_OFF)[lane] = (lane < n) ? (n_w - p.mean_rating) * p.alpha : 0.0;
+        const int last = (f_pos + n == f_end);
+        if (lane == 0) *reinterpret_cast<int4 *>(stg + META_OFF) = make_int4(n, g_base + f_it, f_pos == f_start, last);
+        cp_async_commit();
+        f_pos += n;
+        if (last) {
+            ++f_it;
+            if (f_it >= g_n) claim();
+            else { f_start = f_end; f_end = __shfl_sync(FULL, cpr, f_it + 1); }
+        }
+        if (!f_done) load_next();
+    };
+
+    claim();
+    if (!f_done) load_next();
+#pragma unroll 1
+    for (int s = 0; s < NS; ++s) issue_stage(s);
+
+    double c[10][2];
+    double rrp[4];
+#pragma unroll
+    for (int b = 0; b < 10; ++b) { c[b][0] = 0.0; c[b][1] = 0.0; }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) rrp[a] = 0.0;
+
+    int h = 0;
+#pragma unroll 1
+    for (;;) {
+        cp_async_wait<NS - 1>();
+        __syncwarp();
+        unsigned char *stg = wbase + h * STAGE_BYTES;
+        const int4 meta = *reinterpret_cast<const int4 *>(stg + META_OFF);
+        if (meta.x < 0) break;
+        // ---------------- Gram + rhs of this stage (computeMuLambda, sample.cpp:251-257) ----------------
+        {
+            const unsigned char *row = stg + t * ROWB + g * 8;
+            const double *wq = reinterpret_cast<const double *>(stg + W_OFF) + t;
+            if (!(DBG & 2)) {
+                if (meta.x > 0) gram_group(c, rrp, row, wq);
+                if (meta.x > 4) gram_group(c, rrp, row + 4 * ROWB, wq + 4);
+                if (meta.x > 8) gram_group(c, rrp, row + 8 * ROWB, wq + 8);
+                if (meta.x > 12) gram_group(c, rrp, row + 12 * ROWB, wq + 12);
+            } else if (meta.x > 0) {
+                c[0][0] += *reinterpret_cast<const double *>(row) * *wq;
+            }
+        }
+        __syncwarp();                     // every lane is done reading slot h
+        if (!meta.w) {                    // more stages of this item to come: refill the slot and go on
+            issue_stage(h);
+            h = (h + 1 == NS) ? 0 : h + 1;
+            continue;
+        }
+        // ---------------- tail: one item's Gram is complete; slot h is its scratch until the refill at the end ---------
+        const int idx = meta.y;
+        if (DBG & 1) {
+            double acc = 0.0;
+#pragma unroll
+            for (int b = 0; b < 10; ++b) { acc += c[b][0] + c[b][1]; c[b][0] = 0.0; c[b][1] = 0.0; }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) { acc += rrp[a]; rrp[a] = 0.0; }
+            p.items[(size_t)idx * 32 + lane] = acc;
+            issue_stage(h);
+            h = (h + 1 == NS) ? 0 : h + 1;
+            continue;
+        }
+        double *zy = reinterpret_cast<double *>(stg + V3_ZY_OFF), *zr = reinterpret_cast<double *>(stg + V3_ZR_OFF);
+        double *wb = reinterpret_cast<double *>(stg + V3_B_OFF), *Lp = reinterpret_cast<double *>(stg);
+        // the K normals of this item: rng_set_pos((idx+1)*K*(iter+1)) (sample.cpp:266). Accepted polar attempts are numbered
+        // by ballot; lane n then finishes normal n (one log / sqrt / divide per lane instead of one per attempt).
+        if (!(DBG & 8)) {
+            const uint32_t seed = (uint32_t)(((long long)idx + 1) * 32ll * ((long long)p.iter + 1));
+            int have = 0;
+            for (uint32_t base = 0; have < 32; base += 32) {
+                const U4 bk = stream_block(seed, base + lane);
+                const Polar pa = polar_attempt(bk.v[3], bk.v[2], bk.v[1], bk.v[0]);
+                const unsigned m = __ballot_sync(FULL, pa.ok);
+                const int n = have + __popc(m & ((1u << lane) - 1u));
+                if (pa.ok && n < 32) { zy[n] = pa.y; zr[n] = pa.r2; }
+                have += __popc(m);
+            }
+        }
+        // rr = LambdaF*mu + sum over the quad's four ratings-of-a-group
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            rrp[a] += __shfl_xor_sync(FULL, rrp[a], 1);
+            rrp[a] += __shfl_xor_sync(FULL, rrp[a], 2);
+        }
+        if (t == 0) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) wb[8 * a + g] = srr0[8 * a + g] + rrp[a];
+        }
+        __syncwarp();
+        const double z = (DBG & 8) ? 0.25 * lane : __dmul_rn(zy[lane], polar_mult(zr[lane]));
+        double bb = wb[lane];
+        // MM = LambdaF + alpha * G (sample.cpp:297-298), in place in the accumulator layout
+#pragma unroll
+        for (int I = 0; I < 4; ++I)
+#pragma unroll
+            for (int J = 0; J <= I; ++J)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    c[blk(I, J)][e] = fma(p.alpha, c[blk(I, J)][e], sLF[(8 * J + 2 * t + e) * LFS + 8 * I + g]);   // LambdaF(i,k), i >= k
+        // chol.compute(MM) (sample.cpp:306) as MM = Lu D Lu^T; lane k ends up with d_k and 1 / d_k
+        double myd = 1.0, myrinv = 1.0;
+        bool ok = true;
+        if (!(DBG & 16)) {
+            chol3_block_column<0>(c, myd, myrinv, ok, lane, t);
+            chol3_block_column<1>(c, myd, myrinv, ok, lane, t);
+            chol3_block_column<2>(c, myd, myrinv, ok, lane, t);
+            chol3_block_column<3>(c, myd, myrinv, ok, lane, t);
+        } else {
+            myd = c[0][0] + 2.0; myrinv = fast_rcp(myd);
+        }
+        const double myrs = rsqrt(myd);                       // 1 / L(k,k)
+        // Lu -> shared memory, packed by columns without the unit diagonal: element (i,k), i > k, at col_off1(k) + i - k - 1
+        {
+#pragma unroll
+            for (int J = 0; J < 4; ++J)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int k = 8 * J + 2 * t + e;
+                    const double rk = __shfl_sync(FULL, myrinv, k);
+                    double *lq = Lp + (31 * k - ((k * (k - 1)) >> 1)) + g - k - 1;
+#pragma unroll
+                    for (int I = J; I < 4; ++I)
+                        if (I > J || g > 2 * t + e) lq[8 * I] = c[blk(I, J)][e] * rk;
+                }
+        }
+        // reset the accumulators for the next item
+#pragma unroll
+        for (int b = 0; b < 10; ++b) { c[b][0] = 0.0; c[b][1] = 0.0; }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) rrp[a] = 0.0;
+        __syncwarp();
+        if (ok) {
+            // chol.matrixL().solveInPlace(rr); rr += nrandn(); chol.matrixU().solveInPlace(rr) (sample.cpp:321-323):
+            // lane j owns row j; one broadcast + one FMA per step.
+            if (!(DBG & 32)) {
+                const double *lf = Lp + lane - 1;              // element (lane, k) at lf[col_off1(k) - k]
+#pragma unroll
+                for (int k = 0; k < 31; ++k) {
+                    const double yk = __shfl_sync(FULL, bb, k);
+                    if (lane > k) bb = fma(-lf[col_off1(k) - k], yk, bb);
+                }
+            }
+            double yv = fma(bb, myrinv, myrs * z);             // D^-1 Lu^-1 b + D^(-1/2) z
+            if (!(DBG & 32)) {
+                const double *lb = Lp + (31 * lane - ((lane * (lane - 1)) >> 1)) - lane - 1;   // element (i, lane) at lb[i]
+#pragma unroll
+                for (int i = 31; i >= 1; --i) {
+                    const double xi = __shfl_sync(FULL, yv, i);
+                    if (lane < i) yv = fma(-lb[i], xi, yv);
+                }
+            }
+            // items().col(idx) = rr (sample.cpp:324); push to the peer replicas (replaces send_item, :370)
+            p.items[(size_t)idx * 32 + lane] = yv;
+            for (int pr = 0; pr < p.npeers; ++pr) {
+                double *dst = p.peers[pr];
+                if (dst && dst != p.items) dst[(size_t)idx * 32 + lane] = yv;
+            }
+        } else if (lane == 0) {           // THROWERROR("Cholesky failed") (sample.cpp:308): reported through the error word
+            atomicMax(p.err, ERR_CHOLESKY | (unsigned)idx);
+        }
+        __syncwarp();                     // the scratch is free again
+        issue_stage(h);
+        h = (h + 1 == NS) ? 0 : h + 1;
+    }
+    cp_async_wait<0>();
+}
+
+template <int NS, int NW, int VER, int DBG = 0>
 cudaError_t launch_cfg(bpmf_gpu_ctx *c, const StreamArgs &p, long long n)
 {
     constexpr size_t smem = (size_t)NW * warp_bytes<NS>() + SHARED_BYTES;
     static_assert(smem <= 227 * 1024, "shared memory budget");
-    cudaError_t e = cudaFuncSetAttribute(items_stream32_kernel<NS, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = VER >= 3 ? items_stream32v3_kernel<NS, NW, DBG> : items_stream32_kernel<NS, NW>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     long long grid = c->sm_count;                              // persistent: one CTA per SM
     const long long need = (n + (long long)NW * CLAIM - 1) / ((long long)NW * CLAIM);
     if (grid > need) grid = need;
-    items_stream32_kernel<NS, NW><<<(unsigned)grid, NW * 32, smem, c->stream>>>(p);
+    kern<<<(unsigned)grid, NW * 32, smem, c->stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -502,13 +832,33 @@ cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, doub
     if (e != cudaSuccess) return e;
     const long long n = (long long)s.to - s.from;
     if (n < 1) return cudaSuccess;
-    // tuning knob (bench only): BPMF_STREAM_CFG = "<stages><warps>" e.g. "216"; default 2 stages x 16 warps
-    static const int cfg = [] { const char *v = getenv("BPMF_STREAM_CFG"); return v ? atoi(v) : 216; }();
+    // tuning knob (bench_micro/tune_stream.py): "<version><stages><warps>", e.g. 3216 = v3, 2 stages x 16 warps.
+    // Set with bpmf_gpu_debug_set_tuning or the environment variable BPMF_STREAM_CFG.
+    static const int env_cfg = [] { const char *v = getenv("BPMF_STREAM_CFG"); return v ? atoi(v) : 0; }();
+    const int cfg = c->stream_cfg ? c->stream_cfg : env_cfg;
     switch (cfg) {
-    case 315: e = launch_cfg<3, 15>(c, p, n); break;
-    case 218: e = launch_cfg<2, 18>(c, p, n); break;
-    case 220: e = launch_cfg<2, 20>(c, p, n); break;
-    default: e = launch_cfg<2, 16>(c, p, n); break;
+    case 2216: e = launch_cfg<2, 16, 2>(c, p, n); break;
+    case 2220: e = launch_cfg<2, 20, 2>(c, p, n); break;
+    case 2315: e = launch_cfg<3, 15, 2>(c, p, n); break;
+    case 3220: e = launch_cfg<2, 20, 3>(c, p, n); break;
+    case 3218: e = launch_cfg<2, 18, 3>(c, p, n); break;
+    case 3315: e = launch_cfg<3, 15, 3>(c, p, n); break;
+    case 3411: e = launch_cfg<4, 11, 3>(c, p, n); break;
+#ifdef BPMF_STREAM_PROBES                                    // timing probes: <DBG mask * 10000> + cfg
+    case 13216: e = launch_cfg<2, 16, 3, 1>(c, p, n); break;
+    case 23216: e = launch_cfg<2, 16, 3, 2>(c, p, n); break;
+    case 23220: e = launch_cfg<2, 20, 3, 2>(c, p, n); break;
+    case 43216: e = launch_cfg<2, 16, 3, 4>(c, p, n); break;
+    case 103216: e = launch_cfg<2, 16, 3, 10>(c, p, n); break;
+    case 183216: e = launch_cfg<2, 16, 3, 18>(c, p, n); break;
+    case 343216: e = launch_cfg<2, 16, 3, 34>(c, p, n); break;
+    case 583216: e = launch_cfg<2, 16, 3, 58>(c, p, n); break;
+    case 83216: e = launch_cfg<2, 16, 3, 8>(c, p, n); break;
+    case 163216: e = launch_cfg<2, 16, 3, 16>(c, p, n); break;
+    case 323216: e = launch_cfg<2, 16, 3, 32>(c, p, n); break;
+    case 563216: e = launch_cfg<2, 16, 3, 56>(c, p, n); break;
+#endif
+    default: e = launch_cfg<2, 16, 3>(c, p, n); break;
     }
     c->launches++;
     return e;

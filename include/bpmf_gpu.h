@@ -145,6 +145,8 @@ int bpmf_gpu_last_items_kernel_ms(bpmf_gpu_ctx *ctx, float *ms);
 /* sum of the CUDA-event durations (ms) of the bpmf_gpu_sample_items kernels launched since the previous call
  * of this function, and how many there were (at most the last 128 are kept). Synchronises on them. */
 int bpmf_gpu_items_kernel_time(bpmf_gpu_ctx *ctx, double *total_ms, int *count);
+/* kernel tuning knob of the K == 32 stream kernel: "<version><stages><warps>", e.g. 3216; 0 = default */
+int bpmf_gpu_debug_set_tuning(bpmf_gpu_ctx *ctx, int stream_cfg);
 /* device RNG probes for known-answer tests: n normals of the stream rng_set_pos(c) */
 int bpmf_gpu_debug_randn(bpmf_gpu_ctx *ctx, uint32_t c, int n, double *host_out);
 

@@ -20,7 +20,7 @@ EXE = os.path.join(HOST, "bpmf")
 
 def write_mtx(path, shape, rows, cols, vals):
     with open(path, "w") as f:
-        f.write("%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (shape[0], shape[1], len(vals)))
+        f.write("%%%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (shape[0], shape[1], len(vals)))
         for r, c, v in zip(rows, cols, vals):
             f.write("%d %d %.17g\n" % (r + 1, c + 1, v))
 
