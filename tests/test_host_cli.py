@@ -38,8 +38,13 @@ def exe():
     return EXE
 
 
-@pytest.mark.parametrize("K,shape,nnz,extra", [(32, (300, 200), 6000, []), (10, (4, 2), None, []), (16, (150, 90), 2500, ["-x"])])
+@pytest.mark.parametrize("K,shape,nnz,extra", [(32, (300, 200), 6000, []), (10, (4, 2), None, []), (16, (150, 90), 2500, ["-x"]),
+                                               (32, (500, 310), 9000, ["-g", "2"])])
 def test_cli_matches_oracle(exe, tmp_path, K, shape, nnz, extra):
+    if "-g" in extra:
+        import torch
+        if torch.cuda.device_count() < int(extra[extra.index("-g") + 1]):
+            pytest.skip("needs more GPUs")
     if nnz is None:   # the reference's data/tiny
         train, test = util.TINY_TRAIN, util.TINY_TEST
     else:
