@@ -109,6 +109,8 @@ int bpmf_gpu_create(bpmf_gpu_ctx **out, int device, int num_latent)
     if ((e = cudaMalloc(&ctx->d_err, sizeof(unsigned long long))) != cudaSuccess) return bail(e);
     if ((e = cudaMemset(ctx->d_err, 0, sizeof(unsigned long long))) != cudaSuccess) return bail(e);
     if ((e = cudaMallocHost(&ctx->h_err, sizeof(unsigned long long))) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&ctx->d_zero_row, sizeof(double) * 128)) != cudaSuccess) return bail(e);
+    if ((e = cudaMemset(ctx->d_zero_row, 0, sizeof(double) * 128)) != cudaSuccess) return bail(e);
     if ((e = cudaMallocHost(&ctx->h_pinned, sizeof(double) * (KK + K + 8))) != cudaSuccess) return bail(e);
     for (int i = 0; i < bpmf_gpu_ctx::EV_RING; ++i) {
         if ((e = cudaEventCreate(&ctx->ev0[i])) != cudaSuccess) return bail(e);
@@ -142,7 +144,7 @@ int bpmf_gpu_destroy(bpmf_gpu_ctx *ctx)
     HyperScratch &h = ctx->hs;
     dfree(h.words); dfree(h.acc); dfree(h.rank); dfree(h.pos_of_rank); dfree(h.row_start); dfree(h.row_cls);
     dfree(h.mats); dfree(h.vecs); dfree(h.piv); dfree(h.host_in);
-    dfree(ctx->d_err);
+    dfree(ctx->d_err); dfree(ctx->d_zero_row);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int i = 0; i < bpmf_gpu_ctx::EV_RING; ++i) {

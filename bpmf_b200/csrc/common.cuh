@@ -79,6 +79,7 @@ struct bpmf_gpu_ctx {
     unsigned long long *d_err = nullptr;  // device error word
     unsigned long long *h_err = nullptr;  // pinned host copy
     double *h_pinned = nullptr;           // small pinned staging (K*K + K + 8 doubles)
+    double *d_zero_row = nullptr;         // 128 doubles of zeros (padding rows of the bulk-copy gather)
     // ring of CUDA-event pairs around the item kernels (bench.py reads the per-launch durations from it)
     static constexpr int EV_RING = 128;
     cudaEvent_t ev0[EV_RING] = {}, ev1[EV_RING] = {};

@@ -33,7 +33,8 @@ constexpr int SR = 16;                      // ratings (latent rows) per stage: 
 constexpr int ROWB = 288;                   // bytes per staged row: 256 + 32 pad
 constexpr int W_OFF = SR * ROWB;            // weights (SR doubles)
 constexpr int META_OFF = W_OFF + SR * 8;    // int4 {n, item, first, last}
-constexpr int STAGE_BYTES = META_OFF + 16;
+constexpr int MBAR_OFF = META_OFF + 16;      // one mbarrier per stage (bulk-copy variant)
+constexpr int STAGE_BYTES = META_OFF + 32;
 constexpr int LPACK = 528;                  // packed lower triangle, column-major
 // the tail re-uses the stage it has just consumed as scratch: L (packed) | or, before that, zy, zr, b
 constexpr int ZY_OFF = 0, ZR_OFF = 256, B_OFF = 512;
@@ -59,6 +60,7 @@ struct StreamArgs {
     const double *mu, *LambdaF;
     unsigned int *work_counter;
     unsigned long long *err;
+    const double *zero_row;   // 256 bytes of zeros in global memory (bulk-copy variant: source of the padding rows)
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
@@ -75,6 +77,36 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int sr
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier completion, used by the BULK variant of the v3 kernel
+__device__ __forceinline__ void mbar_init(uint32_t mbar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(mbar), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> this CTA's shared memory, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, unsigned bytes, uint32_t mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 constexpr __host__ __device__ int blk(int I, int J) { return I * (I + 1) / 2 + J; }
 constexpr __host__ __device__ int col_off(int k) { return 32 * k - ((k * (k - 1)) / 2); }
@@ -471,7 +503,9 @@ __device__ __forceinline__ void chol3_block_column(double (&c)[10][2], double &m
 // DBG (bench_micro/tune_stream.py only) is a bit mask: 0 = the product; 1 = no tail (Gram only); 2 = no Gram DMMAs;
 // 4 = no gather (Gram on whatever the stage holds); 8 = no normals; 16 = no factorization; 32 = no triangular solves.
 // Anything but 0 produces garbage: the probes exist to time the parts of the kernel.
-template <int NS, int NW, int DBG>
+// BULK: the gather uses one TMA bulk copy (cp.async.bulk, 256 B) per latent row, issued by the lane that holds the row's
+// index and completed on the stage's mbarrier, instead of sixteen 16-byte cp.async per row spread over half a warp.
+template <int NS, int NW, int DBG, bool BULK>
 __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs p)
 {
     constexpr int WARP_BYTES = warp_bytes<NS>();
@@ -502,8 +536,17 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs
     double n_w = 0.0;
     bool f_done = false;
     const unsigned char *src_lane = reinterpret_cast<const unsigned char *>(p.other) + (lane & 15) * 16;   // this lane's 16 B of a row
-    const uint32_t dst_lane = wbase_s + (lane >> 4) * ROWB + (lane & 15) * 16;
+    const uint32_t dst_lane = BULK ? wbase_s + (lane & 15) * ROWB : wbase_s + (lane >> 4) * ROWB + (lane & 15) * 16;
     const int half = lane >> 4;
+    unsigned phases = 0;                  // BULK: bit h = parity of the phase of stage h the consumer waits for next
+    if (BULK) {
+        if (lane == 0) {
+#pragma unroll 1
+            for (int s = 0; s < NS; ++s) mbar_init(wbase_s + s * STAGE_BYTES + MBAR_OFF, 1);
+        }
+        fence_proxy_async();
+        __syncwarp();
+    }
 
     auto load_next = [&]() {
         const int q = f_pos + (lane & 15);
@@ -534,23 +577,43 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs
         const uint32_t st = dst_lane + slot * STAGE_BYTES;
         unsigned char *stg = wbase + slot * STAGE_BYTES;
         if (f_done) {
-            if (lane == 0) *reinterpret_cast<int4 *>(stg + META_OFF) = make_int4(-1, 0, 0, 0);
-            cp_async_commit();
+            if (lane == 0) {
+                *reinterpret_cast<int4 *>(stg + META_OFF) = make_int4(-1, 0, 0, 0);
+                if (BULK) mbar_arrive_expect_tx(wbase_s + slot * STAGE_BYTES + MBAR_OFF, 0);
+            }
+            if (!BULK) cp_async_commit();
             return;
         }
         const int n = min(SR, f_end - f_pos);
         const int nn = n - half;
+        if (BULK) {
+            // lane r < 16 owns row r of the stage: one 256-byte bulk copy from the row its own index names; the rows that
+            // pad the last group of four come from a row of zeros. The stage was last touched through the generic proxy
+            // (fragment loads, tail scratch), so order those before the async-proxy writes.
+            const uint32_t mbar = wbase_s + slot * STAGE_BYTES + MBAR_OFF;
+            const int n4 = (n + 3) & ~3;
+            fence_proxy_async();
+            if (lane == 0) mbar_arrive_expect_tx(mbar, (unsigned)n4 * 256u);
+            __syncwarp();
+            if (lane < n4 && !(DBG & 4)) {
+                const void *src = (lane < n) ? static_cast<const void *>(p.other + (size_t)(unsigned)n_idx * 32) : static_cast<const void *>(p.zero_row);
+                bulk_g2s(st, src, 256u, mbar);
+            } else if (lane < n4) {
+                bulk_g2s(st, p.zero_row, 256u, mbar);
+            }
+        } else {
 #pragma unroll
-        for (int i = 0; i < SR / 2; ++i) {
-            const unsigned j = (unsigned)__shfl_sync(FULL, n_idx, 2 * i + half);
-            // rows past the item's end are zero-filled (src-size 0 reads nothing; j is still a valid row)
-            if (!(DBG & 4)) cp_async16(st + 2 * i * ROWB, src_lane + (size_t)j * 256, (2 * i < nn) ? 16 : 0);
+            for (int i = 0; i < SR / 2; ++i) {
+                const unsigned j = (unsigned)__shfl_sync(FULL, n_idx, 2 * i + half);
+                // rows past the item's end are zero-filled (src-size 0 reads nothing; j is still a valid row)
+                if (!(DBG & 4)) cp_async16(st + 2 * i * ROWB, src_lane + (size_t)j * 256, (2 * i < nn) ? 16 : 0);
+            }
         }
         // rr weight (v - mean_rating) * alpha (sample.cpp:255)
         if (lane < SR) reinterpret_cast<double *>(stg + W_OFF)[lane] = (lane < n) ? (n_w - p.mean_rating) * p.alpha : 0.0;
         const int last = (f_pos + n == f_end);
         if (lane == 0) *reinterpret_cast<int4 *>(stg + META_OFF) = make_int4(n, g_base + f_it, f_pos == f_start, last);
-        cp_async_commit();
+        if (!BULK) cp_async_commit();
         f_pos += n;
         if (last) {
             ++f_it;
@@ -575,7 +638,12 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs
     int h = 0;
 #pragma unroll 1
     for (;;) {
-        cp_async_wait<NS - 1>();
+        if (BULK) {
+            mbar_wait(wbase_s + h * STAGE_BYTES + MBAR_OFF, (phases >> h) & 1u);
+            phases ^= 1u << h;
+        } else {
+            cp_async_wait<NS - 1>();
+        }
         __syncwarp();
         unsigned char *stg = wbase + h * STAGE_BYTES;
         const int4 meta = *reinterpret_cast<const int4 *>(stg + META_OFF);
@@ -714,7 +782,328 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs
         issue_stage(h);
         h = (h + 1 == NS) ? 0 : h + 1;
     }
-    cp_async_wait<0>();
+    if (!BULK) cp_async_wait<0>();
+}
+
+// =====================================================================================================================
+// Version 4: the same arithmetic as v3 with the two phases in SPECIALISED WARPS of one persistent CTA.
+//   Gram warps (NG)  gather ring + DMMA Gram only. A finished item (the 20 accumulator doubles + 4 rhs partials per lane,
+//                    6 KB, still in the DMMA layout) is handed to a free tail slot in shared memory.
+//   tail warps (NT)  each owns one slot: wait for FULL, pull the accumulators into registers, release the slot, then
+//                    normals + LDL^T + solves + store exactly as v3, in a private scratch.
+// Why: DMMA and scalar fp64 share one pipe per scheduler and a DMMA holds it for 16 cycles, so in v3 every dependent
+// scalar fp64 instruction of a tail queues behind another warp's Gram burst (math_pipe_throttle is the top stall) and the
+// two phases add up instead of overlapping (probes: Gram only 4.74 ms, tail only 5.26 ms, both 8.06 ms). With separate
+// warps the tails' few latency-critical instructions and the Grams' bulk DMMAs interleave; TAIL_HIGH puts the tail
+// warps at the high warp ids, which the issue arbiter favours.
+// Slot protocol (state word per slot in shared memory): 0 EMPTY -> 1 RESERVED (a Gram warp won the CAS and is writing)
+// -> 2 FULL -> 0 ...; 3 EXIT is set by the last Gram warp to finish, only on EMPTY slots.
+// =====================================================================================================================
+constexpr int SLOT_ROWS = 24;                                  // c[10][2] + rrp[4]
+constexpr int SLOT_BYTES = SLOT_ROWS * 32 * 8 + 16;            // + item index
+constexpr int TSCRATCH_BYTES = V3_B_OFF + 256;                 // Lu (packed) | zy | zr | b
+template <int NG, int NT, int NS>
+constexpr __host__ __device__ size_t v4_smem_bytes()
+{
+    return (size_t)SHARED_BYTES + 64 + (size_t)NG * NS * STAGE_BYTES + (size_t)NT * (SLOT_BYTES + TSCRATCH_BYTES);
+}
+
+template <int NG, int NT, int NS, bool TAIL_HIGH, int DBG>
+__global__ void __launch_bounds__((NG + NT) * 32, 1) items_stream32v4_kernel(StreamArgs p)
+{
+    static_assert(NT + 1 <= 16, "state words live in 64 bytes");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    double *sLF = reinterpret_cast<double *>(smem_raw);            // LambdaF(i,k) at sLF[k * LFS + i]
+    double *srr0 = sLF + 32 * LFS;                                 // LambdaF * mu
+    volatile int *sstate = reinterpret_cast<volatile int *>(smem_raw + SHARED_BYTES);   // [NT] slots, [NT] = finished Gram warps
+    unsigned char *rings = smem_raw + SHARED_BYTES + 64;
+    unsigned char *slots = rings + (size_t)NG * NS * STAGE_BYTES;
+    unsigned char *scratch = slots + (size_t)NT * SLOT_BYTES;
+
+    for (int e = tid; e < 1024; e += (NG + NT) * 32) sLF[(e >> 5) * LFS + (e & 31)] = p.LambdaF[e];
+    if (tid < 16) sstate[tid] = 0;
+    __syncthreads();
+    if (tid < 32) {
+        double s = 0.0;
+        for (int j = 0; j < 32; ++j) s += sLF[j * LFS + tid] * p.mu[j];   // rr = LambdaF * hp.mu (sample.cpp:285)
+        srr0[tid] = s;
+    }
+    __syncthreads();
+
+    const bool is_tail = TAIL_HIGH ? (warp >= NG) : (warp < NT);
+
+    if (!is_tail) {
+        // =============================================== Gram warp ===============================================
+        const int gi = TAIL_HIGH ? warp : warp - NT;
+        unsigned char *wbase = rings + (size_t)gi * NS * STAGE_BYTES;
+        const uint32_t wbase_s = (uint32_t)__cvta_generic_to_shared(wbase);
+        int g_base = 0, g_n = 0, f_it = 0;
+        int cpr = 0;                          // per lane: colptr[g_base + lane] - colptr[g_base]
+        int f_pos = 0, f_end = 0, f_start = 0, g_end = 0;
+        const int32_t *g_idx = p.rowidx;
+        const double *g_val = p.val;
+        int32_t n_idx = 0;                    // per lane: index / value of stream position f_pos + (lane & 15): the NEXT stage's
+        double n_w = 0.0;
+        bool f_done = false;
+        const unsigned char *src_lane = reinterpret_cast<const unsigned char *>(p.other) + (lane & 15) * 16;
+        const uint32_t dst_lane = wbase_s + (lane >> 4) * ROWB + (lane & 15) * 16;
+        const int half = lane >> 4;
+        int hint = (gi * NT) / NG;            // where this warp starts looking for an empty slot
+
+        auto load_next = [&]() {
+            const int q = f_pos + (lane & 15);
+            n_idx = 0; n_w = 0.0;
+            if (q < g_end) {
+                n_idx = __ldg(g_idx + q);
+                n_w = __ldg(g_val + q);
+            }
+        };
+        auto claim = [&]() {
+            int base = 0;
+            if (lane == 0) base = p.from + (int)atomicAdd(p.work_counter, (unsigned)CLAIM);
+            base = __shfl_sync(FULL, base, 0);
+            if (base >= p.to) { f_done = true; return; }
+            g_base = base;
+            g_n = min(CLAIM, p.to - base);
+            const int64_t c0 = __ldg(p.colptr + base);
+            cpr = (lane <= g_n) ? (int)(__ldg(p.colptr + base + lane) - c0) : 0;
+            g_idx = p.rowidx + c0;
+            g_val = p.val + c0;
+            f_it = 0;
+            f_start = f_pos = 0;
+            f_end = __shfl_sync(FULL, cpr, 1);
+            g_end = __shfl_sync(FULL, cpr, g_n);
+        };
+        auto issue_stage = [&](int slot) {
+            const uint32_t st = dst_lane + slot * STAGE_BYTES;
+            unsigned char *stg = wbase + slot * STAGE_BYTES;
+            if (f_done) {
+                if (lane == 0) *reinterpret_cast<int4 *>(stg + META_OFF) = make_int4(-1, 0, 0, 0);
+                cp_async_commit();
+                return;
+            }
+            const int n = min(SR, f_end - f_pos);
+            const int nn = n - half;
+#pragma unroll
+            for (int i = 0; i < SR / 2; ++i) {
+                const unsigned j = (unsigned)__shfl_sync(FULL, n_idx, 2 * i + half);
+                if (!(DBG & 4)) cp_async16(st + 2 * i * ROWB, src_lane + (size_t)j * 256, (2 * i < nn) ? 16 : 0);
+            }
+            if (lane < SR) reinterpret_cast<double *>(stg + W_OFF)[lane] = (lane < n) ? (n_w - p.mean_rating) * p.alpha : 0.0;
+            const int last = (f_pos + n == f_end);
+            if (lane == 0) *reinterpret_cast<int4 *>(stg + META_OFF) = make_int4(n, g_base + f_it, f_pos == f_start, last);
+            cp_async_commit();
+            f_pos += n;
+            if (last) {
+                ++f_it;
+                if (f_it >= g_n) claim();
+                else { f_start = f_end; f_end = __shfl_sync(FULL, cpr, f_it + 1); }
+            }
+            if (!f_done) load_next();
+        };
+
+        claim();
+        if (!f_done) load_next();
+#pragma unroll 1
+        for (int s = 0; s < NS; ++s) issue_stage(s);
+
+        double c[10][2];
+        double rrp[4];
+#pragma unroll
+        for (int b = 0; b < 10; ++b) { c[b][0] = 0.0; c[b][1] = 0.0; }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) rrp[a] = 0.0;
+
+        int h = 0;
+#pragma unroll 1
+        for (;;) {
+            cp_async_wait<NS - 1>();
+            __syncwarp();
+            unsigned char *stg = wbase + h * STAGE_BYTES;
+            const int4 meta = *reinterpret_cast<const int4 *>(stg + META_OFF);
+            if (meta.x < 0) break;
+            {
+                const unsigned char *row = stg + t * ROWB + g * 8;
+                const double *wq = reinterpret_cast<const double *>(stg + W_OFF) + t;
+                if (!(DBG & 2)) {
+                    if (meta.x > 0) gram_group(c, rrp, row, wq);
+                    if (meta.x > 4) gram_group(c, rrp, row + 4 * ROWB, wq + 4);
+                    if (meta.x > 8) gram_group(c, rrp, row + 8 * ROWB, wq + 8);
+                    if (meta.x > 12) gram_group(c, rrp, row + 12 * ROWB, wq + 12);
+                } else if (meta.x > 0) {
+                    c[0][0] += *reinterpret_cast<const double *>(row) * *wq;
+                }
+            }
+            __syncwarp();                     // every lane is done reading slot h
+            if (meta.w) {
+                // ---- the item's Gram is complete: hand it to a tail warp
+                int s = 0;
+                if (lane == 0) {
+                    s = hint;
+                    for (;;) {
+                        if (atomicCAS(const_cast<int *>(sstate) + s, 0, 1) == 0) break;
+                        s = (s + 1 == NT) ? 0 : s + 1;
+                        if (s == hint) __nanosleep(64);
+                    }
+                }
+                s = __shfl_sync(FULL, s, 0);
+                hint = (s + 1 == NT) ? 0 : s + 1;
+                double *slot = reinterpret_cast<double *>(slots + (size_t)s * SLOT_BYTES) + lane;
+#pragma unroll
+                for (int b = 0; b < 10; ++b) {
+                    slot[(2 * b) * 32] = c[b][0];
+                    slot[(2 * b + 1) * 32] = c[b][1];
+                    c[b][0] = 0.0; c[b][1] = 0.0;
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a) { slot[(20 + a) * 32] = rrp[a]; rrp[a] = 0.0; }
+                if (lane == 0) *reinterpret_cast<int *>(slots + (size_t)s * SLOT_BYTES + SLOT_ROWS * 32 * 8) = meta.y;
+                __syncwarp();
+                if (lane == 0) { __threadfence_block(); sstate[s] = 2; }
+            }
+            issue_stage(h);
+            h = (h + 1 == NS) ? 0 : h + 1;
+        }
+        cp_async_wait<0>();
+        if (lane == 0) {
+            const int done = atomicAdd(const_cast<int *>(sstate) + NT, 1) + 1;
+            if (done == NG)                   // the last Gram warp tells every tail warp to leave once its slot is empty
+                for (int s = 0; s < NT; ++s)
+                    while (atomicCAS(const_cast<int *>(sstate) + s, 0, 3) != 0) __nanosleep(64);
+        }
+        return;
+    }
+
+    // ================================================= tail warp =================================================
+    const int ti = TAIL_HIGH ? warp - NG : warp;
+    const double *slot = reinterpret_cast<const double *>(slots + (size_t)ti * SLOT_BYTES) + lane;
+    unsigned char *stg = scratch + (size_t)ti * TSCRATCH_BYTES;
+    double *zy = reinterpret_cast<double *>(stg + V3_ZY_OFF), *zr = reinterpret_cast<double *>(stg + V3_ZR_OFF);
+    double *wb = reinterpret_cast<double *>(stg + V3_B_OFF), *Lp = reinterpret_cast<double *>(stg);
+#pragma unroll 1
+    for (;;) {
+        int st = 0;
+        if (lane == 0) {
+            while ((st = sstate[ti]) < 2) __nanosleep(32);
+            __threadfence_block();
+        }
+        st = __shfl_sync(FULL, st, 0);
+        if (st == 3) break;
+        double c[10][2];
+        double rrp[4];
+#pragma unroll
+        for (int b = 0; b < 10; ++b) { c[b][0] = slot[(2 * b) * 32]; c[b][1] = slot[(2 * b + 1) * 32]; }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) rrp[a] = slot[(20 + a) * 32];
+        const int idx = *reinterpret_cast<const int *>(slots + (size_t)ti * SLOT_BYTES + SLOT_ROWS * 32 * 8);
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); sstate[ti] = 0; }   // the slot can take the next item while this one is solved
+        if (DBG & 1) {
+            double acc = 0.0;
+#pragma unroll
+            for (int b = 0; b < 10; ++b) acc += c[b][0] + c[b][1];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) acc += rrp[a];
+            p.items[(size_t)idx * 32 + lane] = acc;
+            continue;
+        }
+        if (!(DBG & 8)) {
+            const uint32_t seed = (uint32_t)(((long long)idx + 1) * 32ll * ((long long)p.iter + 1));
+            int have = 0;
+            for (uint32_t base = 0; have < 32; base += 32) {
+                const U4 bk = stream_block(seed, base + lane);
+                const Polar pa = polar_attempt(bk.v[3], bk.v[2], bk.v[1], bk.v[0]);
+                const unsigned m = __ballot_sync(FULL, pa.ok);
+                const int n = have + __popc(m & ((1u << lane) - 1u));
+                if (pa.ok && n < 32) { zy[n] = pa.y; zr[n] = pa.r2; }
+                have += __popc(m);
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            rrp[a] += __shfl_xor_sync(FULL, rrp[a], 1);
+            rrp[a] += __shfl_xor_sync(FULL, rrp[a], 2);
+        }
+        if (t == 0) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) wb[8 * a + g] = srr0[8 * a + g] + rrp[a];
+        }
+        __syncwarp();
+        const double z = (DBG & 8) ? 0.25 * lane : __dmul_rn(zy[lane], polar_mult(zr[lane]));
+        double bb = wb[lane];
+#pragma unroll
+        for (int I = 0; I < 4; ++I)
+#pragma unroll
+            for (int J = 0; J <= I; ++J)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    c[blk(I, J)][e] = fma(p.alpha, c[blk(I, J)][e], sLF[(8 * J + 2 * t + e) * LFS + 8 * I + g]);
+        double myd = 1.0, myrinv = 1.0;
+        bool ok = true;
+        chol3_block_column<0>(c, myd, myrinv, ok, lane, t);
+        chol3_block_column<1>(c, myd, myrinv, ok, lane, t);
+        chol3_block_column<2>(c, myd, myrinv, ok, lane, t);
+        chol3_block_column<3>(c, myd, myrinv, ok, lane, t);
+        const double myrs = rsqrt(myd);
+        {
+#pragma unroll
+            for (int J = 0; J < 4; ++J)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int k = 8 * J + 2 * t + e;
+                    const double rk = __shfl_sync(FULL, myrinv, k);
+                    double *lq = Lp + (31 * k - ((k * (k - 1)) >> 1)) + g - k - 1;
+#pragma unroll
+                    for (int I = J; I < 4; ++I)
+                        if (I > J || g > 2 * t + e) lq[8 * I] = c[blk(I, J)][e] * rk;
+                }
+        }
+        __syncwarp();
+        if (ok) {
+            {
+                const double *lf = Lp + lane - 1;
+#pragma unroll
+                for (int k = 0; k < 31; ++k) {
+                    const double yk = __shfl_sync(FULL, bb, k);
+                    if (lane > k) bb = fma(-lf[col_off1(k) - k], yk, bb);
+                }
+            }
+            double yv = fma(bb, myrinv, myrs * z);
+            {
+                const double *lb = Lp + (31 * lane - ((lane * (lane - 1)) >> 1)) - lane - 1;
+#pragma unroll
+                for (int i = 31; i >= 1; --i) {
+                    const double xi = __shfl_sync(FULL, yv, i);
+                    if (lane < i) yv = fma(-lb[i], xi, yv);
+                }
+            }
+            p.items[(size_t)idx * 32 + lane] = yv;
+            for (int pr = 0; pr < p.npeers; ++pr) {
+                double *dst = p.peers[pr];
+                if (dst && dst != p.items) dst[(size_t)idx * 32 + lane] = yv;
+            }
+        } else if (lane == 0) {
+            atomicMax(p.err, ERR_CHOLESKY | (unsigned)idx);
+        }
+        __syncwarp();                         // the scratch is free again
+    }
+}
+
+template <int NG, int NT, int NS, bool TAIL_HIGH, int DBG = 0>
+cudaError_t launch_v4(bpmf_gpu_ctx *c, const StreamArgs &p, long long n)
+{
+    constexpr size_t smem = v4_smem_bytes<NG, NT, NS>();
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    auto kern = items_stream32v4_kernel<NG, NT, NS, TAIL_HIGH, DBG>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    long long grid = c->sm_count;                              // persistent: one CTA per SM
+    const long long need = (n + (long long)NG * CLAIM - 1) / ((long long)NG * CLAIM);
+    if (grid > need) grid = need;
+    kern<<<(unsigned)grid, (NG + NT) * 32, smem, c->stream>>>(p);
+    return cudaGetLastError();
 }
 
 template <int NS, int NW, int VER, int DBG = 0>
@@ -722,7 +1111,7 @@ cudaError_t launch_cfg(bpmf_gpu_ctx *c, const StreamArgs &p, long long n)
 {
     constexpr size_t smem = (size_t)NW * warp_bytes<NS>() + SHARED_BYTES;
     static_assert(smem <= 227 * 1024, "shared memory budget");
-    auto kern = VER >= 3 ? items_stream32v3_kernel<NS, NW, DBG> : items_stream32_kernel<NS, NW>;
+    auto kern = VER >= 3 ? items_stream32v3_kernel<NS, NW, DBG, VER == 6> : items_stream32_kernel<NS, NW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     long long grid = c->sm_count;                              // persistent: one CTA per SM
@@ -827,7 +1216,7 @@ cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, doub
     p.other = o.items; p.items = s.items;
     p.npeers = s.npeers; p.peers = s.peers_dev;
     p.mu = s.hp.mu; p.LambdaF = s.hp.LambdaF;
-    p.work_counter = s.work_counter; p.err = c->d_err;
+    p.work_counter = s.work_counter; p.err = c->d_err; p.zero_row = c->d_zero_row;
     cudaError_t e = cudaMemsetAsync(s.work_counter, 0, sizeof(unsigned int), c->stream);
     if (e != cudaSuccess) return e;
     const long long n = (long long)s.to - s.from;
@@ -844,6 +1233,20 @@ cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, doub
     case 3218: e = launch_cfg<2, 18, 3>(c, p, n); break;
     case 3315: e = launch_cfg<3, 15, 3>(c, p, n); break;
     case 3411: e = launch_cfg<4, 11, 3>(c, p, n); break;
+    // 6<NS><NW>: v3 with the TMA bulk-copy gather
+    case 6216: e = launch_cfg<2, 16, 6>(c, p, n); break;
+    case 6220: e = launch_cfg<2, 20, 6>(c, p, n); break;
+    case 6315: e = launch_cfg<3, 15, 6>(c, p, n); break;
+    case 6411: e = launch_cfg<4, 11, 6>(c, p, n); break;
+    // v4: 4<NG><NT><NS> with the tail warps at the high warp ids, 5<NG><NT><NS> with them at the low ids
+    case 48083: e = launch_v4<8, 8, 3, true>(c, p, n); break;
+    case 48082: e = launch_v4<8, 8, 2, true>(c, p, n); break;
+    case 48122: e = launch_v4<8, 12, 2, true>(c, p, n); break;
+    case 58122: e = launch_v4<8, 12, 2, false>(c, p, n); break;
+    case 58083: e = launch_v4<8, 8, 3, false>(c, p, n); break;
+    case 44123: e = launch_v4<4, 12, 3, true>(c, p, n); break;
+    case 46103: e = launch_v4<6, 10, 3, true>(c, p, n); break;
+    case 412082: e = launch_v4<12, 8, 2, true>(c, p, n); break;
 #ifdef BPMF_STREAM_PROBES                                    // timing probes: <DBG mask * 10000> + cfg
     case 13216: e = launch_cfg<2, 16, 3, 1>(c, p, n); break;
     case 23216: e = launch_cfg<2, 16, 3, 2>(c, p, n); break;
@@ -857,6 +1260,12 @@ cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, doub
     case 163216: e = launch_cfg<2, 16, 3, 16>(c, p, n); break;
     case 323216: e = launch_cfg<2, 16, 3, 32>(c, p, n); break;
     case 563216: e = launch_cfg<2, 16, 3, 56>(c, p, n); break;
+    case 16216: e = launch_cfg<2, 16, 6, 1>(c, p, n); break;
+    case 26216: e = launch_cfg<2, 16, 6, 2>(c, p, n); break;
+    case 586216: e = launch_cfg<2, 16, 6, 58>(c, p, n); break;
+    case 148083: e = launch_v4<8, 8, 3, true, 1>(c, p, n); break;
+    case 148122: e = launch_v4<8, 12, 2, true, 1>(c, p, n); break;
+    case 144123: e = launch_v4<4, 12, 3, true, 1>(c, p, n); break;
 #endif
     default: e = launch_cfg<2, 16, 3>(c, p, n); break;
     }
