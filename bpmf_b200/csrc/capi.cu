@@ -219,8 +219,8 @@ int bpmf_gpu_load_side(bpmf_gpu_ctx *ctx, int side, int num_items, int num_other
     CU(cudaMemset(s.cov, 0, sizeof(double) * KK));
     CU(cudaMemset(s.norm, 0, sizeof(double)));
     CU(cudaMalloc(&s.partials, sizeof(double) * (size_t)STATS_BLOCKS * (KK + K + 1)));
-    CU(cudaMalloc(&s.work_counter, sizeof(unsigned int)));
-    CU(cudaMemset(s.work_counter, 0, sizeof(unsigned int)));
+    CU(cudaMalloc(&s.work_counter, 2 * sizeof(unsigned int)));
+    CU(cudaMemset(s.work_counter, 0, 2 * sizeof(unsigned int)));
     s.loaded = true;
     return BPMF_GPU_OK;
 }
@@ -634,7 +634,10 @@ int bpmf_gpu_sample_host(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_v
 int bpmf_gpu_debug_set_tuning(bpmf_gpu_ctx *ctx, int stream_cfg)
 {
     if (!ctx) return BPMF_GPU_EINVAL;
-    ctx->stream_cfg = stream_cfg;
+    // the knob carries two fields: cfg % 1000000 is the kernel configuration, cfg / 1000000 - 1 (when >= 0) the number
+    // of items per warp that are claimed in small groups at the end of a sweep
+    ctx->stream_cfg = stream_cfg % 1000000;
+    ctx->stream_tail = stream_cfg / 1000000 - 1;
     return BPMF_GPU_OK;
 }
 

@@ -87,6 +87,7 @@ struct bpmf_gpu_ctx {
     long long ev_read = 0;       // launches already returned by bpmf_gpu_items_kernel_time
     long long launches = 0;
     int stream_cfg = 0;                   // 0 = default; see launch_items_stream32
+    int stream_tail = -1;                 // items per warp claimed in small groups at the end of a sweep; -1 = default
     std::string err;
     std::vector<void *> ipc_mapped;       // peer allocations opened with cudaIpcOpenMemHandle
 };
