@@ -148,7 +148,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
-    ap.add_argument("--exchange", default="allgather", choices=["allgather", "push"])
+    ap.add_argument("--exchange", default="push", choices=["allgather", "push"])
     ap.add_argument("--variant", default="auto", choices=["auto", "exact", "dmma", "stream"])
     ap.add_argument("--alpha", type=float, default=2.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -5,8 +5,10 @@
 #include "common.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
+#include <utility>
 #include <vector>
 
 using namespace bpmf;
@@ -46,6 +48,7 @@ void free_side(SideDev &s)
     dfree(s.items_own); s.items = nullptr;
     dfree(s.peers_dev);
     dfree(s.hp.mu); dfree(s.hp.LambdaU); dfree(s.hp.LambdaF);
+    dfree(s.hp_next.mu); dfree(s.hp_next.LambdaU); dfree(s.hp_next.LambdaF);
     dfree(s.sum); dfree(s.prod); dfree(s.cov); dfree(s.norm); dfree(s.partials); dfree(s.pred_partials);
     dfree(s.work_counter); dfree(s.aggrMu); dfree(s.aggrLambda);
     s = SideDev();
@@ -116,19 +119,25 @@ int bpmf_gpu_create(bpmf_gpu_ctx **out, int device, int num_latent)
         if ((e = cudaEventCreate(&ctx->ev0[i])) != cudaSuccess) return bail(e);
         if ((e = cudaEventCreate(&ctx->ev1[i])) != cudaSuccess) return bail(e);
     }
-    HyperScratch &h = ctx->hs;
-    // expected consumption is 1.27 (K^2+K) + K/2 blocks; 2 (K^2+4K) + 64 is > 40 standard deviations above it
-    h.nblk = 2 * (KK + 4 * K) + 64;
-    if ((e = cudaMalloc(&h.words, sizeof(uint32_t) * 4 * h.nblk)) != cudaSuccess) return bail(e);
-    if ((e = cudaMalloc(&h.acc, 2 * h.nblk)) != cudaSuccess) return bail(e);
-    if ((e = cudaMalloc(&h.rank, sizeof(int) * 2 * h.nblk)) != cudaSuccess) return bail(e);
-    if ((e = cudaMalloc(&h.pos_of_rank, sizeof(int) * 2 * h.nblk)) != cudaSuccess) return bail(e);
-    if ((e = cudaMalloc(&h.row_start, sizeof(int) * (K + 1))) != cudaSuccess) return bail(e);
-    if ((e = cudaMalloc(&h.row_cls, sizeof(int) * (K + 1))) != cudaSuccess) return bail(e);
-    if ((e = cudaMalloc(&h.mats, sizeof(double) * 6 * KK)) != cudaSuccess) return bail(e);
-    if ((e = cudaMalloc(&h.vecs, sizeof(double) * 4 * K)) != cudaSuccess) return bail(e);
-    if ((e = cudaMalloc(&h.piv, sizeof(int) * K)) != cudaSuccess) return bail(e);
-    if ((e = cudaMalloc(&h.host_in, sizeof(double) * (KK + K))) != cudaSuccess) return bail(e);
+    for (int sd = 0; sd < 2; ++sd) {
+        HyperScratch &h = ctx->hs[sd];
+        // expected consumption is 1.27 (K^2+K) + K/2 blocks; 2 (K^2+4K) + 64 is > 40 standard deviations above it
+        h.nblk = 2 * (KK + 4 * K) + 64;
+        if ((e = cudaMalloc(&h.words, sizeof(uint32_t) * 4 * h.nblk)) != cudaSuccess) return bail(e);
+        if ((e = cudaMalloc(&h.acc, 2 * h.nblk)) != cudaSuccess) return bail(e);
+        if ((e = cudaMalloc(&h.rank, sizeof(int) * 2 * h.nblk)) != cudaSuccess) return bail(e);
+        if ((e = cudaMalloc(&h.pos_of_rank, sizeof(int) * 2 * h.nblk)) != cudaSuccess) return bail(e);
+        if ((e = cudaMalloc(&h.row_start, sizeof(int) * (K + 1))) != cudaSuccess) return bail(e);
+        if ((e = cudaMalloc(&h.row_cls, sizeof(int) * (K + 1))) != cudaSuccess) return bail(e);
+        if ((e = cudaMalloc(&h.mats, sizeof(double) * 6 * KK)) != cudaSuccess) return bail(e);
+        if ((e = cudaMalloc(&h.vecs, sizeof(double) * 4 * K)) != cudaSuccess) return bail(e);
+        if ((e = cudaMalloc(&h.piv, sizeof(int) * K)) != cudaSuccess) return bail(e);
+        if ((e = cudaMalloc(&h.host_in, sizeof(double) * (KK + K))) != cudaSuccess) return bail(e);
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_stats[sd], cudaEventDisableTiming)) != cudaSuccess) return bail(e);
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_hyper[sd], cudaEventDisableTiming)) != cudaSuccess) return bail(e);
+    }
+    if ((e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
+    ctx->overlap_hyper = getenv("BPMF_NO_HYPER_OVERLAP") == nullptr;
     *out = ctx;
     return BPMF_GPU_OK;
 }
@@ -141,9 +150,14 @@ int bpmf_gpu_destroy(bpmf_gpu_ctx *ctx)
     free_side(ctx->side[0]); free_side(ctx->side[1]);
     for (void *m : ctx->ipc_mapped) cudaIpcCloseMemHandle(m);
     ctx->ipc_mapped.clear();
-    HyperScratch &h = ctx->hs;
-    dfree(h.words); dfree(h.acc); dfree(h.rank); dfree(h.pos_of_rank); dfree(h.row_start); dfree(h.row_cls);
-    dfree(h.mats); dfree(h.vecs); dfree(h.piv); dfree(h.host_in);
+    for (int sd = 0; sd < 2; ++sd) {
+        HyperScratch &h = ctx->hs[sd];
+        dfree(h.words); dfree(h.acc); dfree(h.rank); dfree(h.pos_of_rank); dfree(h.row_start); dfree(h.row_cls);
+        dfree(h.mats); dfree(h.vecs); dfree(h.piv); dfree(h.host_in);
+        if (ctx->ev_stats[sd]) cudaEventDestroy(ctx->ev_stats[sd]);
+        if (ctx->ev_hyper[sd]) cudaEventDestroy(ctx->ev_hyper[sd]);
+    }
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     dfree(ctx->d_err); dfree(ctx->d_zero_row);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -183,6 +197,7 @@ int bpmf_gpu_load_side(bpmf_gpu_ctx *ctx, int side, int num_items, int num_other
         if (rowidx[p] < 0 || rowidx[p] >= num_other) return fail(ctx, BPMF_GPU_EINVAL, "row index out of range");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->aux_stream));
     SideDev &s = ctx->side[side];
     free_side(s);
     const int K = ctx->K, KK = K * K;
@@ -210,6 +225,9 @@ int bpmf_gpu_load_side(bpmf_gpu_ctx *ctx, int side, int num_items, int num_other
     CU(cudaMemset(s.hp.mu, 0, sizeof(double) * K));
     CU(cudaMemset(s.hp.LambdaU, 0, sizeof(double) * KK));
     CU(cudaMemset(s.hp.LambdaF, 0, sizeof(double) * KK));
+    CU(cudaMalloc(&s.hp_next.mu, sizeof(double) * K));
+    CU(cudaMalloc(&s.hp_next.LambdaU, sizeof(double) * KK));
+    CU(cudaMalloc(&s.hp_next.LambdaF, sizeof(double) * KK));
     CU(cudaMalloc(&s.sum, sizeof(double) * K));
     CU(cudaMalloc(&s.prod, sizeof(double) * KK));
     CU(cudaMalloc(&s.cov, sizeof(double) * KK));
@@ -399,21 +417,33 @@ int bpmf_gpu_sample_hyper(bpmf_gpu_ctx *ctx, int side, uint32_t iter, const doub
     if (s.num < 1) return fail(ctx, BPMF_GPU_EINVAL, "hyper draw needs at least one item");
     CU(cudaSetDevice(ctx->device));
     const int K = ctx->K, KK = K * K;
+    if (!host_sum && !host_cov && s.pre_iter == (int)iter) {
+        // this iteration's draw was launched right after the previous sweep's reductions (bpmf_gpu_reduce_stats): it has
+        // been running on the auxiliary stream under the other side's sweep. Order the stream after it and swap it in.
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_hyper[side], 0));
+        std::swap(s.hp, s.hp_next);
+        s.pre_iter = -2147483647;
+        return BPMF_GPU_OK;
+    }
+    s.pre_iter = -2147483647;
     const double *d_sum = nullptr, *d_cov = s.cov;
     if (host_sum || host_cov) {
         CU(cudaStreamSynchronize(ctx->stream));  // h_pinned / host_in may still be in use by an earlier call
         if (host_sum) {
             memcpy(ctx->h_pinned, host_sum, sizeof(double) * K);
-            CU(cudaMemcpyAsync(ctx->hs.host_in, ctx->h_pinned, sizeof(double) * K, cudaMemcpyHostToDevice, ctx->stream));
-            d_sum = ctx->hs.host_in;
+            CU(cudaMemcpyAsync(ctx->hs[side].host_in, ctx->h_pinned, sizeof(double) * K, cudaMemcpyHostToDevice, ctx->stream));
+            d_sum = ctx->hs[side].host_in;
         }
         if (host_cov) {
             memcpy(ctx->h_pinned + K, host_cov, sizeof(double) * KK);
-            CU(cudaMemcpyAsync(ctx->hs.host_in + K, ctx->h_pinned + K, sizeof(double) * KK, cudaMemcpyHostToDevice, ctx->stream));
-            d_cov = ctx->hs.host_in + K;
+            CU(cudaMemcpyAsync(ctx->hs[side].host_in + K, ctx->h_pinned + K, sizeof(double) * KK, cudaMemcpyHostToDevice, ctx->stream));
+            d_cov = ctx->hs[side].host_in + K;
         }
     }
-    CU(launch_hyper(ctx, side, iter, d_sum, d_cov));
+    // a stale pre-launched draw of this side may still be running on the auxiliary stream with the same scratch
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_hyper[side], 0));
+    CU(launch_hyper(ctx, side, iter, d_sum, d_cov, false));
+    CU(cudaEventRecord(ctx->ev_hyper[side], ctx->stream));   // orders a later pre-launch (same scratch) after this draw
     return BPMF_GPU_OK;
 }
 
@@ -474,6 +504,15 @@ int bpmf_gpu_reduce_stats(bpmf_gpu_ctx *ctx, int side)
     if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
     CU(cudaSetDevice(ctx->device));
     CU(launch_stats(ctx, side));
+    if (ctx->overlap_hyper && s.num >= 1) {
+        // hp.sample of the NEXT iteration needs only this cov (c++/sample.cpp:350): start it now on the auxiliary stream
+        CU(cudaEventRecord(ctx->ev_stats[side], ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_stats[side], 0));
+        CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_hyper[side], 0));
+        CU(launch_hyper(ctx, side, (uint32_t)(s.iter + 1), nullptr, s.cov, true));
+        CU(cudaEventRecord(ctx->ev_hyper[side], ctx->aux_stream));
+        s.pre_iter = s.iter + 1;
+    }
     return BPMF_GPU_OK;
 }
 

@@ -41,6 +41,8 @@ struct SideDev {          // the device mirror of one Sys (c++/bpmf.h:112-239)
     int npeers = 0;
     double **peers_dev = nullptr;   // device array[MAX_PEERS] of replica pointers
     HyperDev hp;
+    HyperDev hp_next;               // written by the pre-launched draw of the next iteration, swapped in when it is consumed
+    int pre_iter = -2147483647;     // iteration whose hyper-parameters are (being) drawn into hp_next; INT_MIN + 1 = none
     // reductions
     double *sum = nullptr, *prod = nullptr, *cov = nullptr, *norm = nullptr;
     double *partials = nullptr;     // STATS_BLOCKS x (K*K + K + 1)
@@ -75,7 +77,10 @@ struct bpmf_gpu_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     bpmf::SideDev side[2];
-    bpmf::HyperScratch hs;
+    bpmf::HyperScratch hs[2];             // per side: the two sides' draws may be in flight at the same time
+    cudaStream_t aux_stream = nullptr;    // the next iteration's hyper draw runs here, under the other side's sweep
+    cudaEvent_t ev_stats[2] = {}, ev_hyper[2] = {};
+    bool overlap_hyper = true;
     unsigned long long *d_err = nullptr;  // device error word
     unsigned long long *h_err = nullptr;  // pinned host copy
     double *h_pinned = nullptr;           // small pinned staging (K*K + K + 8 doubles)
@@ -95,7 +100,7 @@ struct bpmf_gpu_ctx {
 // ---- launchers implemented in the kernel translation units ------------------------------------
 namespace bpmf {
 // exact_kernels.cu (compiled with -fmad=false)
-cudaError_t launch_hyper(bpmf_gpu_ctx *c, int side, uint32_t iter, const double *d_sum, const double *d_cov);
+cudaError_t launch_hyper(bpmf_gpu_ctx *c, int side, uint32_t iter, const double *d_sum, const double *d_cov, bool ahead);
 cudaError_t launch_items_exact(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha);
 cudaError_t launch_stats(bpmf_gpu_ctx *c, int side);
 cudaError_t launch_predict(bpmf_gpu_ctx *c, int side, int n);

@@ -292,18 +292,22 @@ __global__ void __launch_bounds__(1024) hyper_kernel(HyperArgs a)
     }
 }
 
-cudaError_t launch_hyper(bpmf_gpu_ctx *c, int side, uint32_t iter, const double *d_sum, const double *d_cov)
+// ahead = false: draw into hp on the context's stream. ahead = true: the draw for the NEXT iteration, on the auxiliary
+// stream into hp_next (capi.cu swaps it in when that iteration starts), so it runs under the other side's sweep.
+cudaError_t launch_hyper(bpmf_gpu_ctx *c, int side, uint32_t iter, const double *d_sum, const double *d_cov, bool ahead)
 {
     SideDev &s = c->side[side];
+    const HyperScratch &hs = c->hs[side];
+    const HyperDev &out = ahead ? s.hp_next : s.hp;
     HyperArgs a;
-    a.K = c->K; a.N = s.num; a.nblk = c->hs.nblk; a.iter = iter;
+    a.K = c->K; a.N = s.num; a.nblk = hs.nblk; a.iter = iter;
     a.sum = d_sum; a.cov = d_cov;
-    a.words = c->hs.words; a.acc = c->hs.acc; a.rank = c->hs.rank; a.pos_of_rank = c->hs.pos_of_rank;
-    a.row_start = c->hs.row_start; a.row_cls = c->hs.row_cls; a.piv = c->hs.piv;
-    a.mats = c->hs.mats; a.vecs = c->hs.vecs;
-    a.mu = s.hp.mu; a.LambdaU = s.hp.LambdaU; a.LambdaF = s.hp.LambdaF;
+    a.words = hs.words; a.acc = hs.acc; a.rank = hs.rank; a.pos_of_rank = hs.pos_of_rank;
+    a.row_start = hs.row_start; a.row_cls = hs.row_cls; a.piv = hs.piv;
+    a.mats = hs.mats; a.vecs = hs.vecs;
+    a.mu = out.mu; a.LambdaU = out.LambdaU; a.LambdaF = out.LambdaF;
     a.err = c->d_err;
-    hyper_kernel<<<1, 1024, 0, c->stream>>>(a);
+    hyper_kernel<<<1, 1024, 0, ahead ? c->aux_stream : c->stream>>>(a);
     c->launches++;
     return cudaGetLastError();
 }
