@@ -266,3 +266,45 @@ def test_two_gpus_match_one(gpu, mode):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "identical to single GPU" in r.stdout
+
+
+@pytest.mark.parametrize("name", ["tiny_k10", "synth_k32"])
+def test_chain_matches_committed_golden(gpu, name):
+    """Whole chains through bpmf_gpu_sample / bpmf_gpu_predict against the committed fixtures tests/golden/chain_*.json
+    (no oracle binary involved): per-iteration column means to 1e-10, RMSE to 1e-6 — BASELINE.json's parity gate."""
+    import importlib.util
+    import json
+    import os
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    gold = json.load(open(os.path.join(gdir, "chain_%s.json" % name)))
+    spec_mod = importlib.util.spec_from_file_location("make_chain_golden", os.path.join(gdir, "make_chain_golden.py"))
+    mod = importlib.util.module_from_spec(spec_mod)
+    spec_mod.loader.exec_module(mod)
+    spec = gold["spec"]
+    (shape, rows, cols, vals), (tshape, trows, tcols, tvals) = mod.problem(spec)
+    import scipy.sparse as sp
+    K, burnin = spec["K"], spec["burnin"]
+    R = sp.coo_matrix((vals, (rows, cols)), shape=shape)
+    T = sp.coo_matrix((tvals, (trows, tcols)), shape=tshape)
+    mean = float(np.asarray(vals).sum() / len(vals))
+    ctx = gpu.Context(K)
+    for side, M in ((MOVIES, R.tocsc()), (USERS, R.T.tocsc())):
+        M.sort_indices()
+        ctx.load_side(side, M.shape[1], M.shape[0], M.indptr.astype(np.int64), M.indices.astype(np.int32), M.data, mean)
+    for side, M in ((MOVIES, T.tocsc()), (USERS, T.T.tocsc())):
+        M.sort_indices()
+        ctx.load_test(side, M.indptr.astype(np.int64), M.indices.astype(np.int32), M.data)
+    for g in gold["iterations"]:
+        ctx.sample(MOVIES, 2.0, gpu.KERNEL_AUTO)
+        ctx.sample(USERS, 2.0, gpu.KERNEL_AUTO)
+        rm = ctx.predict(MOVIES, burnin)
+        ctx.predict(USERS, burnin)
+        V, U = ctx.get_items(MOVIES), ctx.get_items(USERS)
+        np.testing.assert_allclose(V.mean(0), g["V_mean"], rtol=0, atol=TOL_ITEMS)
+        np.testing.assert_allclose(U.mean(0), g["U_mean"], rtol=0, atol=TOL_ITEMS)
+        np.testing.assert_allclose(V[0], g["V_first"], rtol=0, atol=TOL_ITEMS * max(1.0, np.abs(g["V_first"]).max()))
+        np.testing.assert_allclose(U[-1], g["U_last"], rtol=0, atol=TOL_ITEMS * max(1.0, np.abs(g["U_last"]).max()))
+        assert abs(rm[0] - g["rmse"]) <= TOL_RMSE and abs(rm[1] - g["rmse_avg"]) <= TOL_RMSE
+    final = ctx.predict(MOVIES, burnin)      # the extra predict of c++/bpmf.cpp:225|242
+    assert abs(final[1] - gold["final_avg_rmse"]) <= TOL_RMSE
+    ctx.close()
