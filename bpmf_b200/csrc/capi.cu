@@ -137,6 +137,10 @@ int bpmf_gpu_create(bpmf_gpu_ctx **out, int device, int num_latent)
         if ((e = cudaEventCreateWithFlags(&ctx->ev_hyper[sd], cudaEventDisableTiming)) != cudaSuccess) return bail(e);
     }
     if ((e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
+    for (int i = 0; i < bpmf_gpu_ctx::HOST_PARTS; ++i)
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_part[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming)) != cudaSuccess) return bail(e);
     ctx->overlap_hyper = getenv("BPMF_NO_HYPER_OVERLAP") == nullptr;
     *out = ctx;
     return BPMF_GPU_OK;
@@ -158,6 +162,10 @@ int bpmf_gpu_destroy(bpmf_gpu_ctx *ctx)
         if (ctx->ev_hyper[sd]) cudaEventDestroy(ctx->ev_hyper[sd]);
     }
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < bpmf_gpu_ctx::HOST_PARTS; ++i)
+        if (ctx->ev_part[i]) cudaEventDestroy(ctx->ev_part[i]);
+    if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
     dfree(ctx->d_err); dfree(ctx->d_zero_row);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -663,10 +671,45 @@ int bpmf_gpu_sample_host(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_v
     const size_t K = (size_t)ctx->K;
     if (host_other_items)   // other.items() lives in host memory in the reference (bpmf.h:193-194)
         CU(cudaMemcpyAsync(o.items, host_other_items, sizeof(double) * K * o.num, cudaMemcpyHostToDevice, ctx->stream));
-    const int rc = bpmf_gpu_sample(ctx, side, alpha, kernel_variant);
+    const int from = s.from, to = s.to;
+    constexpr int P = bpmf_gpu_ctx::HOST_PARTS;
+    if (!host_items || to - from < 16384 * P) {
+        const int rc = bpmf_gpu_sample(ctx, side, alpha, kernel_variant);
+        if (rc) return rc;
+        if (host_items)
+            CU(cudaMemcpyAsync(host_items, s.items, sizeof(double) * K * s.num, cudaMemcpyDeviceToHost, ctx->stream));
+        return check_device_error(ctx);   // synchronises the stream
+    }
+    // Large sweep with a host destination: sample the range in P parts and download each part on the copy stream while
+    // the next one is being sampled, so only the last part's copy is exposed. Same stages as bpmf_gpu_sample.
+    s.iter++;
+    int rc = bpmf_gpu_sample_hyper(ctx, side, (uint32_t)s.iter, nullptr, nullptr);
     if (rc) return rc;
-    if (host_items)
-        CU(cudaMemcpyAsync(host_items, s.items, sizeof(double) * K * s.num, cudaMemcpyDeviceToHost, ctx->stream));
+    if (from > 0)   // items other contexts sample (multi-GPU ranges): current on the device, copied as they are
+        CU(cudaMemcpyAsync(host_items, s.items, sizeof(double) * K * from, cudaMemcpyDeviceToHost, ctx->stream));
+    if (to < s.num)
+        CU(cudaMemcpyAsync(host_items + K * to, s.items + K * to, sizeof(double) * K * (s.num - to), cudaMemcpyDeviceToHost, ctx->stream));
+    for (int part = 0; part < P && !rc; ++part) {
+        const int lo = from + (int)((long long)(to - from) * part / P), hi = from + (int)((long long)(to - from) * (part + 1) / P);
+        s.from = lo; s.to = hi;
+        rc = bpmf_gpu_sample_items(ctx, side, (uint32_t)s.iter, alpha, kernel_variant);
+        if (rc) break;
+        cudaError_t e = cudaEventRecord(ctx->ev_part[part], ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_part[part], 0);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(host_items + K * lo, s.items + K * lo, sizeof(double) * K * (hi - lo), cudaMemcpyDeviceToHost, ctx->copy_stream);
+        if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = BPMF_GPU_ECUDA; }
+    }
+    s.from = from; s.to = to;
+    if (rc) return rc;
+    if (s.aggrMu && s.iter >= s.aggr_burnin) {
+        rc = bpmf_gpu_aggregate(ctx, side);
+        if (rc) return rc;
+    }
+    rc = bpmf_gpu_reduce_stats(ctx, side);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
     return check_device_error(ctx);   // synchronises the stream
 }
 

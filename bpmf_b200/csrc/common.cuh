@@ -81,6 +81,9 @@ struct bpmf_gpu_ctx {
     cudaStream_t aux_stream = nullptr;    // the next iteration's hyper draw runs here, under the other side's sweep
     cudaEvent_t ev_stats[2] = {}, ev_hyper[2] = {};
     bool overlap_hyper = true;
+    cudaStream_t copy_stream = nullptr;   // bpmf_gpu_sample_host: downloads finished item ranges while the rest is sampled
+    static constexpr int HOST_PARTS = 4;
+    cudaEvent_t ev_part[HOST_PARTS] = {}, ev_copied = nullptr;
     unsigned long long *d_err = nullptr;  // device error word
     unsigned long long *h_err = nullptr;  // pinned host copy
     double *h_pinned = nullptr;           // small pinned staging (K*K + K + 8 doubles)

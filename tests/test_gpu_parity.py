@@ -308,3 +308,33 @@ def test_chain_matches_committed_golden(gpu, name):
     final = ctx.predict(MOVIES, burnin)      # the extra predict of c++/bpmf.cpp:225|242
     assert abs(final[1] - gold["final_avg_rmse"]) <= TOL_RMSE
     ctx.close()
+
+
+def test_sample_host_matches_device_resident_sample(gpu):
+    """bpmf_gpu_sample_host (host-resident latent matrices, the e2e path of bench.py) against bpmf_gpu_sample on a second
+    context: bit-identical, for a side small enough for the single-copy path and one large enough for the path that
+    samples in parts and downloads each part while the next is sampled."""
+    import scipy.sparse as sp
+    K = 32
+    train, _ = util.synth_ratings(70000, 500, 400000, 21, skew=0.2)
+    (shape, rows, cols, vals) = train
+    R = sp.coo_matrix((vals, (rows, cols)), shape=shape)
+    mean = float(vals.mean())
+    ctxs = [gpu.Context(K), gpu.Context(K)]
+    for ctx in ctxs:
+        for side, M in ((MOVIES, R.tocsc()), (USERS, R.T.tocsc())):
+            M.sort_indices()
+            ctx.load_side(side, M.shape[1], M.shape[0], M.indptr.astype(np.int64), M.indices.astype(np.int32), M.data, mean)
+    a, b = ctxs
+    host = [np.zeros((500, K)), np.zeros((70000, K))]
+    for it in range(3):
+        for side in (MOVIES, USERS):
+            a.sample(side, 2.0, gpu.KERNEL_AUTO)
+            b.sample_host(side, host[1 - side].ctypes.data, host[side].ctypes.data, 2.0, gpu.KERNEL_AUTO)
+            ref = a.get_items(side)
+            assert host[side].tobytes() == ref.tobytes(), (it, side, np.abs(host[side] - ref).max())
+            assert b.get_items(side).tobytes() == ref.tobytes()
+    sa, sb = a.get_stats(USERS), b.get_stats(USERS)
+    assert sa[2].tobytes() == sb[2].tobytes() and sa[3] == sb[3]
+    for ctx in ctxs:
+        ctx.close()
