@@ -22,7 +22,7 @@ UNITS = [
     ("fast_kernels.cu", []),
     ("stream_kernel.cu", ["-DBPMF_STREAM_PROBES"] if os.environ.get("BPMF_STREAM_PROBES") else []),
 ]
-HEADERS = ["common.cuh", "rng.cuh", os.path.join(ROOT, "include", "bpmf_gpu.h")]
+HEADERS = ["common.cuh", "rng.cuh", "stream_experiments.cuh", os.path.join(ROOT, "include", "bpmf_gpu.h")]
 
 
 def _nvcc():

@@ -12,6 +12,10 @@ constexpr int LPACK = 528;                  // packed lower triangle, column-maj
 constexpr int ZY_OFF = 0, ZR_OFF = 256, B_OFF = 512;
 constexpr __host__ __device__ int col_off(int k) { return 32 * k - ((k * (k - 1)) / 2); }
 static_assert(LPACK * 8 <= STAGE_BYTES && B_OFF + 256 <= STAGE_BYTES, "tail scratch must fit in one stage");
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(mbar) : "memory");
+}
 // the mbarrier gets one arrival from this thread once all cp.async it has issued so far have landed (count pre-accounted)
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t mbar)
 {
@@ -647,7 +651,7 @@ cudaError_t launch_v4(bpmf_gpu_ctx *c, const StreamArgs &p, long long n)
 template <int NM, int NT, int NS>
 constexpr __host__ __device__ size_t v7_smem_bytes()
 {
-    return (size_t)SHARED_BYTES + 64 + 128 + (size_t)NM * NS * STAGE_BYTES + (size_t)NT * (SLOT_BYTES + TSCRATCH_BYTES);
+    return (size_t)SHARED_BYTES + 64 + 128 + 512 + (size_t)NM * NS * STAGE_BYTES + (size_t)NT * (SLOT_BYTES + TSCRATCH_BYTES);
 }
 
 template <int NM, int NT, int NS, int DBG>
@@ -662,13 +666,19 @@ __global__ void __launch_bounds__((2 * NM + NT) * 32, 1) items_stream32v7_kernel
     double *srr0 = sLF + 32 * LFS;                                 // LambdaF * mu
     volatile int *sstate = reinterpret_cast<volatile int *>(smem_raw + SHARED_BYTES);        // [NT] slots, [NT] = finished MMA warps
     volatile int *sflag = reinterpret_cast<volatile int *>(smem_raw + SHARED_BYTES + 64);    // [NM][NS] stage flags
-    unsigned char *rings = smem_raw + SHARED_BYTES + 64 + 128;
+    // mbarriers: [NM][NS] "stage empty" (MMA warp -> producer) at +0, [NT] "slot full" (MMA warp -> tail warp) at +256
+    const uint32_t bars = (uint32_t)__cvta_generic_to_shared(smem_raw + SHARED_BYTES + 64 + 128);
+    unsigned char *rings = smem_raw + SHARED_BYTES + 64 + 128 + 512;
     unsigned char *slots = rings + (size_t)NM * NS * STAGE_BYTES;
     unsigned char *scratch = slots + (size_t)NT * SLOT_BYTES;
 
     for (int e = tid; e < 1024; e += (2 * NM + NT) * 32) sLF[(e >> 5) * LFS + (e & 31)] = p.LambdaF[e];
     if (tid < 16) sstate[tid] = 0;
     if (tid < 32) sflag[tid] = 0;
+    if (tid == 0) {
+        for (int i = 0; i < NM * NS; ++i) mbar_init(bars + i * 8, 1);
+        for (int i = 0; i < NT; ++i) mbar_init(bars + 256 + i * 8, 1);
+    }
     __syncthreads();
     if (tid < 32) {
         double s = 0.0;
@@ -685,7 +695,6 @@ __global__ void __launch_bounds__((2 * NM + NT) * 32, 1) items_stream32v7_kernel
         const int gi = warp - NM;
         unsigned char *wbase = rings + (size_t)gi * NS * STAGE_BYTES;
         const uint32_t wbase_s = (uint32_t)__cvta_generic_to_shared(wbase);
-        volatile int *flag = sflag + gi * NS;
         int g_base = 0, g_n = 0, f_it = 0;
         int cpr = 0;
         int f_pos = 0, f_end = 0, f_start = 0, g_end = 0;
@@ -746,7 +755,8 @@ __global__ void __launch_bounds__((2 * NM + NT) * 32, 1) items_stream32v7_kernel
         Plan plan[PF];
 #pragma unroll
         for (int k = 0; k < PF; ++k) plan[k] = plan_next();
-        int s_issue = 0;
+        int s_issue = 0, issued = 0;
+        unsigned ephase = 0;                  // bit s: parity of the "empty" phase of stage s to wait for next
         bool done = false;
 #pragma unroll 1
         while (!done) {
@@ -755,11 +765,12 @@ __global__ void __launch_bounds__((2 * NM + NT) * 32, 1) items_stream32v7_kernel
                 if (done) break;
                 const Plan cur = plan[k];
                 plan[k] = plan_next();
-                // wait until the MMA warp has released the stage, then mark it as being filled
-                if (lane == 0) {
-                    while (flag[s_issue] != 0) __nanosleep(20);
-                    flag[s_issue] = 1;
+                // wait until the MMA warp has released the stage (the first NS uses find it empty)
+                if (issued >= NS) {
+                    mbar_wait(bars + (gi * NS + s_issue) * 8, (ephase >> s_issue) & 1u);
+                    ephase ^= 1u << s_issue;
                 }
+                ++issued;
                 __syncwarp();
                 const uint32_t st = dst_lane + s_issue * STAGE_BYTES;
                 unsigned char *stg = wbase + s_issue * STAGE_BYTES;
@@ -791,7 +802,6 @@ __global__ void __launch_bounds__((2 * NM + NT) * 32, 1) items_stream32v7_kernel
         // =============================================== MMA warp ===============================================
         const int gi = warp;
         unsigned char *wbase = rings + (size_t)gi * NS * STAGE_BYTES;
-        volatile int *flag = sflag + gi * NS;
         int hint = (gi * NT) / NM;
         double c[10][2];
         double rrp[4];
@@ -828,7 +838,7 @@ __global__ void __launch_bounds__((2 * NM + NT) * 32, 1) items_stream32v7_kernel
                 }
             }
             __syncwarp();                     // every lane is done reading the stage
-            if (lane == 0) { __threadfence_block(); flag[h] = 0; }
+            if (lane == 0) mbar_arrive(bars + (gi * NS + h) * 8);
             h = (h + 1 == NS) ? 0 : h + 1;
             if (meta.w) {
                 // ---- the item's Gram is complete: hand it to a tail warp
@@ -854,14 +864,16 @@ __global__ void __launch_bounds__((2 * NM + NT) * 32, 1) items_stream32v7_kernel
                 for (int a = 0; a < 4; ++a) { slot[(20 + a) * 32] = rrp[a]; rrp[a] = 0.0; }
                 if (lane == 0) *reinterpret_cast<int *>(slots + (size_t)s * SLOT_BYTES + SLOT_ROWS * 32 * 8) = meta.y;
                 __syncwarp();
-                if (lane == 0) { __threadfence_block(); sstate[s] = 2; }
+                if (lane == 0) { sstate[s] = 2; mbar_arrive(bars + 256 + s * 8); }
             }
         }
         if (lane == 0) {
             const int done = atomicAdd(const_cast<int *>(sstate) + NT, 1) + 1;
             if (done == NM)                   // the last MMA warp tells every tail warp to leave once its slot is empty
-                for (int s = 0; s < NT; ++s)
+                for (int s = 0; s < NT; ++s) {
                     while (atomicCAS(const_cast<int *>(sstate) + s, 0, 3) != 0) __nanosleep(64);
+                    mbar_arrive(bars + 256 + s * 8);
+                }
         }
         return;
     }
@@ -873,13 +885,11 @@ __global__ void __launch_bounds__((2 * NM + NT) * 32, 1) items_stream32v7_kernel
     double *zy = reinterpret_cast<double *>(stg + V3_ZY_OFF), *zr = reinterpret_cast<double *>(stg + V3_ZR_OFF);
     double *wb = reinterpret_cast<double *>(stg + V3_B_OFF), *Lp = reinterpret_cast<double *>(stg);
 #pragma unroll 1
+    unsigned fphase = 0;
     for (;;) {
-        int st = 0;
-        if (lane == 0) {
-            while ((st = sstate[ti]) < 2) __nanosleep(32);
-            __threadfence_block();
-        }
-        st = __shfl_sync(FULL, st, 0);
+        mbar_wait(bars + 256 + ti * 8, fphase);
+        fphase ^= 1u;
+        const int st = sstate[ti];
         if (st == 3) break;
         double c[10][2];
         double rrp[4];
