@@ -52,6 +52,7 @@ SYMBOLS = {
     "bpmf_gpu_predict": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                    C.POINTER(C.c_int64)]),
     "bpmf_gpu_get_predictions": (C.c_int, [C.c_void_p, C.c_int, _f64p, _f64p]),
+    "bpmf_gpu_set_prop_posterior": (C.c_int, [C.c_void_p, C.c_int, _opt, _opt]),
     "bpmf_gpu_enable_aggregation": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "bpmf_gpu_aggregate": (C.c_int, [C.c_void_p, C.c_int]),
     "bpmf_gpu_get_aggregates": (C.c_int, [C.c_void_p, C.c_int, _f64p, _f64p]),
@@ -231,6 +232,12 @@ class Context:
         a, b = np.empty(n), np.empty(n)
         self._ck(self.L.bpmf_gpu_get_predictions(self.h, side, a, b))
         return a, b
+
+    def set_prop_posterior(self, side, mu, lam):
+        """per-item priors of -m / -l: mu [item, K] (unused by the draw, like the reference), lam [item, K*K]"""
+        mu = None if mu is None else np.ascontiguousarray(mu, np.float64)
+        lam = None if lam is None else np.ascontiguousarray(lam, np.float64)
+        self._ck(self.L.bpmf_gpu_set_prop_posterior(self.h, side, _ptr(mu), _ptr(lam)))
 
     def enable_aggregation(self, side, burnin): self._ck(self.L.bpmf_gpu_enable_aggregation(self.h, side, burnin))
     def aggregate(self, side): self._ck(self.L.bpmf_gpu_aggregate(self.h, side))

@@ -50,7 +50,7 @@ void free_side(SideDev &s)
     dfree(s.hp.mu); dfree(s.hp.LambdaU); dfree(s.hp.LambdaF);
     dfree(s.hp_next.mu); dfree(s.hp_next.LambdaU); dfree(s.hp_next.LambdaF);
     dfree(s.sum); dfree(s.prod); dfree(s.cov); dfree(s.norm); dfree(s.partials); dfree(s.pred_partials);
-    dfree(s.work_counter); dfree(s.aggrMu); dfree(s.aggrLambda);
+    dfree(s.work_counter); dfree(s.aggrMu); dfree(s.aggrLambda); dfree(s.propLambda);
     s = SideDev();
 }
 
@@ -73,9 +73,10 @@ int check_device_error(bpmf_gpu_ctx *ctx)
     return fail(ctx, BPMF_GPU_ECUDA, b);
 }
 
-int pick_variant(const bpmf_gpu_ctx *ctx, int v)
+int pick_variant(const bpmf_gpu_ctx *ctx, int side, int v)
 {
-    if (v == BPMF_GPU_KERNEL_AUTO) return ctx->K == 32 ? BPMF_GPU_KERNEL_STREAM : BPMF_GPU_KERNEL_EXACT;
+    // per-item prior precisions (propagated posterior) are only read by the any-K kernel
+    if (v == BPMF_GPU_KERNEL_AUTO) return (ctx->K == 32 && !ctx->side[side].propLambda) ? BPMF_GPU_KERNEL_STREAM : BPMF_GPU_KERNEL_EXACT;
     return v;
 }
 
@@ -489,7 +490,8 @@ int bpmf_gpu_sample_items(bpmf_gpu_ctx *ctx, int side, uint32_t iter, double alp
     if (!s.loaded || !o.loaded) return fail(ctx, BPMF_GPU_EINVAL, "both sides must be loaded");
     if (s.num_other != o.num) return fail(ctx, BPMF_GPU_EINVAL, "sides disagree on dimensions");
     CU(cudaSetDevice(ctx->device));
-    const int v = pick_variant(ctx, kernel_variant);
+    const int v = pick_variant(ctx, side, kernel_variant);
+    if (s.propLambda && v != BPMF_GPU_KERNEL_EXACT) return fail(ctx, BPMF_GPU_EINVAL, "a propagated posterior needs the EXACT (or AUTO) kernel variant");
     const int slot = (int)(ctx->ev_count % bpmf_gpu_ctx::EV_RING);
     CU(cudaEventRecord(ctx->ev0[slot], ctx->stream));
     if (v == BPMF_GPU_KERNEL_EXACT) CU(launch_items_exact(ctx, side, iter, alpha));
@@ -553,6 +555,22 @@ int bpmf_gpu_sample(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_varian
         if (rc) return rc;
     }
     return bpmf_gpu_reduce_stats(ctx, side);                              // :379-384
+}
+
+int bpmf_gpu_set_prop_posterior(bpmf_gpu_ctx *ctx, int side, const double *host_mu, const double *host_Lambda)
+{
+    (void)host_mu;   // read and shape-checked by the reference, never used in the draw (c++/sample.cpp:285, quirk Q5)
+    if (!ctx || !side_ok(side)) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    dfree(s.propLambda);
+    if (!host_Lambda) return BPMF_GPU_OK;
+    const size_t n = sizeof(double) * (size_t)ctx->K * ctx->K * (size_t)(s.num > 0 ? s.num : 1);
+    CU(cudaMalloc(&s.propLambda, n));
+    CU(cudaMemcpy(s.propLambda, host_Lambda, sizeof(double) * (size_t)ctx->K * ctx->K * s.num, cudaMemcpyHostToDevice));
+    return BPMF_GPU_OK;
 }
 
 int bpmf_gpu_enable_aggregation(bpmf_gpu_ctx *ctx, int side, int burnin)

@@ -48,6 +48,8 @@ struct SideDev {          // the device mirror of one Sys (c++/bpmf.h:112-239)
     double *partials = nullptr;     // STATS_BLOCKS x (K*K + K + 1)
     double *pred_partials = nullptr;
     int pred_blocks = 0;
+    // propagated posterior (-m / -l): per-item prior precision K*K x num, nullptr = none (bpmf_gpu_set_prop_posterior)
+    double *propLambda = nullptr;
     // posterior aggregation (-o): K x num and K*K x num, allocated by bpmf_gpu_enable_aggregation
     double *aggrMu = nullptr, *aggrLambda = nullptr;
     int aggr_burnin = 0;

@@ -327,6 +327,7 @@ struct ItemArgs {
     int npeers;
     double *const *peers;
     const double *mu, *LambdaF;
+    const double *propLambda;   // K*K x num per-item prior precisions (-m / -l, sample.cpp:272-277) or nullptr
     unsigned int *work_counter;
     unsigned long long *err;
 };
@@ -354,10 +355,12 @@ __global__ void items_exact_kernel(ItemArgs p)
         // rng_set_pos((idx+1) * num_latent * (iter+1))  (sample.cpp:266), uint32 truncation
         const uint32_t c = (uint32_t)(((long long)idx + 1) * (long long)K * ((long long)p.iter + 1));
         if (tid < 32) warp_randn(c, K, z);
-        // rr = LambdaF * hp.mu (sample.cpp:285); MM = 0
+        // hp_LambdaF: the item's propagated posterior precision if there is one (sample.cpp:272-283)
+        const double *LF = p.propLambda ? p.propLambda + (size_t)idx * KK : p.LambdaF;
+        // rr = hp_LambdaF * hp.mu (sample.cpp:285; the global mu even with a propagated posterior, quirk Q5); MM = 0
         for (int a = tid; a < K; a += T) {
             double s = 0.0;
-            for (int j = 0; j < K; ++j) s += p.LambdaF[a + j * K] * p.mu[j];
+            for (int j = 0; j < K; ++j) s += LF[a + j * K] * p.mu[j];
             rr[a] = s;
         }
         for (int e = tid; e < KK; e += T) MM[e] = 0.0;
@@ -390,7 +393,7 @@ __global__ void items_exact_kernel(ItemArgs p)
         // lower triangle of MM = LambdaF + alpha * MM (sample.cpp:297-298); the LLT only reads the lower part
         for (int e = tid; e < KK; e += T) {
             const int a = e % K, b = e / K;
-            if (a >= b) MM[a + b * K] = p.LambdaF[a + b * K] + p.alpha * MM[b + a * K];
+            if (a >= b) MM[a + b * K] = LF[a + b * K] + p.alpha * MM[b + a * K];
         }
         __syncthreads();
         // chol.compute(MM) (sample.cpp:306): right-looking, per-element update order j = 0..k-1 as in the oracle
@@ -451,7 +454,7 @@ cudaError_t launch_items_exact(bpmf_gpu_ctx *c, int side, uint32_t iter, double 
     p.colptr = s.colptr; p.rowidx = s.rowidx; p.val = s.val;
     p.other = o.items; p.items = s.items;
     p.npeers = s.npeers; p.peers = s.peers_dev;
-    p.mu = s.hp.mu; p.LambdaF = s.hp.LambdaF;
+    p.mu = s.hp.mu; p.LambdaF = s.hp.LambdaF; p.propLambda = s.propLambda;
     p.work_counter = s.work_counter; p.err = c->d_err;
     cudaError_t e = cudaMemsetAsync(s.work_counter, 0, sizeof(unsigned int), c->stream);
     if (e != cudaSuccess) return e;

@@ -130,6 +130,7 @@ void CUDA_Sys::alloc_and_init()
         check(c, bpmf_gpu_load_test(c, s, T.colptr.data(), T.rowidx.data(), T.val.data()), "load_test");
         check(c, bpmf_gpu_set_range(c, s, gpu_dom[(size_t)g], gpu_dom[(size_t)g + 1]), "set_range");
         if (Sys::odirname.size()) check(c, bpmf_gpu_enable_aggregation(c, s, Sys::burnin), "enable_aggregation");
+        if (has_prop_posterior()) check(c, bpmf_gpu_set_prop_posterior(c, s, propMu.data(), propLambda.data()), "set_prop_posterior");
     }
     if (ngpus > 1) {
         std::vector<double *> reps((size_t)ngpus, nullptr);

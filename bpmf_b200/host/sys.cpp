@@ -62,8 +62,8 @@ Sys::Sys(std::string name_, const SparseMatrixD &Mt, const SparseMatrixD &Pt)
 
 Sys::~Sys() {}
 
-// c++/sample.cpp:157-174. The files are read and checked like the reference does; the device path does not consume
-// them yet, so a run that passes -m / -l stops here instead of silently ignoring the priors.
+// c++/sample.cpp:157-174: the propagated posterior of an earlier run (its U-mu / U-Lambda outputs) as per-item priors.
+// The back end uploads propLambda in alloc_and_init (bpmf_gpu_set_prop_posterior).
 void Sys::add_prop_posterior(std::string fnames)
 {
     if (fnames.empty()) return;
@@ -75,7 +75,6 @@ void Sys::add_prop_posterior(std::string fnames)
     if (propMu.cols() != num() || propLambda.cols() != num()) THROWERROR("propagated posterior: wrong number of columns");
     if (propMu.rows() != num_latent || propLambda.rows() != (int64_t)num_latent * num_latent)
         THROWERROR("propagated posterior: wrong number of rows");
-    THROWERROR("propagated posterior priors (-m / -l) are not supported by the CUDA back end yet");
 }
 
 // c++/sample.cpp:179-226 (items().setZero() happens in the back end, which owns items_ptr)

@@ -100,7 +100,7 @@ struct Sys {
     const double *items() const { return items_ptr; }
     const double *items_col(long i) const { return items_ptr + i * num_latent; }
 
-    //-- propagated posterior (-m / -l): read and checked like the reference, not yet used by the device path
+    //-- propagated posterior (-m / -l): per-item priors, uploaded by the back end
     DenseMatrixD propMu, propLambda;
     void add_prop_posterior(std::string);
     bool has_prop_posterior() const { return propMu.nonZeros() > 0; }

@@ -129,6 +129,13 @@ int bpmf_gpu_get_stats(bpmf_gpu_ctx *ctx, int side, double *sum, double *prod, d
 int bpmf_gpu_predict(bpmf_gpu_ctx *ctx, int side, int burnin, double *rmse, double *rmse_avg, int64_t *num_predict);
 int bpmf_gpu_get_predictions(bpmf_gpu_ctx *ctx, int side, double *pavg, double *pm2);
 
+/* ---- propagated posterior of -m / -l (c++/sample.cpp:152-174,272-283) -------------------------------------------
+ * Per-item prior precisions: Lambda is K*K x num_items (item i's K x K matrix, column-major, at Lambda + i*K*K), what
+ * Sys::add_prop_posterior reads into propLambda. mu (K x num_items) is accepted for symmetry with the reference, which
+ * reads and checks propMu but draws with the global hp.mu (c++/sample.cpp:285). host_Lambda == NULL removes the prior.
+ * Items are then sampled by the any-K kernel (KERNEL_AUTO picks it). */
+int bpmf_gpu_set_prop_posterior(bpmf_gpu_ctx *ctx, int side, const double *host_mu, const double *host_Lambda);
+
 /* ---- posterior aggregation of -o (c++/sample.cpp:195-199,364-368; read back for c++/bpmf.cpp:229-239) ----
  * After _enable_aggregation, every bpmf_gpu_sample whose iteration is >= burnin adds r to aggrMu.col(i) and
  * vec(r r^T) to aggrLambda.col(i) for the items of [from,to) (K*num + K*K*num doubles of device memory).

@@ -369,6 +369,10 @@ struct Side {
     int64_t num_predict = 0;
     bool keep_aggr = false, no_covariance = false;
     std::vector<double> aggrMu, aggrLambda;
+    // propagated posterior (-m / -l, sample.cpp:152-174): per-item prior precision K*K x num(); propMu is read and
+    // checked by the reference but never used in the draw (quirk Q5: rr = hp_LambdaF * hp.mu uses the GLOBAL mu)
+    std::vector<double> propMu, propLambda;
+    bool has_prop_posterior() const { return !propMu.empty(); }
     // last sweep's raw reductions (exposed for parity tests of the device reductions)
     std::vector<double> last_sum, last_prod;
 
@@ -396,10 +400,12 @@ struct Side {
     void sample_item(Rng &rng, long idx, const Side &other, double alpha, double *rr, double *MM) const
     {
         rng.set_pos((uint32_t)((idx + 1) * (long)K * (long)(iter + 1)));  // :266, 64-bit product truncated
-        // rr = LambdaF * hp.mu  (:285)
+        // hp_LambdaF = propLambda.col(idx) with a propagated posterior, else hp.LambdaF (:272-283)
+        const double *LF = has_prop_posterior() ? &propLambda[(size_t)idx * K * K] : hp.LambdaF.data();
+        // rr = hp_LambdaF * hp.mu  (:285; hp.mu, not hp_mu: quirk Q5)
         for (int i = 0; i < K; ++i) {
             double s = 0.0;
-            for (int j = 0; j < K; ++j) s += hp.LambdaF[i + j * K] * hp.mu[j];
+            for (int j = 0; j < K; ++j) s += LF[i + j * K] * hp.mu[j];
             rr[i] = s;
         }
         std::fill(MM, MM + (size_t)K * K, 0.0);
@@ -416,7 +422,7 @@ struct Side {
         // mirror upper -> lower, MM = LambdaF + alpha * MM (:297-298)
         for (int b = 0; b < K; ++b)
             for (int a = b + 1; a < K; ++a) MM[a + b * K] = MM[b + a * K];
-        for (size_t e = 0; e < (size_t)K * K; ++e) MM[e] = hp.LambdaF[e] + alpha * MM[e];
+        for (size_t e = 0; e < (size_t)K * K; ++e) MM[e] = LF[e] + alpha * MM[e];
         if (no_covariance)  // BPMF_NO_COVARIANCE (:300-304)
             for (int b = 0; b < K; ++b)
                 for (int a = 0; a < K; ++a)

@@ -66,6 +66,7 @@ def lib():
     L.bpmf_oracle_get_pred.argtypes = [C.c_void_p, C.c_int, _f64p, _f64p]
     L.bpmf_oracle_get_csc.argtypes = [C.c_void_p, C.c_int, C.c_int, _i64p, _i32p, _f64p]
     L.bpmf_oracle_get_aggr.argtypes = [C.c_void_p, C.c_int, _f64p, _f64p]
+    L.bpmf_oracle_set_prop.argtypes = [C.c_void_p, C.c_int, _f64p, _f64p]
     _lib = L
     return L
 
@@ -194,6 +195,13 @@ class Oracle:
         val = np.zeros(n, np.float64)
         lib().bpmf_oracle_get_csc(self._h, side, which, colptr, rowidx, val)
         return colptr, rowidx, val
+
+    def set_prop(self, side, mu, lam):
+        """propagated posterior of -m / -l: mu [item, K], lam [item, K*K] (column-major K x K per item)"""
+        mu = np.ascontiguousarray(mu, np.float64)
+        lam = np.ascontiguousarray(lam, np.float64)
+        assert mu.shape == (self.num(side), self.K) and lam.shape == (self.num(side), self.K * self.K)
+        lib().bpmf_oracle_set_prop(self._h, side, mu.reshape(-1), lam.reshape(-1))
 
     def aggr(self, side):
         K, n = self.K, self.num(side)

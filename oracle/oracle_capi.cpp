@@ -195,6 +195,14 @@ void bpmf_oracle_get_aggr(void *h, int side, double *aggrMu, double *aggrLambda)
     if (aggrMu) std::memcpy(aggrMu, s.aggrMu.data(), sizeof(double) * s.aggrMu.size());
     if (aggrLambda) std::memcpy(aggrLambda, s.aggrLambda.data(), sizeof(double) * s.aggrLambda.size());
 }
+// add_prop_posterior (sample.cpp:157-174): mu is K x num, lambda K*K x num, both item-major
+void bpmf_oracle_set_prop(void *h, int side, const double *mu, const double *lambda)
+{
+    Side &s = side_of(h, side);
+    s.propMu.assign(mu, mu + (size_t)s.K * s.num());
+    s.propLambda.assign(lambda, lambda + (size_t)s.K * s.K * s.num());
+}
+
 int bpmf_oracle_max_threads()
 {
 #ifdef _OPENMP

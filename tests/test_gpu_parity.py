@@ -338,3 +338,34 @@ def test_sample_host_matches_device_resident_sample(gpu):
     assert sa[2].tobytes() == sb[2].tobytes() and sa[3] == sb[3]
     for ctx in ctxs:
         ctx.close()
+
+
+@pytest.mark.parametrize("K", [16, 32])
+def test_propagated_posterior_priors(gpu, K):
+    """-m / -l (c++/sample.cpp:152-174,272-283): per-item prior precisions replace hp.LambdaF, the rhs still uses the
+    GLOBAL hp.mu (quirk Q5). Device (any-K kernel, picked by KERNEL_AUTO) against the oracle."""
+    train, test = util.synth_ratings(120, 90, 2500, 5 + K)
+    orc = util.make_oracle(K, train, test)
+    ctx = util.make_gpu_from_oracle(orc, K)
+    _prime(orc, ctx, K, 17)
+    rng = np.random.default_rng(K)
+    for side in (MOVIES, USERS):
+        n = orc.num(side)
+        lam = np.stack([util.random_spd(K, 1000 * side + i, scale=2.0).T.reshape(-1) for i in range(n)])
+        mu = rng.normal(size=(n, K))
+        orc.set_prop(side, mu, lam)
+        ctx.set_prop_posterior(side, mu, lam)
+    for side, it in ((MOVIES, 2), (USERS, 2), (MOVIES, 3)):
+        orc.set_iter(side, it)
+        orc.sample_range(side, 0, orc.num(side))
+        ctx.sample_items(side, it, 2.0, gpu.KERNEL_AUTO)
+        got, ref = ctx.get_items(side), orc.items(side)
+        assert np.abs(got - ref).max() <= TOL_EXACT * 50 * max(1.0, np.abs(ref).max()), (side, it)
+        ctx.set_items(side, ref)
+    if K == 32:   # the tensor-core kernels read the shared LambdaF only: asking for them with a prior is an error
+        with pytest.raises(gpu.BpmfGpuError):
+            ctx.sample_items(MOVIES, 4, 2.0, gpu.KERNEL_STREAM)
+    ctx.set_prop_posterior(MOVIES, None, None)          # priors removed: back to the fast kernel
+    ctx.sample_items(MOVIES, 4, 2.0, gpu.KERNEL_STREAM if K == 32 else gpu.KERNEL_AUTO)
+    ctx.sync()
+    ctx.close()

@@ -105,3 +105,37 @@ def test_cli_usage_errors(exe, tmp_path):
     assert subprocess.run([exe], capture_output=True).returncode != 0          # no arguments: usage + abort
     res = subprocess.run([exe, "-n", str(tmp_path / "nope.mtx"), "-p", str(tmp_path / "nope.mtx")], capture_output=True)
     assert res.returncode != 0
+
+
+def test_cli_propagated_posterior(exe, tmp_path):
+    """-m MU,LAMBDA (movies) and -l MU,LAMBDA (users): per-item priors read from .ddm files (c++/bpmf.cpp:134-135,
+    c++/sample.cpp:157-174) — the chained-run mechanism of the reference — against the oracle with the same priors."""
+    K = 16
+    train, test = util.synth_ratings(80, 60, 1500, 77)
+    write_mtx(tmp_path / "train.mtx", *train)
+    write_mtx(tmp_path / "test.mtx", *test)
+    out = tmp_path / "out"
+    out.mkdir()
+    orc = util.make_oracle(K, train, test, alpha=2.0, burnin=1)
+    rng = np.random.default_rng(3)
+    args = []
+    for flag, side, name in (("-m", util.MOVIES, "V"), ("-l", util.USERS, "U")):
+        n = orc.num(side)
+        lam = np.stack([util.random_spd(K, 50 * side + i, scale=1.5).T.reshape(-1) for i in range(n)])
+        mu = rng.normal(size=(n, K))
+        orc.set_prop(side, mu, lam)
+        for tag, a in (("mu", mu), ("Lambda", lam)):
+            with open(tmp_path / ("%s-%s.ddm" % (name, tag)), "wb") as f:
+                f.write(struct.pack("<QQ", a.shape[1], a.shape[0]) + np.ascontiguousarray(a, "<f8").tobytes())
+        args += [flag, "%s,%s" % (tmp_path / (name + "-mu.ddm"), tmp_path / (name + "-Lambda.ddm"))]
+    nsims = 3
+    cmd = [exe, "-n", str(tmp_path / "train.mtx"), "-p", str(tmp_path / "test.mtx"), "-i", str(nsims), "-b", "1", "-d", str(K),
+           "-v", "-o", str(out)] + args
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert "with propagated posterior" in res.stdout
+    for it in range(nsims):
+        orc.iterate()
+        for name, side in (("V", util.MOVIES), ("U", util.USERS)):
+            got, ref = read_ddm(out / ("%s-%d.ddm" % (name, it))), orc.items(side)
+            assert np.abs(got - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max()), (it, name)
