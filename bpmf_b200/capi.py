@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libbpmf_b200.so")
 
 MOVIES, USERS = 0, 1
-KERNEL_AUTO, KERNEL_EXACT, KERNEL_DMMA, KERNEL_STREAM = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_EXACT, KERNEL_DMMA, KERNEL_STREAM, KERNEL_BLOCK = 0, 1, 2, 3, 4
 
 _f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 _i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")

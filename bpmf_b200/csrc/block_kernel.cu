@@ -1,0 +1,384 @@
+// block_kernel.cu — the fused per-item conditional update (c++/sample.cpp:263-336 + 248-258) for num_latent = 16 * m
+// other than 32 (16, 48, 64, 80, 96, 112, 128) on sm_100a: ONE CTA PER ITEM, NB/2 warps (NB = K / 8).
+//
+//   gather  The K-vectors of the item's ratings are staged global -> shared with cp.async in stages of 16 rows (row pitch
+//           8K + 32 bytes: conflict-free fragment loads), two stages in flight, every thread copying four 16-byte chunks.
+//   Gram    fp64 tensor cores (mma.sync.m8n8k4, DMMA). The lower triangle of NB x NB blocks of 8 x 8 is spread over the
+//           warps' REGISTERS: warp w owns block rows w and NB-1-w (NB + 1 blocks, 2 NB + 2 accumulator doubles per
+//           lane). Per four ratings it loads NB - w fragments and issues NB + 1 DMMAs; the rhs costs 2 DFMAs.
+//   tail    MM = LambdaF + alpha G goes to shared memory as 8 x 8 row-major TILES of the lower block triangle (they alias
+//           the gather ring, idle by then). Blocked right-looking LDL^T: per block column every warp factorises the diagonal
+//           tile redundantly in registers (warp shuffles, as the K = 32 kernel does) together with its share of the panel
+//           tiles, the trailing tiles are updated with DMMAs (fragments straight from the tiles: a row-major tile IS the
+//           C fragment layout, and its rows are A/B fragments). The unit-lower factor is stored divided by the pivots, so
+//           the two triangular solves (warp 0, right-hand side in registers) are shuffle + FMA chains; K normals from
+//           Philox4x32-10 (rng.cuh).
+// Algorithmic bytes: 8K per rating. The Gram needs (NB+1) NB / 2 DMMAs per four ratings: at K = 128 that is 16.4 kflop per
+// gathered KB, so the kernel is bound by the fp64 tensor pipe (37 TFLOP/s), not by HBM.
+#include "common.cuh"
+#include "rng.cuh"
+
+namespace bpmf {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int SR = 16;   // ratings per stage
+constexpr int NS = 2;    // stages in flight
+
+struct BlockArgs {
+    int from, to;
+    uint32_t iter;
+    double alpha, mean_rating;
+    const int64_t *colptr;
+    const int32_t *rowidx;
+    const double *val;
+    const double *other;
+    double *items;
+    int npeers;
+    double *const *peers;
+    const double *mu, *LambdaF;
+    unsigned int *work_counter;
+    unsigned long long *err;
+};
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+template <int NB>
+struct Cfg {
+    static constexpr int K = 8 * NB, NWB = NB / 2, T = 32 * NWB;
+    static constexpr int ROWB = 8 * K + 32;                       // bytes per staged row
+    static constexpr int STAGE = SR * ROWB;                       // rows only; weights live apart
+    static constexpr int NTILE = NB * (NB + 1) / 2;               // 8 x 8 tiles of the lower block triangle, 512 B each
+    static constexpr int BIG = (NS * STAGE > NTILE * 512) ? NS * STAGE : NTILE * 512;   // ring and tiles alias each other
+    // layout: [BIG][w: NS*SR][z: K][b: K][rr0: K][d: K][rinv: K][ints: 4]
+    static constexpr int W_OFF = BIG, Z_OFF = W_OFF + NS * SR * 8, B_OFF = Z_OFF + K * 8, RR0_OFF = B_OFF + K * 8;
+    static constexpr int D_OFF = RR0_OFF + K * 8, RI_OFF = D_OFF + K * 8, INT_OFF = RI_OFF + K * 8, SMEM = INT_OFF + 16;
+    __host__ __device__ static constexpr int tile(int I, int J) { return (I * (I + 1) / 2 + J) * 64; }   // doubles
+};
+
+// 1 / p for a positive normal p: MUFU.RCP64H seed + one cubic step (same as the K = 32 kernel)
+__device__ __forceinline__ double fast_rcp(double p)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(p));
+    const double e = fma(-p, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
+}
+
+// The Gram of one item for warp W (compile-time, so that the accumulators are registers): block rows W and NB-1-W.
+template <int NB, int W>
+__device__ __forceinline__ void item_gram(const BlockArgs &p, unsigned char *smem, int64_t ps, int64_t pe, double *MMp, double *rr)
+{
+    using C = Cfg<NB>;
+    constexpr int K = C::K, T = C::T, R0 = W, R1 = NB - 1 - W, NF = NB - W;   // fragments f[0 .. NF-1] cover both rows
+    const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(smem);
+    double *sw = reinterpret_cast<double *>(smem + C::W_OFF);
+    double c0[R0 + 1][2], c1[R1 + 1][2], r0 = 0.0, r1 = 0.0;
+#pragma unroll
+    for (int j = 0; j <= R0; ++j) { c0[j][0] = 0.0; c0[j][1] = 0.0; }
+#pragma unroll
+    for (int j = 0; j <= R1; ++j) { c1[j][0] = 0.0; c1[j][1] = 0.0; }
+
+    const int nst = (int)((pe - ps + SR - 1) / SR);
+    // this thread's four 16-byte chunks of a stage: rows rq, rq + 4, rq + 8, rq + 12, chunk cq of the row
+    const int rq = tid / (K / 2), cq = tid % (K / 2);
+    auto issue = [&](int s) {
+        if (s < nst) {
+            const int64_t p0 = ps + (int64_t)s * SR;
+            const int slot = s % NS;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = rq + 4 * j;
+                const bool live = p0 + r < pe;
+                const unsigned row = live ? (unsigned)__ldg(p.rowidx + p0 + r) : 0u;
+                cp_async16(ring_s + slot * C::STAGE + r * C::ROWB + cq * 16,
+                           reinterpret_cast<const unsigned char *>(p.other) + (size_t)row * (K * 8) + cq * 16, live ? 16 : 0);
+            }
+            if (tid < SR) sw[slot * SR + tid] = (p0 + tid < pe) ? (__ldg(p.val + p0 + tid) - p.mean_rating) * p.alpha : 0.0;
+        }
+        cp_async_commit();
+    };
+#pragma unroll 1
+    for (int s = 0; s < NS; ++s) issue(s);
+#pragma unroll 1
+    for (int s = 0; s < nst; ++s) {
+        cp_async_wait<NS - 1>();
+        __syncthreads();
+        const unsigned char *stg = smem + (s % NS) * C::STAGE;
+        const int left = (int)min((int64_t)SR, pe - (ps + (int64_t)s * SR));
+#pragma unroll 1
+        for (int q = 0; q * 4 < left; ++q) {
+            const unsigned char *row = stg + (4 * q + t) * C::ROWB + g * 8;
+            double f[NF];
+#pragma unroll
+            for (int j = 0; j < NF; ++j) f[j] = *reinterpret_cast<const double *>(row + j * 64);
+            const double w = sw[(s % NS) * SR + 4 * q + t];
+#pragma unroll
+            for (int j = 0; j <= R0; ++j) dmma884(c0[j][0], c0[j][1], f[R0], f[j]);
+#pragma unroll
+            for (int j = 0; j <= R1; ++j) dmma884(c1[j][0], c1[j][1], f[R1], f[j]);
+            r0 = fma(f[R0], w, r0);
+            r1 = fma(f[R1], w, r1);
+        }
+        __syncthreads();                  // the slot is free
+        issue(s + NS);
+    }
+    cp_async_wait<0>();
+    __syncthreads();                      // the ring is dead: MM may overwrite it
+    // MM = LambdaF + alpha * G (sample.cpp:297-298) into the tiles: lane (g, t) owns elements (g, 2t) and (g, 2t + 1)
+    auto put = [&](int I, int J, const double (&cc)[2]) {
+        const int i = 8 * I + g, k = 8 * J + 2 * t;
+        double2 v;
+        v.x = fma(p.alpha, cc[0], __ldg(p.LambdaF + i + (size_t)k * K));
+        v.y = fma(p.alpha, cc[1], __ldg(p.LambdaF + i + (size_t)(k + 1) * K));
+        *reinterpret_cast<double2 *>(MMp + C::tile(I, J) + 8 * g + 2 * t) = v;
+    };
+#pragma unroll
+    for (int j = 0; j <= R0; ++j) put(R0, j, c0[j]);
+#pragma unroll
+    for (int j = 0; j <= R1; ++j) put(R1, j, c1[j]);
+    // rhs: sum over the quad's four ratings-of-a-group, + LambdaF * mu (sample.cpp:285), which the caller put into rr
+    r0 += __shfl_xor_sync(FULL, r0, 1); r0 += __shfl_xor_sync(FULL, r0, 2);
+    r1 += __shfl_xor_sync(FULL, r1, 1); r1 += __shfl_xor_sync(FULL, r1, 2);
+    if (t == 0) { rr[8 * R0 + g] += r0; rr[8 * R1 + g] += r1; }
+}
+
+template <int NB>
+__global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB >= 6 ? 4 : 8)) items_block_kernel(BlockArgs p)
+{
+    using C = Cfg<NB>;
+    constexpr int K = C::K, T = C::T, NWB = C::NWB;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *MMp = reinterpret_cast<double *>(smem);
+    double *z = reinterpret_cast<double *>(smem + C::Z_OFF), *b = reinterpret_cast<double *>(smem + C::B_OFF);
+    double *rr0 = reinterpret_cast<double *>(smem + C::RR0_OFF);
+    double *sd = reinterpret_cast<double *>(smem + C::D_OFF), *srinv = reinterpret_cast<double *>(smem + C::RI_OFF);
+    const int g = lane >> 2, t = lane & 3;
+    int *sint = reinterpret_cast<int *>(smem + C::INT_OFF);   // [0] item, [1] failed
+
+    for (int a = tid; a < K; a += T) {    // LambdaF * hp.mu, the same for every item
+        double s = 0.0;
+        for (int j = 0; j < K; ++j) s += __ldg(p.LambdaF + a + (size_t)j * K) * __ldg(p.mu + j);
+        rr0[a] = s;
+    }
+#pragma unroll 1
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) { sint[0] = p.from + (int)atomicAdd(p.work_counter, 1u); sint[1] = 0; }
+        __syncthreads();
+        const int idx = sint[0];
+        if (idx >= p.to) break;
+        for (int a = tid; a < K; a += T) b[a] = rr0[a];
+        // the K normals of this item: rng_set_pos((idx+1) * K * (iter+1)) (sample.cpp:266)
+        if (warp == NWB - 1) warp_randn((uint32_t)(((long long)idx + 1) * (long long)K * ((long long)p.iter + 1)), K, z);
+        __syncthreads();
+        const int64_t ps = __ldg(p.colptr + idx), pe = __ldg(p.colptr + idx + 1);
+        switch (warp) {                   // accumulators must be registers: one instantiation per warp role
+        case 0: item_gram<NB, 0>(p, smem, ps, pe, MMp, b); break;
+        case 1: if constexpr (NWB > 1) item_gram<NB, 1>(p, smem, ps, pe, MMp, b); break;
+        case 2: if constexpr (NWB > 2) item_gram<NB, 2>(p, smem, ps, pe, MMp, b); break;
+        case 3: if constexpr (NWB > 3) item_gram<NB, 3>(p, smem, ps, pe, MMp, b); break;
+        case 4: if constexpr (NWB > 4) item_gram<NB, 4>(p, smem, ps, pe, MMp, b); break;
+        case 5: if constexpr (NWB > 5) item_gram<NB, 5>(p, smem, ps, pe, MMp, b); break;
+        case 6: if constexpr (NWB > 6) item_gram<NB, 6>(p, smem, ps, pe, MMp, b); break;
+        default: if constexpr (NWB > 7) item_gram<NB, 7>(p, smem, ps, pe, MMp, b); break;
+        }
+        __syncthreads();
+        // ---- chol.compute(MM) (sample.cpp:306) as MM = Lu D Lu^T, blocked by 8, on the tiles
+#pragma unroll 1
+        for (int kb = 0; kb < NB; ++kb) {
+            // every warp: the diagonal tile (redundantly) + its share of the panel tiles below it (I = I0, I0 + NWB)
+            const double2 d2 = *reinterpret_cast<const double2 *>(MMp + C::tile(kb, kb) + 8 * g + 2 * t);
+            double dg[2] = {d2.x, d2.y};
+            const int I0 = kb + 1 + ((warp - (kb + 1)) % NWB + NWB) % NWB;
+            double pt[2][2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int I = I0 + u * NWB;
+                double2 v = make_double2(0.0, 0.0);
+                if (I < NB) v = *reinterpret_cast<const double2 *>(MMp + C::tile(I, kb) + 8 * g + 2 * t);
+                pt[u][0] = v.x; pt[u][1] = v.y;
+            }
+            double myd = 1.0, myrinv = 1.0;   // lane k < 8 ends up with d_k and 1 / d_k of this block column
+            bool ok = true;
+#pragma unroll 1
+            for (int k2 = 0; k2 < 4; ++k2) {
+                const int qsrc = (lane & ~3) | k2;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int k = 2 * k2 + e;
+                    const double pv = __shfl_sync(FULL, dg[e], 4 * k + k2);          // pivot: lane (g = k, t = k2), register e
+                    double bl0 = __shfl_sync(FULL, dg[e], 4 * (2 * t) + k2);         // a[2t][k], a[2t+1][k] (unscaled)
+                    double bl1 = __shfl_sync(FULL, dg[e], 4 * (2 * t + 1) + k2);
+                    const double ad = __shfl_sync(FULL, dg[e], qsrc);                // a[g][k] of the diagonal tile
+                    const double a0 = __shfl_sync(FULL, pt[0][e], qsrc), a1 = __shfl_sync(FULL, pt[1][e], qsrc);
+                    if (!(pv > 0.0)) ok = false;                                     // pivot <= 0 -> "Cholesky failed"
+                    const double rinv = fast_rcp(pv);
+                    if (lane == k) { myd = pv; myrinv = rinv; }
+                    bl0 = (2 * t > k) ? -(bl0 * rinv) : 0.0;
+                    bl1 = (2 * t + 1 > k) ? -(bl1 * rinv) : 0.0;
+                    dg[0] = fma(ad, bl0, dg[0]); dg[1] = fma(ad, bl1, dg[1]);
+                    pt[0][0] = fma(a0, bl0, pt[0][0]); pt[0][1] = fma(a0, bl1, pt[0][1]);
+                    pt[1][0] = fma(a1, bl0, pt[1][0]); pt[1][1] = fma(a1, bl1, pt[1][1]);
+                }
+            }
+            // store the unit-lower factor divided by the pivots (Lu = A~ D^-1) back into the tiles
+            const double rv0 = __shfl_sync(FULL, myrinv, 2 * t), rv1 = __shfl_sync(FULL, myrinv, 2 * t + 1);
+            if (warp == 0) {
+                if (lane < 8) { sd[8 * kb + lane] = myd; srinv[8 * kb + lane] = myrinv; }
+                if (!ok && lane == 0) sint[1] = 1;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int I = I0 + u * NWB;
+                if (I < NB) *reinterpret_cast<double2 *>(MMp + C::tile(I, kb) + 8 * g + 2 * t) = make_double2(pt[u][0] * rv0, pt[u][1] * rv1);
+            }
+            __syncthreads();
+            // (only now: the other warps read the unfactored diagonal tile at the top of this iteration)
+            if (warp == 0) *reinterpret_cast<double2 *>(MMp + C::tile(kb, kb) + 8 * g + 2 * t) = make_double2(dg[0] * rv0, dg[1] * rv1);
+            // trailing tiles (I, J), kb < J <= I:  A(I,J) -= Lu(I,kb) D Lu(J,kb)^T  on the tensor cores, tiles dealt round-robin
+            if (kb + 1 < NB) {
+                const double dc0 = sd[8 * kb + t], dc1 = sd[8 * kb + 4 + t];
+                // tile number e (row-major over the trailing triangle) belongs to warp e % NWB: walk e = warp, warp + NWB, ...
+                int I = kb + 1, J = kb + 1 + warp;
+                while (J > I) { J -= I - kb; ++I; }          // row I holds I - kb tiles (J = kb+1 .. I)
+                while (I < NB) {
+                    const double *ta = MMp + C::tile(I, kb) + 8 * g + t;
+                    const double *tb = MMp + C::tile(J, kb) + 8 * g + t;
+                    double2 *tc = reinterpret_cast<double2 *>(MMp + C::tile(I, J) + 8 * g + 2 * t);
+                    double2 cv = *tc;
+                    dmma884(cv.x, cv.y, -ta[0], tb[0] * dc0);
+                    dmma884(cv.x, cv.y, -ta[4], tb[4] * dc1);
+                    *tc = cv;
+                    J += NWB;
+                    while (I < NB && J > I) { J -= I - kb; ++I; }
+                }
+            }
+            __syncthreads();
+        }
+        if (sint[1]) {                    // THROWERROR("Cholesky failed") (sample.cpp:308)
+            if (tid == 0) atomicMax(p.err, ERR_CHOLESKY | (unsigned)idx);
+            continue;
+        }
+        // ---- L \ rr; rr += nrandn; L^T \ rr (sample.cpp:321-323) with L = Lu D^(1/2):  x = Lu^-T (D^-1 Lu^-1 b + D^(-1/2) z)
+        // by warp 0, the vector in registers: lane holds rows lane + 32 r. Lu(i,k) = tile(i / 8, k / 8)[8 (i % 8) + k % 8].
+        if (warp == 0) {
+            constexpr int R = (K + 31) / 32;
+            double v[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[r] = (lane + 32 * r < K) ? b[lane + 32 * r] : 0.0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+#pragma unroll 4
+                for (int kk = 0; kk < 32; ++kk) {
+                    const int k = 32 * r + kk;
+                    if (k >= K) break;
+                    const double yk = __shfl_sync(FULL, v[r], kk);
+#pragma unroll
+                    for (int r2 = r; r2 < R; ++r2) {
+                        const int i = lane + 32 * r2;
+                        if (i > k && i < K) v[r2] = fma(-MMp[C::tile(i >> 3, k >> 3) + 8 * (i & 7) + (k & 7)], yk, v[r2]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int i = lane + 32 * r;
+                if (i < K) v[r] = fma(v[r], srinv[i], rsqrt(sd[i]) * z[i]);
+            }
+#pragma unroll
+            for (int r = R - 1; r >= 0; --r) {
+#pragma unroll 4
+                for (int kk = 31; kk >= 0; --kk) {
+                    const int k = 32 * r + kk;
+                    if (k >= K) continue;
+                    const double xk = __shfl_sync(FULL, v[r], kk);
+#pragma unroll
+                    for (int r2 = 0; r2 <= r; ++r2) {
+                        const int i = lane + 32 * r2;
+                        if (i < k) v[r2] = fma(-MMp[C::tile(k >> 3, i >> 3) + 8 * (k & 7) + (i & 7)], xk, v[r2]);
+                    }
+                }
+            }
+            // items().col(idx) = rr (sample.cpp:324), and into every peer replica (replaces send_item)
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int i = lane + 32 * r;
+                if (i < K) {
+                    p.items[(size_t)idx * K + i] = v[r];
+                    for (int q = 0; q < p.npeers; ++q)
+                        if (p.peers[q] && p.peers[q] != p.items) p.peers[q][(size_t)idx * K + i] = v[r];
+                }
+            }
+        }
+    }
+}
+
+template <int NB>
+cudaError_t launch_nb(bpmf_gpu_ctx *c, const BlockArgs &p, long long n)
+{
+    using C = Cfg<NB>;
+    static_assert(C::SMEM <= 227 * 1024, "shared memory budget");
+    auto kern = items_block_kernel<NB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) return e;
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::T, C::SMEM);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)c->sm_count * per_sm;
+    if (grid > n) grid = n;
+    kern<<<(unsigned)grid, C::T, C::SMEM, c->stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+bool block_kernel_supports(int K) { return K % 16 == 0 && K >= 16 && K <= 128 && K != 32; }
+
+cudaError_t launch_items_block(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha)
+{
+    SideDev &s = c->side[side];
+    const SideDev &o = c->side[1 - side];
+    BlockArgs p;
+    p.from = s.from; p.to = s.to; p.iter = iter; p.alpha = alpha; p.mean_rating = s.mean_rating;
+    p.colptr = s.colptr; p.rowidx = s.rowidx; p.val = s.val;
+    p.other = o.items; p.items = s.items;
+    p.npeers = s.npeers; p.peers = s.peers_dev;
+    p.mu = s.hp.mu; p.LambdaF = s.hp.LambdaF;
+    p.work_counter = s.work_counter; p.err = c->d_err;
+    cudaError_t e = cudaMemsetAsync(s.work_counter, 0, sizeof(unsigned int), c->stream);
+    if (e != cudaSuccess) return e;
+    const long long n = (long long)s.to - s.from;
+    if (n < 1) return cudaSuccess;
+    switch (c->K) {
+    case 16: e = launch_nb<2>(c, p, n); break;
+    case 48: e = launch_nb<6>(c, p, n); break;
+    case 64: e = launch_nb<8>(c, p, n); break;
+    case 80: e = launch_nb<10>(c, p, n); break;
+    case 96: e = launch_nb<12>(c, p, n); break;
+    case 112: e = launch_nb<14>(c, p, n); break;
+    case 128: e = launch_nb<16>(c, p, n); break;
+    default: return cudaErrorInvalidValue;
+    }
+    c->launches++;
+    return e;
+}
+
+}  // namespace bpmf

@@ -76,7 +76,11 @@ int check_device_error(bpmf_gpu_ctx *ctx)
 int pick_variant(const bpmf_gpu_ctx *ctx, int side, int v)
 {
     // per-item prior precisions (propagated posterior) are only read by the any-K kernel
-    if (v == BPMF_GPU_KERNEL_AUTO) return (ctx->K == 32 && !ctx->side[side].propLambda) ? BPMF_GPU_KERNEL_STREAM : BPMF_GPU_KERNEL_EXACT;
+    if (v == BPMF_GPU_KERNEL_AUTO) {
+        if (ctx->side[side].propLambda) return BPMF_GPU_KERNEL_EXACT;
+        if (ctx->K == 32) return BPMF_GPU_KERNEL_STREAM;
+        return block_kernel_supports(ctx->K) ? BPMF_GPU_KERNEL_BLOCK : BPMF_GPU_KERNEL_EXACT;
+    }
     return v;
 }
 
@@ -501,6 +505,9 @@ int bpmf_gpu_sample_items(bpmf_gpu_ctx *ctx, int side, uint32_t iter, double alp
     } else if (v == BPMF_GPU_KERNEL_STREAM) {
         if (ctx->K != 32) return fail(ctx, BPMF_GPU_EINVAL, "the stream kernel is built for num_latent == 32");
         CU(launch_items_stream32(ctx, side, iter, alpha));
+    } else if (v == BPMF_GPU_KERNEL_BLOCK) {
+        if (!block_kernel_supports(ctx->K)) return fail(ctx, BPMF_GPU_EINVAL, "the block kernel is built for num_latent = 16, 48, 64, 80, 96, 112, 128");
+        CU(launch_items_block(ctx, side, iter, alpha));
     } else return fail(ctx, BPMF_GPU_EINVAL, "unknown kernel variant");
     CU(cudaEventRecord(ctx->ev1[slot], ctx->stream));
     ctx->ev_count++;

@@ -114,6 +114,9 @@ cudaError_t launch_debug_randn(bpmf_gpu_ctx *c, uint32_t seed, int n, double *d_
 size_t exact_items_smem_bytes(int K);
 // fast_kernels.cu
 cudaError_t launch_items_dmma32(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha);
+// block_kernel.cu
+bool block_kernel_supports(int K);
+cudaError_t launch_items_block(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha);
 // stream_kernel.cu
 cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha);
 cudaError_t launch_stats_partial32(bpmf_gpu_ctx *c, int side);

@@ -540,7 +540,8 @@ cudaError_t launch_cfg(bpmf_gpu_ctx *c, const StreamArgs &p, long long n)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     long long grid = c->sm_count;                              // persistent: one CTA per SM
-    const long long need = (n + (long long)NW * CLAIM - 1) / ((long long)NW * CLAIM);
+    // small sweeps are claimed CLAIM_TAIL items at a time (bulk_end == from): enough CTAs for every claim to find a warp
+    const long long need = (n + (long long)NW * CLAIM_TAIL - 1) / ((long long)NW * CLAIM_TAIL);
     if (grid > need) grid = need;
     kern<<<(unsigned)grid, NW * 32, smem, c->stream>>>(p);
     return cudaGetLastError();

@@ -42,7 +42,8 @@ extern "C" {
 #define BPMF_GPU_KERNEL_AUTO 0   /* fastest available for this K                                          */
 #define BPMF_GPU_KERNEL_EXACT 1  /* any K; reference summation order, no FMA contraction (debug / fallback) */
 #define BPMF_GPU_KERNEL_DMMA 2   /* K == 32: warp per item, fp64 tensor-core (DMMA) Gram, registers         */
-#define BPMF_GPU_KERNEL_STREAM 3 /* K == 32: persistent, cp.async-staged gather ring, DMMA Gram + blocked Cholesky */
+#define BPMF_GPU_KERNEL_STREAM 3 /* K == 32: persistent, cp.async-staged gather ring, DMMA Gram + blocked LDL^T in registers */
+#define BPMF_GPU_KERNEL_BLOCK 4  /* K = 16 m, K != 32, K <= 128: one CTA per item, DMMA Gram in registers, tail in shared memory */
 
 typedef struct bpmf_gpu_ctx bpmf_gpu_ctx;
 

@@ -94,17 +94,22 @@ CASES = [
     (32, 500, 64, 4000, dict(skew=1.2, empty_rows=40, heavy_col=450)),   # empty rows, a hot column > 32*k
     (16, 120, 90, 1500, {}),
     (64, 90, 70, 2500, {}),
+    (48, 150, 40, 2000, dict(skew=1.0, empty_rows=10, heavy_col=120)),
+    (128, 60, 50, 1800, dict(heavy_col=55)),
 ]
 
 
-VARIANTS = {"exact": 1, "dmma": 2, "stream": 3}
+VARIANTS = {"exact": 1, "dmma": 2, "stream": 3, "block": 4}
+BLOCK_K = (16, 48, 64, 80, 96, 112, 128)
 
 
 @pytest.mark.parametrize("K,nr,nc,nnz,kw", CASES)
-@pytest.mark.parametrize("variant", ["exact", "dmma", "stream"])
+@pytest.mark.parametrize("variant", ["exact", "dmma", "stream", "block"])
 def test_item_update_one_sweep(gpu, K, nr, nc, nnz, kw, variant):
-    if variant != "exact" and K != 32:
-        pytest.skip("the tensor-core kernels are K == 32")
+    if variant in ("dmma", "stream") and K != 32:
+        pytest.skip("the warp-per-item tensor-core kernels are K == 32")
+    if variant == "block" and K not in BLOCK_K:
+        pytest.skip("the CTA-per-item tensor-core kernel is K = 16 m, K != 32")
     v = VARIANTS[variant]
     tol = TOL_EXACT if variant == "exact" else TOL_ITEMS
     train, test = util.synth_ratings(nr, nc, nnz, 7 + K, **kw)
@@ -186,6 +191,14 @@ def test_full_run_movielens_shaped_k32(gpu, variant):
     train, test = util.synth_ratings(943, 1682, 110000, 2026, rank=10, skew=0.7, test_frac=0.2)
     worst = _run_both(gpu, 32, train, test, 20, 5, v)
     print("worst latent deviation over 20 iterations (%s): %.3e" % (variant, worst))
+
+
+@pytest.mark.parametrize("K", [16, 64, 128])
+def test_full_run_block_kernel(gpu, K):
+    # the CTA-per-item kernel (KERNEL_AUTO picks it for these K): whole chains incl. hyper draw, stats, predict
+    train, test = util.synth_ratings(400, 250, 12000, 31 + K, rank=6, skew=0.6, empty_rows=15, heavy_col=200)
+    worst = _run_both(gpu, K, train, test, 8, 3, gpu.KERNEL_AUTO)
+    print("worst latent deviation over 8 iterations (K=%d): %.3e" % (K, worst))
 
 
 def test_full_run_chembl_shaped_k32(gpu):
