@@ -289,19 +289,23 @@ def main():
                 if world == 1:
                     gs.ctx.sample_host(side, host[1 - side].data_ptr(), host[side].data_ptr(), args.alpha, variant)
                 else:
-                    gs.ctx.set_items_ptr(1 - side, host[1 - side].data_ptr())
+                    # every rank's host memory holds ITS slice of each latent matrix: upload the slice of the other side,
+                    # hand it to the peers over NVLink, sample, download the freshly sampled slice of this side
+                    gs.upload_slice(1 - side, host[1 - side].data_ptr())
                     gs.sample(side)
-                    gs.ctx.get_items_ptr(side, host[side].data_ptr())
+                    lo, hi, _ = gs.range[side]
+                    gs.ctx.get_items_range_ptr(side, lo, hi, host[side].data_ptr())
 
         # iteration counters continue; the latents uploaded are the ones just downloaded, so the chain is unchanged
         e2e_step()
         e_steps = max(2, min(args.steps, 5))
         e_ms = timed_region(e2e_step, e_steps)
         hb = (gs.num[MOVIES] + gs.num[USERS]) * K * 8
-        e2e = {"value": n_samples * e_steps / (e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": hb * world,
-               "d2h_bytes_per_step": hb * world, "ms_per_step": e_ms / e_steps, "steps": e_steps,
+        e2e = {"value": n_samples * e_steps / (e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": hb,
+               "d2h_bytes_per_step": hb, "ms_per_step": e_ms / e_steps, "steps": e_steps,
                "api": "bpmf_gpu_sample_host (C ABI) with pinned host latent matrices" if world == 1 else
-                      "bpmf_gpu_set_items / sample stages / bpmf_gpu_get_items per rank with pinned host latent matrices"}
+                      "per rank: bpmf_gpu_set_items_range (its slice of the other side) + NVLink exchange, sample stages, "
+                      "bpmf_gpu_get_items_range (its fresh slice); host latent matrices pinned, one slice per rank"}
 
     total_launches = launches
     if world > 1:

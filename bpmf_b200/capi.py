@@ -39,6 +39,9 @@ SYMBOLS = {
     "bpmf_gpu_host_free": (C.c_int, [C.c_void_p]),
     "bpmf_gpu_set_items": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "bpmf_gpu_get_items": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "bpmf_gpu_set_items_range": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "bpmf_gpu_get_items_range": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "bpmf_gpu_push_range": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "bpmf_gpu_get_iter": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "bpmf_gpu_set_iter": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "bpmf_gpu_sample": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int]),
@@ -179,6 +182,15 @@ class Context:
         out = np.empty((self.num[side], self.K), np.float64)
         self._ck(self.L.bpmf_gpu_get_items(self.h, side, C.c_void_p(out.ctypes.data)))
         return out
+
+    def set_items_range_ptr(self, side, lo, hi, host_ptr):
+        """upload items [lo, hi) from a raw host address of the FULL K x num matrix"""
+        self._ck(self.L.bpmf_gpu_set_items_range(self.h, side, lo, hi, C.c_void_p(host_ptr)))
+
+    def get_items_range_ptr(self, side, lo, hi, host_ptr):
+        self._ck(self.L.bpmf_gpu_get_items_range(self.h, side, lo, hi, C.c_void_p(host_ptr)))
+
+    def push_range(self, side, lo, hi): self._ck(self.L.bpmf_gpu_push_range(self.h, side, lo, hi))
 
     def get_iter(self, side):
         i = C.c_int()

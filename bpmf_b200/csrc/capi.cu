@@ -329,6 +329,7 @@ int bpmf_gpu_set_peers(bpmf_gpu_ctx *ctx, int side, int npeers, double *const *d
     for (int i = 0; i < npeers; ++i) tmp[i] = dev_peer_items[i];
     CU(cudaMemcpyAsync(s.peers_dev, tmp, sizeof(tmp), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < MAX_PEERS; ++i) s.peers_host[i] = tmp[i];
     s.npeers = npeers;
     return BPMF_GPU_OK;
 }
@@ -407,6 +408,43 @@ int bpmf_gpu_get_items(bpmf_gpu_ctx *ctx, int side, double *host_items)
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemcpyAsync(host_items, s.items, sizeof(double) * (size_t)ctx->K * s.num, cudaMemcpyDeviceToHost, ctx->stream));
     return check_device_error(ctx);
+}
+
+int bpmf_gpu_set_items_range(bpmf_gpu_ctx *ctx, int side, int from, int to, const double *host_items)
+{
+    if (!ctx || !side_ok(side) || !host_items) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded || from < 0 || to < from || to > s.num) return fail(ctx, BPMF_GPU_EINVAL, "bad range");
+    CU(cudaSetDevice(ctx->device));
+    const size_t K = (size_t)ctx->K;
+    CU(cudaMemcpyAsync(s.items + K * from, host_items + K * from, sizeof(double) * K * (to - from), cudaMemcpyHostToDevice, ctx->stream));
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_get_items_range(bpmf_gpu_ctx *ctx, int side, int from, int to, double *host_items)
+{
+    if (!ctx || !side_ok(side) || !host_items) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded || from < 0 || to < from || to > s.num) return fail(ctx, BPMF_GPU_EINVAL, "bad range");
+    CU(cudaSetDevice(ctx->device));
+    const size_t K = (size_t)ctx->K;
+    CU(cudaMemcpyAsync(host_items + K * from, s.items + K * from, sizeof(double) * K * (to - from), cudaMemcpyDeviceToHost, ctx->stream));
+    return check_device_error(ctx);
+}
+
+int bpmf_gpu_push_range(bpmf_gpu_ctx *ctx, int side, int from, int to)
+{
+    if (!ctx || !side_ok(side)) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded || from < 0 || to < from || to > s.num) return fail(ctx, BPMF_GPU_EINVAL, "bad range");
+    CU(cudaSetDevice(ctx->device));
+    const size_t K = (size_t)ctx->K;
+    for (int q = 0; q < s.npeers; ++q) {
+        double *dst = s.peers_host[q];
+        if (!dst || dst == s.items) continue;
+        CU(cudaMemcpyAsync(dst + K * from, s.items + K * from, sizeof(double) * K * (to - from), cudaMemcpyDefault, ctx->stream));
+    }
+    return BPMF_GPU_OK;
 }
 
 int bpmf_gpu_get_iter(bpmf_gpu_ctx *ctx, int side, int *iter)

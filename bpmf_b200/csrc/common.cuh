@@ -40,6 +40,7 @@ struct SideDev {          // the device mirror of one Sys (c++/bpmf.h:112-239)
     double *items_own = nullptr;
     int npeers = 0;
     double **peers_dev = nullptr;   // device array[MAX_PEERS] of replica pointers
+    double *peers_host[MAX_PEERS] = {};   // the same pointers, host copy (bpmf_gpu_push_range)
     HyperDev hp;
     HyperDev hp_next;               // written by the pre-launched draw of the next iteration, swapped in when it is consumed
     int pre_iter = -2147483647;     // iteration whose hyper-parameters are (being) drawn into hp_next; INT_MIN + 1 = none

@@ -214,6 +214,9 @@ __device__ __forceinline__ void chol3_block_column(double (&c)[10][2], double &m
 // instead of 8 (14.6 with one streaming warp; profiles/r01_fp64_latency_microbench.txt), which is what made the tails
 // slow. With TOK != 0 at most ONE warp per scheduler (warp id % 4) executes Gram DMMAs at a time: 1 = the token is held
 // per stage (<= 40 DMMAs), 2 = per item. A single warp saturates the DMMA pipe, so the Gram loses nothing.
+// TOK == 3 ("phased"): the warps of a CTA run their Gram phases together and their tails together (two CTA barriers
+// per item). Nobody is in a tail while DMMAs stream, so the tails' dependent scalar fp64 chains run at the uncontended
+// 8 cycles per instruction instead of 15-56, and the Gram phase keeps the DMMA pipe full with every warp.
 template <int NS, int NW, int DBG, bool BULK, int TOK>
 __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs p)
 {
@@ -367,7 +370,15 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs
         __syncwarp();
         unsigned char *stg = wbase + h * STAGE_BYTES;
         const int4 meta = *reinterpret_cast<const int4 *>(stg + META_OFF);
-        if (meta.x < 0) break;
+        if (meta.x < 0) {
+            if (TOK == 3) {               // out of items: keep the CTA's barrier protocol going until every warp is
+                for (;;) {
+                    if (!__syncthreads_or(0)) break;
+                    __syncthreads();
+                }
+            }
+            break;
+        }
         // ---------------- Gram + rhs of this stage (computeMuLambda, sample.cpp:251-257) ----------------
         {
             const unsigned char *row = stg + t * ROWB + g * 8;
@@ -404,6 +415,7 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs
             h = (h + 1 == NS) ? 0 : h + 1;
             continue;
         }
+        if (TOK == 3) __syncthreads_or(1);   // phase boundary: every warp's Gram is complete
         // ---------------- tail: one item's Gram is complete; slot h is its scratch until the refill at the end ---------
         const int idx = meta.y;
         if (DBG & 1) {
@@ -518,6 +530,7 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs
         __syncwarp();                     // the scratch is free again
         issue_stage(h);
         h = (h + 1 == NS) ? 0 : h + 1;
+        if (TOK == 3) __syncthreads();    // phase boundary: every warp's tail is complete
     }
     if (!BULK) cp_async_wait<0>();
 }
@@ -532,10 +545,10 @@ cudaError_t launch_cfg(bpmf_gpu_ctx *c, const StreamArgs &p, long long n)
     constexpr size_t smem = (size_t)NW * warp_bytes<NS>() + SHARED_BYTES;
     static_assert(smem <= 227 * 1024, "shared memory budget");
 #ifdef BPMF_STREAM_PROBES
-    auto kern = VER >= 3 ? items_stream32v3_kernel<NS, NW, DBG, VER == 6, (VER == 7 ? 1 : VER == 8 ? 2 : 0)> : items_stream32_kernel<NS, NW>;
+    auto kern = VER >= 3 ? items_stream32v3_kernel<NS, NW, DBG, VER == 6, (VER == 7 ? 1 : VER == 8 ? 2 : VER == 9 ? 3 : 0)> : items_stream32_kernel<NS, NW>;
 #else
     static_assert(VER >= 3, "the v2 kernel is an experiment (stream_experiments.cuh)");
-    auto kern = items_stream32v3_kernel<NS, NW, DBG, VER == 6, (VER == 7 ? 1 : VER == 8 ? 2 : 0)>;
+    auto kern = items_stream32v3_kernel<NS, NW, DBG, VER == 6, (VER == 7 ? 1 : VER == 8 ? 2 : VER == 9 ? 3 : 0)>;
 #endif
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -666,6 +679,11 @@ cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, doub
     const int cfg = c->stream_cfg ? c->stream_cfg : env_cfg;
     switch (cfg) {
     case 3218: e = launch_cfg<2, 18, 3>(c, p, n); break;
+    // 11<NS><NW>: v3 "phased" (all Grams of a CTA together, all tails together)
+    case 11216: e = launch_cfg<2, 16, 9>(c, p, n); break;
+    case 11220: e = launch_cfg<2, 20, 9>(c, p, n); break;
+    case 11315: e = launch_cfg<3, 15, 9>(c, p, n); break;
+    case 11212: e = launch_cfg<2, 12, 9>(c, p, n); break;
     case 3315: e = launch_cfg<3, 15, 3>(c, p, n); break;
     // 6<NS><NW>: v3 with the TMA bulk-copy gather (cp.async.bulk + mbarrier; measured slower, profiles/r01_tune_bulk_tma.log)
     case 6216: e = launch_cfg<2, 16, 6>(c, p, n); break;

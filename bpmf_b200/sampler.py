@@ -86,6 +86,19 @@ class GibbsSampler:
         else:
             raise ValueError(self.exchange)
 
+    def upload_slice(self, side, host_ptr):
+        """Multi-GPU hosts hold one slice of a latent matrix per rank: upload this rank's slice of `side` from the host
+        matrix at `host_ptr` and distribute it to every replica (all-gather, or NVLink copies into the peer replicas)."""
+        lo, hi, _ = self.range[side]
+        self.ctx.set_items_range_ptr(side, lo, hi, host_ptr)
+        if self.world == 1:
+            return
+        if self.exchange == "allgather":
+            allgather_slices(self.dist, self.items[side], self.rank, self.world)
+        else:
+            self.ctx.push_range(side, lo, hi)
+            self.dist.all_reduce(self._tiny)      # every rank's copies are ordered before the next kernel of any rank
+
     def step(self):
         """movies.sample(users); users.sample(movies)  (bpmf.cpp:184-185)"""
         self.sample(MOVIES)

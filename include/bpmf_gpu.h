@@ -92,6 +92,12 @@ int bpmf_gpu_host_free(void *host_ptr);
 
 int bpmf_gpu_set_items(bpmf_gpu_ctx *ctx, int side, const double *host_items);
 int bpmf_gpu_get_items(bpmf_gpu_ctx *ctx, int side, double *host_items); /* synchronises */
+/* Multi-GPU hosts keep one slice of a latent matrix per rank in host memory: upload / download only the items of
+ * [from,to) (host_items is the base of the full K x num_items matrix; only that range is touched), and copy a range of
+ * this context's replica into every peer replica set with bpmf_gpu_set_peers (NVLink, asynchronous on the stream). */
+int bpmf_gpu_set_items_range(bpmf_gpu_ctx *ctx, int side, int from, int to, const double *host_items);
+int bpmf_gpu_get_items_range(bpmf_gpu_ctx *ctx, int side, int from, int to, double *host_items); /* synchronises */
+int bpmf_gpu_push_range(bpmf_gpu_ctx *ctx, int side, int from, int to);
 int bpmf_gpu_get_iter(bpmf_gpu_ctx *ctx, int side, int *iter);
 int bpmf_gpu_set_iter(bpmf_gpu_ctx *ctx, int side, int iter);
 

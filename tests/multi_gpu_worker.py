@@ -42,6 +42,23 @@ def main():
             a, b = multi.items_host(side), single.get_items(side)
             worst = max(worst, float(np.abs(a - b).max()))
             assert a.tobytes() == b.tobytes(), "rank %d iteration %d side %d differs by %g" % (rank, it, side, np.abs(a - b).max())
+    # the end-to-end path of bench.py: every rank keeps ITS slice of each latent matrix in (pinned) host memory
+    host = [torch.from_numpy(multi.items_host(s)).pin_memory() for s in (MOVIES, USERS)]
+    for it in range(2):
+        for side in (MOVIES, USERS):
+            lo, hi, _ = multi.range[1 - side]
+            other = host[1 - side].clone()
+            other[:lo] = float("nan"); other[hi:] = float("nan")      # only the own slice may be read
+            other = other.pin_memory()
+            multi.upload_slice(1 - side, other.data_ptr())
+            multi.sample(side)
+            lo, hi, _ = multi.range[side]
+            multi.ctx.get_items_range_ptr(side, lo, hi, host[side].data_ptr())
+            single.sample(side)
+            ref = single.get_items(side)
+            assert host[side].numpy()[lo:hi].tobytes() == ref[lo:hi].tobytes(), "e2e slice path differs (rank %d)" % rank
+            assert multi.items_host(side).tobytes() == ref.tobytes()
+            host[side] = torch.from_numpy(ref.copy()).pin_memory()
     multi.ctx.sync()
     t = torch.tensor([worst], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
