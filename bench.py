@@ -265,7 +265,7 @@ def main():
     k_avg_ms = k_ms / max(1, k_n)
     achieved = bytes_per_launch / (k_avg_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": ("items_exact_kernel" if K != 32 or args.variant == "exact" else
+                "kernel": ("items_exact_kernel" if args.variant == "exact" or K % 16 else "items_block_kernel<%d>" % (K // 8) if K != 32 else
                            "items_dmma32_kernel" if args.variant == "dmma" else "items_stream32v3_kernel<2,20>"),
                 "kernel_ms_avg": k_avg_ms, "kernel_launches_timed": k_n, "kernel_share_of_step": k_ms / ms,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src + " (of measured, burst)"}

@@ -572,10 +572,11 @@ __global__ void __launch_bounds__((NG + NT) * 32, 1) items_stream32v4_kernel(Str
                     c[blk(I, J)][e] = fma(p.alpha, c[blk(I, J)][e], sLF[(8 * J + 2 * t + e) * LFS + 8 * I + g]);
         double myd = 1.0, myrinv = 1.0;
         bool ok = true;
-        chol3_block_column<0>(c, myd, myrinv, ok, lane, t);
-        chol3_block_column<1>(c, myd, myrinv, ok, lane, t);
-        chol3_block_column<2>(c, myd, myrinv, ok, lane, t);
-        chol3_block_column<3>(c, myd, myrinv, ok, lane, t);
+        chol3_block_column<0>(c, myd, myrinv, lane, t);
+        chol3_block_column<1>(c, myd, myrinv, lane, t);
+        chol3_block_column<2>(c, myd, myrinv, lane, t);
+        chol3_block_column<3>(c, myd, myrinv, lane, t);
+        ok = __all_sync(FULL, myd > 0.0);
         const double myrs = rsqrt(myd);
         {
 #pragma unroll
@@ -942,10 +943,11 @@ __global__ void __launch_bounds__((2 * NM + NT) * 32, 1) items_stream32v7_kernel
                     c[blk(I, J)][e] = fma(p.alpha, c[blk(I, J)][e], sLF[(8 * J + 2 * t + e) * LFS + 8 * I + g]);
         double myd = 1.0, myrinv = 1.0;
         bool ok = true;
-        chol3_block_column<0>(c, myd, myrinv, ok, lane, t);
-        chol3_block_column<1>(c, myd, myrinv, ok, lane, t);
-        chol3_block_column<2>(c, myd, myrinv, ok, lane, t);
-        chol3_block_column<3>(c, myd, myrinv, ok, lane, t);
+        chol3_block_column<0>(c, myd, myrinv, lane, t);
+        chol3_block_column<1>(c, myd, myrinv, lane, t);
+        chol3_block_column<2>(c, myd, myrinv, lane, t);
+        chol3_block_column<3>(c, myd, myrinv, lane, t);
+        ok = __all_sync(FULL, myd > 0.0);
         const double myrs = rsqrt(myd);
         {
 #pragma unroll

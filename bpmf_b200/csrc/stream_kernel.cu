@@ -153,7 +153,7 @@ __device__ __forceinline__ double fast_rcp(double p)
 }
 
 template <int KB>
-__device__ __forceinline__ void chol3_block_column(double (&c)[10][2], double &myd, double &myrinv, bool &ok, int lane, int t)
+__device__ __forceinline__ void chol3_block_column(double (&c)[10][2], double &myd, double &myrinv, int lane, int t)
 {
     constexpr int D = blk(KB, KB);
 #pragma unroll 1
@@ -169,7 +169,6 @@ __device__ __forceinline__ void chol3_block_column(double (&c)[10][2], double &m
             double a[4];
 #pragma unroll
             for (int I = KB; I < 4; ++I) a[I] = __shfl_sync(FULL, c[blk(I, KB)][e], qsrc);   // a[8I+g][k]
-            if (!(p > 0.0)) ok = false;                                     // Eigen LLT: pivot <= 0 -> "Cholesky failed"
             const double rinv = fast_rcp(p);
             if (lane == 8 * KB + k) { myd = p; myrinv = rinv; }
             bl0 = (2 * t > k) ? -(bl0 * rinv) : 0.0;                        // zero where this lane's column is not right of k
@@ -470,13 +469,15 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs
         double myd = 1.0, myrinv = 1.0;
         bool ok = true;
         if (!(DBG & 16)) {
-            chol3_block_column<0>(c, myd, myrinv, ok, lane, t);
-            chol3_block_column<1>(c, myd, myrinv, ok, lane, t);
-            chol3_block_column<2>(c, myd, myrinv, ok, lane, t);
-            chol3_block_column<3>(c, myd, myrinv, ok, lane, t);
+            chol3_block_column<0>(c, myd, myrinv, lane, t);
+            chol3_block_column<1>(c, myd, myrinv, lane, t);
+            chol3_block_column<2>(c, myd, myrinv, lane, t);
+            chol3_block_column<3>(c, myd, myrinv, lane, t);
         } else {
             myd = c[0][0] + 2.0; myrinv = fast_rcp(myd);
         }
+        // Eigen LLT: a pivot <= 0 -> "Cholesky failed". Lane k holds d_k; a bad pivot poisons what follows (NaN also fails)
+        ok = __all_sync(FULL, myd > 0.0);
         const double myrs = rsqrt(myd);                       // 1 / L(k,k)
         // Lu -> shared memory, packed by columns without the unit diagonal: element (i,k), i > k, at col_off1(k) + i - k - 1
         {
