@@ -27,6 +27,7 @@ SYMBOLS = {
     "bpmf_gpu_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bpmf_gpu_sync": (C.c_int, [C.c_void_p]),
     "bpmf_gpu_load_side": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _i64p, _i32p, _f64p, C.c_double]),
+    "bpmf_gpu_set_heavy_threshold": (C.c_int, [C.c_void_p, C.c_int64]),
     "bpmf_gpu_load_test": (C.c_int, [C.c_void_p, C.c_int, _i64p, _i32p, _f64p]),
     "bpmf_gpu_set_range": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "bpmf_gpu_bind_items": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
@@ -135,6 +136,8 @@ class Context:
         assert colptr.shape == (num_items + 1,)
         self._ck(self.L.bpmf_gpu_load_side(self.h, side, num_items, num_other, colptr, rowidx, val, mean_rating))
         self.num[side] = num_items
+
+    def set_heavy_threshold(self, n): self._ck(self.L.bpmf_gpu_set_heavy_threshold(self.h, n))
 
     def load_test(self, side, colptr, rowidx, val):
         colptr = np.ascontiguousarray(colptr, np.int64)

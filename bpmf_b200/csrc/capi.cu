@@ -4,6 +4,7 @@
 #include "../../include/bpmf_gpu.h"
 #include "common.cuh"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -51,6 +52,7 @@ void free_side(SideDev &s)
     dfree(s.hp_next.mu); dfree(s.hp_next.LambdaU); dfree(s.hp_next.LambdaF);
     dfree(s.sum); dfree(s.prod); dfree(s.cov); dfree(s.norm); dfree(s.partials); dfree(s.pred_partials);
     dfree(s.work_counter); dfree(s.aggrMu); dfree(s.aggrLambda); dfree(s.propLambda);
+    dfree(s.hv_item); dfree(s.hv_first); dfree(s.hv_p0); dfree(s.hv_p1); dfree(s.hv_partials);
     s = SideDev();
 }
 
@@ -252,6 +254,32 @@ int bpmf_gpu_load_side(bpmf_gpu_ctx *ctx, int side, int num_items, int num_other
     CU(cudaMalloc(&s.partials, sizeof(double) * (size_t)STATS_BLOCKS * (KK + K + 1)));
     CU(cudaMalloc(&s.work_counter, 2 * sizeof(unsigned int)));
     CU(cudaMemset(s.work_counter, 0, 2 * sizeof(unsigned int)));
+    // skew handling for the K == 32 stream kernel: items far heavier than the rest are sampled by the chunked path
+    if (K == 32 && num_items > 0) {
+        const long long thr = std::max<long long>(ctx->heavy_threshold, 16 * (nnz / num_items + 1));
+        std::vector<int> items, first(1, 0);
+        std::vector<int64_t> p0, p1;
+        const int CH = heavy_chunk_size();
+        for (int i = 0; i < num_items && (int)items.size() <= 16; ++i) {
+            if (colptr[i + 1] - colptr[i] <= thr) continue;
+            items.push_back(i);
+            for (int64_t q = colptr[i]; q < colptr[i + 1]; q += CH) { p0.push_back(q); p1.push_back(std::min<int64_t>(q + CH, colptr[i + 1])); }
+            first.push_back((int)p0.size());
+        }
+        if (!items.empty() && items.size() <= 16) {   // more than 16: the side is heavy everywhere, nothing to balance
+            s.n_heavy = (int)items.size();
+            s.h_heavy_item = items; s.h_heavy_first = first;
+            CU(cudaMalloc(&s.hv_item, sizeof(int) * items.size()));
+            CU(cudaMalloc(&s.hv_first, sizeof(int) * first.size()));
+            CU(cudaMalloc(&s.hv_p0, sizeof(int64_t) * p0.size()));
+            CU(cudaMalloc(&s.hv_p1, sizeof(int64_t) * p1.size()));
+            CU(cudaMalloc(&s.hv_partials, sizeof(double) * p0.size() * heavy_partial_doubles()));
+            CU(cudaMemcpy(s.hv_item, items.data(), sizeof(int) * items.size(), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(s.hv_first, first.data(), sizeof(int) * first.size(), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(s.hv_p0, p0.data(), sizeof(int64_t) * p0.size(), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(s.hv_p1, p1.data(), sizeof(int64_t) * p1.size(), cudaMemcpyHostToDevice));
+        }
+    }
     s.loaded = true;
     return BPMF_GPU_OK;
 }
@@ -774,6 +802,13 @@ int bpmf_gpu_sample_host(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_v
     CU(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
     return check_device_error(ctx);   // synchronises the stream
+}
+
+int bpmf_gpu_set_heavy_threshold(bpmf_gpu_ctx *ctx, int64_t num_ratings)
+{
+    if (!ctx || num_ratings < 1) return BPMF_GPU_EINVAL;
+    ctx->heavy_threshold = num_ratings;
+    return BPMF_GPU_OK;
 }
 
 int bpmf_gpu_debug_set_tuning(bpmf_gpu_ctx *ctx, int stream_cfg)

@@ -54,6 +54,12 @@ struct SideDev {          // the device mirror of one Sys (c++/bpmf.h:112-239)
     // posterior aggregation (-o): K x num and K*K x num, allocated by bpmf_gpu_enable_aggregation
     double *aggrMu = nullptr, *aggrLambda = nullptr;
     int aggr_burnin = 0;
+    // heavy items (K == 32 stream kernel): items with more than the threshold of ratings, cut into chunks (stream_kernel.cu)
+    int n_heavy = 0;
+    std::vector<int> h_heavy_item, h_heavy_first;     // host copies: item index (ascending), first chunk (n_heavy + 1)
+    int *hv_item = nullptr, *hv_first = nullptr;
+    int64_t *hv_p0 = nullptr, *hv_p1 = nullptr;       // per chunk: rating range
+    double *hv_partials = nullptr;                    // per chunk: partial Gram + rhs in the DMMA layout
     // dynamic work counter for the item kernels
     unsigned int *work_counter = nullptr;
 };
@@ -97,6 +103,7 @@ struct bpmf_gpu_ctx {
     long long ev_count = 0;      // item-kernel launches timed so far
     long long ev_read = 0;       // launches already returned by bpmf_gpu_items_kernel_time
     long long launches = 0;
+    long long heavy_threshold = 16384;    // items with more ratings go through the chunked path (K == 32)
     int stream_cfg = 0;                   // 0 = default; see launch_items_stream32
     int stream_tail = -1;                 // items per warp claimed in small groups at the end of a sweep; -1 = default
     std::string err;
@@ -121,4 +128,6 @@ cudaError_t launch_items_block(bpmf_gpu_ctx *c, int side, uint32_t iter, double 
 // stream_kernel.cu
 cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha);
 cudaError_t launch_stats_partial32(bpmf_gpu_ctx *c, int side);
+int heavy_chunk_size();
+int heavy_partial_doubles();
 }  // namespace bpmf

@@ -203,6 +203,116 @@ __device__ __forceinline__ void chol3_block_column(double (&c)[10][2], double &m
     }
 }
 
+// The tail of one item for one warp (shared by the stream kernel and the heavy-item kernel): on entry the accumulators
+// hold the item's Gram (DMMA layout) and rrp the quad-partial right-hand side; `stg` is TSCRATCH bytes of the warp's
+// shared memory. Normals, MM = LambdaF + alpha G, LDL^T, solves, store (sample.cpp:266,297-324). Resets c and rrp.
+template <int DBG>
+__device__ __forceinline__ void tail32_warp(double (&c)[10][2], double (&rrp)[4], const int idx, unsigned char *stg, const double *sLF,
+                                            const double *srr0, const StreamArgs &p, const int lane)
+{
+    const int g = lane >> 2, t = lane & 3;
+    double *zy = reinterpret_cast<double *>(stg + V3_ZY_OFF), *zr = reinterpret_cast<double *>(stg + V3_ZR_OFF);
+    double *wb = reinterpret_cast<double *>(stg + V3_B_OFF), *Lp = reinterpret_cast<double *>(stg);
+    // the K normals of this item: rng_set_pos((idx+1)*K*(iter+1)) (sample.cpp:266). Accepted polar attempts are numbered
+    // by ballot; lane n then finishes normal n (one log / sqrt / divide per lane instead of one per attempt).
+    if (!(DBG & 8)) {
+        const uint32_t seed = (uint32_t)(((long long)idx + 1) * 32ll * ((long long)p.iter + 1));
+        int have = 0;
+        for (uint32_t base = 0; have < 32; base += 32) {
+            const U4 bk = stream_block(seed, base + lane);
+            const Polar pa = polar_attempt(bk.v[3], bk.v[2], bk.v[1], bk.v[0]);
+            const unsigned m = __ballot_sync(FULL, pa.ok);
+            const int n = have + __popc(m & ((1u << lane) - 1u));
+            if (pa.ok && n < 32) { zy[n] = pa.y; zr[n] = pa.r2; }
+            have += __popc(m);
+        }
+    }
+    // rr = LambdaF*mu + sum over the quad's four ratings-of-a-group
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        rrp[a] += __shfl_xor_sync(FULL, rrp[a], 1);
+        rrp[a] += __shfl_xor_sync(FULL, rrp[a], 2);
+    }
+    if (t == 0) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) wb[8 * a + g] = srr0[8 * a + g] + rrp[a];
+    }
+    __syncwarp();
+    const double z = (DBG & 8) ? 0.25 * lane : __dmul_rn(zy[lane], polar_mult(zr[lane]));
+    double bb = wb[lane];
+    // MM = LambdaF + alpha * G (sample.cpp:297-298), in place in the accumulator layout
+#pragma unroll
+    for (int I = 0; I < 4; ++I)
+#pragma unroll
+        for (int J = 0; J <= I; ++J)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+                c[blk(I, J)][e] = fma(p.alpha, c[blk(I, J)][e], sLF[(8 * J + 2 * t + e) * LFS + 8 * I + g]);   // LambdaF(i,k), i >= k
+    // chol.compute(MM) (sample.cpp:306) as MM = Lu D Lu^T; lane k ends up with d_k and 1 / d_k
+    double myd = 1.0, myrinv = 1.0;
+    bool ok = true;
+    if (!(DBG & 16)) {
+        chol3_block_column<0>(c, myd, myrinv, lane, t);
+        chol3_block_column<1>(c, myd, myrinv, lane, t);
+        chol3_block_column<2>(c, myd, myrinv, lane, t);
+        chol3_block_column<3>(c, myd, myrinv, lane, t);
+    } else {
+        myd = c[0][0] + 2.0; myrinv = fast_rcp(myd);
+    }
+    // Eigen LLT: a pivot <= 0 -> "Cholesky failed". Lane k holds d_k; a bad pivot poisons what follows (NaN also fails)
+    ok = __all_sync(FULL, myd > 0.0);
+    const double myrs = rsqrt(myd);                       // 1 / L(k,k)
+    // Lu -> shared memory, packed by columns without the unit diagonal: element (i,k), i > k, at col_off1(k) + i - k - 1
+    {
+#pragma unroll
+        for (int J = 0; J < 4; ++J)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int k = 8 * J + 2 * t + e;
+                const double rk = __shfl_sync(FULL, myrinv, k);
+                double *lq = Lp + (31 * k - ((k * (k - 1)) >> 1)) + g - k - 1;
+#pragma unroll
+                for (int I = J; I < 4; ++I)
+                    if (I > J || g > 2 * t + e) lq[8 * I] = c[blk(I, J)][e] * rk;
+            }
+    }
+    // reset the accumulators for the next item
+#pragma unroll
+    for (int b = 0; b < 10; ++b) { c[b][0] = 0.0; c[b][1] = 0.0; }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) rrp[a] = 0.0;
+    __syncwarp();
+    if (ok) {
+        // chol.matrixL().solveInPlace(rr); rr += nrandn(); chol.matrixU().solveInPlace(rr) (sample.cpp:321-323):
+        // lane j owns row j; one broadcast + one FMA per step.
+        if (!(DBG & 32)) {
+            const double *lf = Lp + lane - 1;              // element (lane, k) at lf[col_off1(k) - k]
+#pragma unroll
+            for (int k = 0; k < 31; ++k) {
+                const double yk = __shfl_sync(FULL, bb, k);
+                if (lane > k) bb = fma(-lf[col_off1(k) - k], yk, bb);
+            }
+        }
+        double yv = fma(bb, myrinv, myrs * z);             // D^-1 Lu^-1 b + D^(-1/2) z
+        if (!(DBG & 32)) {
+            const double *lb = Lp + (31 * lane - ((lane * (lane - 1)) >> 1)) - lane - 1;   // element (i, lane) at lb[i]
+#pragma unroll
+            for (int i = 31; i >= 1; --i) {
+                const double xi = __shfl_sync(FULL, yv, i);
+                if (lane < i) yv = fma(-lb[i], xi, yv);
+            }
+        }
+        // items().col(idx) = rr (sample.cpp:324); push to the peer replicas (replaces send_item, :370)
+        p.items[(size_t)idx * 32 + lane] = yv;
+        for (int pr = 0; pr < p.npeers; ++pr) {
+            double *dst = p.peers[pr];
+            if (dst && dst != p.items) dst[(size_t)idx * 32 + lane] = yv;
+        }
+    } else if (lane == 0) {           // THROWERROR("Cholesky failed") (sample.cpp:308): reported through the error word
+        atomicMax(p.err, ERR_CHOLESKY | (unsigned)idx);
+    }
+}
+
 // DBG (bench_micro/tune_stream.py only) is a bit mask: 0 = the product; 1 = no tail (Gram only); 2 = no Gram DMMAs;
 // 4 = no gather (Gram on whatever the stage holds); 8 = no normals; 16 = no factorization; 32 = no triangular solves.
 // Anything but 0 produces garbage: the probes exist to time the parts of the kernel.
@@ -428,112 +538,94 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs
             h = (h + 1 == NS) ? 0 : h + 1;
             continue;
         }
-        double *zy = reinterpret_cast<double *>(stg + V3_ZY_OFF), *zr = reinterpret_cast<double *>(stg + V3_ZR_OFF);
-        double *wb = reinterpret_cast<double *>(stg + V3_B_OFF), *Lp = reinterpret_cast<double *>(stg);
-        // the K normals of this item: rng_set_pos((idx+1)*K*(iter+1)) (sample.cpp:266). Accepted polar attempts are numbered
-        // by ballot; lane n then finishes normal n (one log / sqrt / divide per lane instead of one per attempt).
-        if (!(DBG & 8)) {
-            const uint32_t seed = (uint32_t)(((long long)idx + 1) * 32ll * ((long long)p.iter + 1));
-            int have = 0;
-            for (uint32_t base = 0; have < 32; base += 32) {
-                const U4 bk = stream_block(seed, base + lane);
-                const Polar pa = polar_attempt(bk.v[3], bk.v[2], bk.v[1], bk.v[0]);
-                const unsigned m = __ballot_sync(FULL, pa.ok);
-                const int n = have + __popc(m & ((1u << lane) - 1u));
-                if (pa.ok && n < 32) { zy[n] = pa.y; zr[n] = pa.r2; }
-                have += __popc(m);
-            }
-        }
-        // rr = LambdaF*mu + sum over the quad's four ratings-of-a-group
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            rrp[a] += __shfl_xor_sync(FULL, rrp[a], 1);
-            rrp[a] += __shfl_xor_sync(FULL, rrp[a], 2);
-        }
-        if (t == 0) {
-#pragma unroll
-            for (int a = 0; a < 4; ++a) wb[8 * a + g] = srr0[8 * a + g] + rrp[a];
-        }
-        __syncwarp();
-        const double z = (DBG & 8) ? 0.25 * lane : __dmul_rn(zy[lane], polar_mult(zr[lane]));
-        double bb = wb[lane];
-        // MM = LambdaF + alpha * G (sample.cpp:297-298), in place in the accumulator layout
-#pragma unroll
-        for (int I = 0; I < 4; ++I)
-#pragma unroll
-            for (int J = 0; J <= I; ++J)
-#pragma unroll
-                for (int e = 0; e < 2; ++e)
-                    c[blk(I, J)][e] = fma(p.alpha, c[blk(I, J)][e], sLF[(8 * J + 2 * t + e) * LFS + 8 * I + g]);   // LambdaF(i,k), i >= k
-        // chol.compute(MM) (sample.cpp:306) as MM = Lu D Lu^T; lane k ends up with d_k and 1 / d_k
-        double myd = 1.0, myrinv = 1.0;
-        bool ok = true;
-        if (!(DBG & 16)) {
-            chol3_block_column<0>(c, myd, myrinv, lane, t);
-            chol3_block_column<1>(c, myd, myrinv, lane, t);
-            chol3_block_column<2>(c, myd, myrinv, lane, t);
-            chol3_block_column<3>(c, myd, myrinv, lane, t);
-        } else {
-            myd = c[0][0] + 2.0; myrinv = fast_rcp(myd);
-        }
-        // Eigen LLT: a pivot <= 0 -> "Cholesky failed". Lane k holds d_k; a bad pivot poisons what follows (NaN also fails)
-        ok = __all_sync(FULL, myd > 0.0);
-        const double myrs = rsqrt(myd);                       // 1 / L(k,k)
-        // Lu -> shared memory, packed by columns without the unit diagonal: element (i,k), i > k, at col_off1(k) + i - k - 1
-        {
-#pragma unroll
-            for (int J = 0; J < 4; ++J)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int k = 8 * J + 2 * t + e;
-                    const double rk = __shfl_sync(FULL, myrinv, k);
-                    double *lq = Lp + (31 * k - ((k * (k - 1)) >> 1)) + g - k - 1;
-#pragma unroll
-                    for (int I = J; I < 4; ++I)
-                        if (I > J || g > 2 * t + e) lq[8 * I] = c[blk(I, J)][e] * rk;
-                }
-        }
-        // reset the accumulators for the next item
-#pragma unroll
-        for (int b = 0; b < 10; ++b) { c[b][0] = 0.0; c[b][1] = 0.0; }
-#pragma unroll
-        for (int a = 0; a < 4; ++a) rrp[a] = 0.0;
-        __syncwarp();
-        if (ok) {
-            // chol.matrixL().solveInPlace(rr); rr += nrandn(); chol.matrixU().solveInPlace(rr) (sample.cpp:321-323):
-            // lane j owns row j; one broadcast + one FMA per step.
-            if (!(DBG & 32)) {
-                const double *lf = Lp + lane - 1;              // element (lane, k) at lf[col_off1(k) - k]
-#pragma unroll
-                for (int k = 0; k < 31; ++k) {
-                    const double yk = __shfl_sync(FULL, bb, k);
-                    if (lane > k) bb = fma(-lf[col_off1(k) - k], yk, bb);
-                }
-            }
-            double yv = fma(bb, myrinv, myrs * z);             // D^-1 Lu^-1 b + D^(-1/2) z
-            if (!(DBG & 32)) {
-                const double *lb = Lp + (31 * lane - ((lane * (lane - 1)) >> 1)) - lane - 1;   // element (i, lane) at lb[i]
-#pragma unroll
-                for (int i = 31; i >= 1; --i) {
-                    const double xi = __shfl_sync(FULL, yv, i);
-                    if (lane < i) yv = fma(-lb[i], xi, yv);
-                }
-            }
-            // items().col(idx) = rr (sample.cpp:324); push to the peer replicas (replaces send_item, :370)
-            p.items[(size_t)idx * 32 + lane] = yv;
-            for (int pr = 0; pr < p.npeers; ++pr) {
-                double *dst = p.peers[pr];
-                if (dst && dst != p.items) dst[(size_t)idx * 32 + lane] = yv;
-            }
-        } else if (lane == 0) {           // THROWERROR("Cholesky failed") (sample.cpp:308): reported through the error word
-            atomicMax(p.err, ERR_CHOLESKY | (unsigned)idx);
-        }
+        tail32_warp<DBG>(c, rrp, idx, stg, sLF, srr0, p, lane);
         __syncwarp();                     // the scratch is free again
         issue_stage(h);
         h = (h + 1 == NS) ? 0 : h + 1;
         if (TOK == 3) __syncthreads();    // phase boundary: every warp's tail is complete
     }
     if (!BULK) cp_async_wait<0>();
+}
+
+// =====================================================================================================================
+// Heavy items (skew handling): an item with tens of thousands of ratings (ChEMBL's hottest target has 110 118) would be
+// ONE warp's work in the stream kernel and set the duration of the whole sweep. Such items are cut into chunks of
+// HEAVY_CHUNK ratings: heavy_gram32_kernel computes one partial Gram per chunk (a warp per chunk, DMMA, fragments
+// straight from global memory), heavy_tail32_kernel adds an item's partials in chunk order (so the result does not
+// depend on scheduling) and runs the same tail as the stream kernel. The stream kernel is launched on the index ranges
+// between the heavy items.
+// =====================================================================================================================
+constexpr int HEAVY_CHUNK = 2048;
+constexpr int HEAVY_PART = 24 * 32;           // doubles per partial: c[10][2] + rrp[4] per lane, in the DMMA layout
+
+__global__ void __launch_bounds__(128) heavy_gram32_kernel(StreamArgs p, int nchunks, const int64_t *__restrict__ ch_p0,
+                                                           const int64_t *__restrict__ ch_p1, double *__restrict__ partials)
+{
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int ch = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (ch >= nchunks) return;
+    const int64_t p0 = ch_p0[ch], p1 = ch_p1[ch];
+    double c[10][2], rrp[4];
+#pragma unroll
+    for (int b = 0; b < 10; ++b) { c[b][0] = 0.0; c[b][1] = 0.0; }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) rrp[a] = 0.0;
+    for (int64_t q = p0; q < p1; q += 4) {
+        const bool live = q + t < p1;
+        double f[4], w = 0.0;
+        if (live) {
+            const double *row = p.other + (size_t)__ldg(p.rowidx + q + t) * 32 + g;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) f[a] = __ldg(row + 8 * a);
+            w = (__ldg(p.val + q + t) - p.mean_rating) * p.alpha;
+        } else {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) f[a] = 0.0;
+        }
+#pragma unroll
+        for (int I = 0; I < 4; ++I)
+#pragma unroll
+            for (int J = 0; J <= I; ++J) dmma884(c[blk(I, J)][0], c[blk(I, J)][1], f[I], f[J]);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) rrp[a] = fma(f[a], w, rrp[a]);
+    }
+    double *out = partials + (size_t)ch * HEAVY_PART + lane;
+#pragma unroll
+    for (int b = 0; b < 10; ++b) { out[(2 * b) * 32] = c[b][0]; out[(2 * b + 1) * 32] = c[b][1]; }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) out[(20 + a) * 32] = rrp[a];
+}
+
+// one warp (one CTA) per heavy item
+__global__ void __launch_bounds__(32) heavy_tail32_kernel(StreamArgs p, const int *__restrict__ hv_item, const int *__restrict__ hv_first,
+                                                          const double *__restrict__ partials)
+{
+    __shared__ __align__(16) double sLF[32 * LFS + 32];
+    __shared__ __align__(16) unsigned char scratch[V3_B_OFF + 256];
+    const int lane = threadIdx.x;
+    double *srr0 = sLF + 32 * LFS;
+    for (int e = lane; e < 1024; e += 32) sLF[(e >> 5) * LFS + (e & 31)] = p.LambdaF[e];
+    __syncwarp();
+    {
+        double s = 0.0;
+        for (int j = 0; j < 32; ++j) s += sLF[j * LFS + lane] * p.mu[j];
+        srr0[lane] = s;
+    }
+    __syncwarp();
+    const int h = blockIdx.x;
+    double c[10][2], rrp[4];
+#pragma unroll
+    for (int b = 0; b < 10; ++b) { c[b][0] = 0.0; c[b][1] = 0.0; }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) rrp[a] = 0.0;
+    for (int ch = hv_first[h]; ch < hv_first[h + 1]; ++ch) {       // fixed order: independent of scheduling
+        const double *in = partials + (size_t)ch * HEAVY_PART + lane;
+#pragma unroll
+        for (int b = 0; b < 10; ++b) { c[b][0] += in[(2 * b) * 32]; c[b][1] += in[(2 * b + 1) * 32]; }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) rrp[a] += in[(20 + a) * 32];
+    }
+    tail32_warp<0>(c, rrp, hv_item[h], scratch, sLF, srr0, p, lane);
 }
 
 #ifdef BPMF_STREAM_PROBES
@@ -646,12 +738,12 @@ cudaError_t launch_stats_partial32(bpmf_gpu_ctx *c, int side)
     return cudaGetLastError();
 }
 
-cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha)
+static cudaError_t launch_stream_range(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha, int from, int to)
 {
     SideDev &s = c->side[side];
     const SideDev &o = c->side[1 - side];
     StreamArgs p;
-    p.from = s.from; p.to = s.to; p.iter = iter; p.alpha = alpha; p.mean_rating = s.mean_rating;
+    p.from = from; p.to = to; p.iter = iter; p.alpha = alpha; p.mean_rating = s.mean_rating;
     p.colptr = s.colptr; p.rowidx = s.rowidx; p.val = s.val;
     p.other = o.items; p.items = s.items;
     p.npeers = s.npeers; p.peers = s.peers_dev;
@@ -659,7 +751,7 @@ cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, doub
     p.work_counter = s.work_counter; p.err = c->d_err; p.zero_row = c->d_zero_row;
     cudaError_t e = cudaMemsetAsync(s.work_counter, 0, 2 * sizeof(unsigned int), c->stream);
     if (e != cudaSuccess) return e;
-    const long long n = (long long)s.to - s.from;
+    const long long n = (long long)to - from;
     if (n < 1) return cudaSuccess;
     {   // the last ~4 items per resident warp are handed out CLAIM_TAIL at a time (v3 kernel); bulk region is a multiple of CLAIM
         static const int tail_per_warp = [] { const char *v = getenv("BPMF_STREAM_TAIL"); return v ? atoi(v) : 8; }();
@@ -667,11 +759,11 @@ cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, doub
         long long bulk = n - tail_items;
         if (bulk < 0) bulk = 0;
         bulk -= bulk % CLAIM;
-        p.bulk_end = s.from + (int)bulk;
+        p.bulk_end = from + (int)bulk;
         if (c->stream_tail >= 0) {
             tail_items = (long long)c->sm_count * 16 * c->stream_tail;
             bulk = n - tail_items; if (bulk < 0) bulk = 0; bulk -= bulk % CLAIM;
-            p.bulk_end = s.from + (int)bulk;
+            p.bulk_end = from + (int)bulk;
         }
     }
     // tuning knob (bench_micro/tune_stream.py): "<version><stages><warps>", e.g. 3216 = v3, 2 stages x 16 warps.
@@ -753,5 +845,45 @@ cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, doub
     c->launches++;
     return e;
 }
+
+cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha)
+{
+    SideDev &s = c->side[side];
+    const SideDev &o = c->side[1 - side];
+    // heavy items of [from, to): the stream kernel runs on the ranges between them
+    int first = 0, last = 0;
+    while (first < s.n_heavy && s.h_heavy_item[first] < s.from) ++first;
+    last = first;
+    while (last < s.n_heavy && s.h_heavy_item[last] < s.to) ++last;
+    if (first == last) return launch_stream_range(c, side, iter, alpha, s.from, s.to);
+    int lo = s.from;
+    for (int h = first; h <= last; ++h) {
+        const int hi = h < last ? s.h_heavy_item[h] : s.to;
+        if (hi > lo) {
+            const cudaError_t e = launch_stream_range(c, side, iter, alpha, lo, hi);
+            if (e != cudaSuccess) return e;
+        }
+        lo = hi + 1;
+    }
+    StreamArgs p;
+    p.from = s.from; p.to = s.to; p.iter = iter; p.alpha = alpha; p.mean_rating = s.mean_rating;
+    p.colptr = s.colptr; p.rowidx = s.rowidx; p.val = s.val;
+    p.other = o.items; p.items = s.items;
+    p.npeers = s.npeers; p.peers = s.peers_dev;
+    p.mu = s.hp.mu; p.LambdaF = s.hp.LambdaF;
+    p.work_counter = s.work_counter; p.err = c->d_err; p.zero_row = c->d_zero_row; p.bulk_end = s.to;
+    const int ch0 = s.h_heavy_first[first], ch1 = s.h_heavy_first[last];
+    heavy_gram32_kernel<<<(ch1 - ch0 + 3) / 4, 128, 0, c->stream>>>(p, ch1 - ch0, s.hv_p0 + ch0, s.hv_p1 + ch0,
+                                                                     s.hv_partials + (size_t)ch0 * HEAVY_PART);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    heavy_tail32_kernel<<<last - first, 32, 0, c->stream>>>(p, s.hv_item + first, s.hv_first + first, s.hv_partials);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+int heavy_chunk_size() { return HEAVY_CHUNK; }
+int heavy_partial_doubles() { return HEAVY_PART; }
 
 }  // namespace bpmf

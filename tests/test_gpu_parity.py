@@ -382,3 +382,51 @@ def test_propagated_posterior_priors(gpu, K):
     ctx.sample_items(MOVIES, 4, 2.0, gpu.KERNEL_STREAM if K == 32 else gpu.KERNEL_AUTO)
     ctx.sync()
     ctx.close()
+
+
+def test_heavy_items_chunked_path(gpu):
+    """Skew handling: items far heavier than the rest are cut into chunks (partial Grams by separate warps, added in a
+    fixed order) and the stream kernel runs on the index ranges between them. Two hot movies of ~5000 and ~2600 ratings
+    (threshold lowered to 2100 so that both take the chunked path: 3 and 2 chunks), against the oracle and against the
+    plain path (same context type without the threshold)."""
+    K = 32
+    rng = np.random.default_rng(8)
+    nr, nc = 6000, 400
+    rows = rng.integers(0, nr, size=30000); cols = rng.integers(0, nc, size=30000)
+    hot_a = rng.choice(nr, size=5000, replace=False); hot_b = rng.choice(nr, size=2600, replace=False)
+    rows = np.concatenate([rows, hot_a, hot_b]); cols = np.concatenate([cols, np.full(5000, 7), np.full(2600, 399)])
+    key = rows.astype(np.int64) * nc + cols
+    _, first = np.unique(key, return_index=True)
+    rows, cols = rows[first].astype(np.int32), cols[first].astype(np.int32)
+    vals = rng.normal(3.5, 1.0, size=len(rows))
+    train = ((nr, nc), rows, cols, vals)
+    test = ((nr, nc), rows[:50].copy(), cols[:50].copy(), vals[:50].copy())
+    orc = util.make_oracle(K, train, test)
+    chunked = util.make_gpu_from_oracle(orc, K, heavy_threshold=2100)
+    plain = util.make_gpu_from_oracle(orc, K)
+    for ctx in (chunked, plain):
+        _prime(orc, ctx, K, 5)
+    for it in (1, 2):
+        orc.set_iter(MOVIES, it)
+        orc.sample_range(MOVIES, 0, orc.num(MOVIES))
+        ref = orc.items(MOVIES)
+        outs = []
+        for ctx in (chunked, plain):
+            ctx.sample_items(MOVIES, it, 2.0, gpu.KERNEL_STREAM)
+            got = ctx.get_items(MOVIES)
+            assert np.abs(got - ref).max() <= TOL_ITEMS * max(1.0, np.abs(ref).max()), it
+            outs.append(got)
+            ctx.set_items(MOVIES, ref)
+        # every item that is not heavy is computed by the same code in the same order: bit-identical
+        mask = np.ones(nc, bool); mask[[7, 399]] = False
+        assert outs[0][mask].tobytes() == outs[1][mask].tobytes()
+    assert chunked.launch_count() > plain.launch_count()
+    # a sub-range that ends between the two heavy items (multi-GPU ranges)
+    chunked.set_range(MOVIES, 3, 200)
+    chunked.sample_items(MOVIES, 3, 2.0, gpu.KERNEL_STREAM)
+    orc.set_iter(MOVIES, 3)
+    orc.sample_range(MOVIES, 3, 200)
+    got, ref = chunked.get_items(MOVIES), orc.items(MOVIES)
+    assert np.abs(got - ref).max() <= TOL_ITEMS * max(1.0, np.abs(ref).max())
+    for ctx in (chunked, plain):
+        ctx.close()

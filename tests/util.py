@@ -48,10 +48,12 @@ def make_oracle(K, train, test, **kw):
                     np.asarray(tr, np.int32), np.asarray(tc, np.int32), np.asarray(tv, np.float64), **kw)
 
 
-def make_gpu_from_oracle(orc, K, device=0):
+def make_gpu_from_oracle(orc, K, device=0, heavy_threshold=None):
     """A GPU context loaded with exactly the CSC structure / mean ratings the oracle built."""
     import bpmf_b200
     ctx = bpmf_b200.Context(K, device)
+    if heavy_threshold:
+        ctx.set_heavy_threshold(heavy_threshold)
     for side in (MOVIES, USERS):
         colptr, rowidx, val = orc.csc(side, 0)
         ctx.load_side(side, orc.num(side), orc.num(1 - side), colptr, rowidx, val, orc.mean_rating(side))
