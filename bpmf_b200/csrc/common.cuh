@@ -103,7 +103,7 @@ struct bpmf_gpu_ctx {
     long long ev_count = 0;      // item-kernel launches timed so far
     long long ev_read = 0;       // launches already returned by bpmf_gpu_items_kernel_time
     long long launches = 0;
-    long long heavy_threshold = 16384;    // items with more ratings go through the chunked path (K == 32)
+    long long heavy_threshold = 4096;    // items with more ratings go through the chunked path (K == 32)
     int stream_cfg = 0;                   // 0 = default; see launch_items_stream32
     int stream_tail = -1;                 // items per warp claimed in small groups at the end of a sweep; -1 = default
     std::string err;

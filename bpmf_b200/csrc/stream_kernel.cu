@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs
 // depend on scheduling) and runs the same tail as the stream kernel. The stream kernel is launched on the index ranges
 // between the heavy items.
 // =====================================================================================================================
-constexpr int HEAVY_CHUNK = 2048;
+constexpr int HEAVY_CHUNK = 1024;
 constexpr int HEAVY_PART = 24 * 32;           // doubles per partial: c[10][2] + rrp[4] per lane, in the DMMA layout
 
 __global__ void __launch_bounds__(128) heavy_gram32_kernel(StreamArgs p, int nchunks, const int64_t *__restrict__ ch_p0,

@@ -388,7 +388,7 @@ def test_heavy_items_chunked_path(gpu):
     """Skew handling: items far heavier than the rest are cut into chunks (partial Grams by separate warps, added in a
     fixed order) and the stream kernel runs on the index ranges between them. Two hot movies of ~5000 and ~2600 ratings
     (threshold lowered to 2100 so that both take the chunked path: 3 and 2 chunks), against the oracle and against the
-    plain path (same context type without the threshold)."""
+    plain path (threshold out of reach)."""
     K = 32
     rng = np.random.default_rng(8)
     nr, nc = 6000, 400
@@ -403,7 +403,7 @@ def test_heavy_items_chunked_path(gpu):
     test = ((nr, nc), rows[:50].copy(), cols[:50].copy(), vals[:50].copy())
     orc = util.make_oracle(K, train, test)
     chunked = util.make_gpu_from_oracle(orc, K, heavy_threshold=2100)
-    plain = util.make_gpu_from_oracle(orc, K)
+    plain = util.make_gpu_from_oracle(orc, K, heavy_threshold=1 << 40)
     for ctx in (chunked, plain):
         _prime(orc, ctx, K, 5)
     for it in (1, 2):
