@@ -13,6 +13,7 @@ Both compressed forms the two sweeps need are returned:
 exactly the `Sys::M` of each side (c++/sample.cpp:112-137): int32 inner indices ascending.
 """
 import os
+import sys
 import time
 
 import numpy as np
@@ -84,7 +85,7 @@ def generate(nrows, ncols, mean_nnz_row, seed, rank=16, test_frac=0.01, verbose=
     np.cumsum(np.bincount(rows, minlength=nrows), out=r.u_ptr[1:])
     r.u_idx, r.u_val = cols, vals
     if verbose:
-        print("  [synthetic] %d x %d, %d nnz by rows in %.1fs" % (nrows, ncols, r.nnz, time.time() - t0), flush=True)
+        print("  [synthetic] %d x %d, %d nnz by rows in %.1fs" % (nrows, ncols, r.nnz, time.time() - t0), flush=True, file=sys.stderr)
     # the other orientation: scipy's csr->csc is O(nnz) and keeps row ids ascending inside a column
     import scipy.sparse as sp
     csr = sp.csr_matrix((vals, cols, r.u_ptr.astype(np.int64)), shape=(nrows, ncols))
@@ -98,7 +99,7 @@ def generate(nrows, ncols, mean_nnz_row, seed, rank=16, test_frac=0.01, verbose=
     r.t_cols = rng.integers(0, ncols, nt).astype(np.int32)
     r.t_vals = _planted_values(rng, r.t_rows, r.t_cols, U, V)
     if verbose:
-        print("  [synthetic] both orientations + %d test entries in %.1fs" % (nt, time.time() - t0), flush=True)
+        print("  [synthetic] both orientations + %d test entries in %.1fs" % (nt, time.time() - t0), flush=True, file=sys.stderr)
     return r
 
 
