@@ -281,8 +281,16 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB >= 6 ? 4 : 8)) 
         if (warp == 0) {
             constexpr int R = (K + 31) / 32;
             double v[R];
+            // this lane's rows i = lane + 32 r: start of tile row i / 8 (+ row inside the tile), and i's offset as a COLUMN
+            const double *rowp[R];
+            int colo[R];
 #pragma unroll
-            for (int r = 0; r < R; ++r) v[r] = (lane + 32 * r < K) ? b[lane + 32 * r] : 0.0;
+            for (int r = 0; r < R; ++r) {
+                const int i = lane + 32 * r, I = i >> 3;
+                v[r] = (i < K) ? b[i] : 0.0;
+                rowp[r] = MMp + (I * (I + 1) / 2) * 64 + 8 * (i & 7);
+                colo[r] = I * 64 + (i & 7);
+            }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
 #pragma unroll 4
@@ -290,10 +298,11 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB >= 6 ? 4 : 8)) 
                     const int k = 32 * r + kk;
                     if (k >= K) break;
                     const double yk = __shfl_sync(FULL, v[r], kk);
+                    const int ko = (k >> 3) * 64 + (k & 7);                  // Lu(i,k) = rowp(i)[ko]
 #pragma unroll
                     for (int r2 = r; r2 < R; ++r2) {
                         const int i = lane + 32 * r2;
-                        if (i > k && i < K) v[r2] = fma(-MMp[C::tile(i >> 3, k >> 3) + 8 * (i & 7) + (k & 7)], yk, v[r2]);
+                        if (i > k && i < K) v[r2] = fma(-rowp[r2][ko], yk, v[r2]);
                     }
                 }
             }
@@ -309,10 +318,11 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB >= 6 ? 4 : 8)) 
                     const int k = 32 * r + kk;
                     if (k >= K) continue;
                     const double xk = __shfl_sync(FULL, v[r], kk);
+                    const double *krow = MMp + ((k >> 3) * ((k >> 3) + 1) / 2) * 64 + 8 * (k & 7);   // Lu(k,i) = krow[colo(i)]
 #pragma unroll
                     for (int r2 = 0; r2 <= r; ++r2) {
                         const int i = lane + 32 * r2;
-                        if (i < k) v[r2] = fma(-MMp[C::tile(k >> 3, i >> 3) + 8 * (k & 7) + (i & 7)], xk, v[r2]);
+                        if (i < k) v[r2] = fma(-krow[colo[r2]], xk, v[r2]);
                     }
                 }
             }
