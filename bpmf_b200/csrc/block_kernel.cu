@@ -2,10 +2,13 @@
 // other than 32 (16, 48, 64, 80, 96, 112, 128) on sm_100a: ONE CTA PER ITEM, NB/2 warps (NB = K / 8).
 //
 //   gather  The K-vectors of the item's ratings are staged global -> shared with cp.async in stages of 16 rows (row pitch
-//           8K + 32 bytes: conflict-free fragment loads), two stages in flight, every thread copying four 16-byte chunks.
+//           8K + 32 bytes: conflict-free fragment loads), three stages in flight, every thread copying four 16-byte chunks
+//           whose row indices were loaded one stage earlier.
 //   Gram    fp64 tensor cores (mma.sync.m8n8k4, DMMA). The lower triangle of NB x NB blocks of 8 x 8 is spread over the
 //           warps' REGISTERS: warp w owns block rows w and NB-1-w (NB + 1 blocks, 2 NB + 2 accumulator doubles per
-//           lane). Per four ratings it loads NB - w fragments and issues NB + 1 DMMAs; the rhs costs 2 DFMAs.
+//           lane). Per four ratings it loads NB - w fragments and issues NB + 1 DMMAs; the rhs costs 2 DFMAs. Only that
+//           inner part is instantiated per warp role (the operands of a DMMA must be registers); the stage loop around it
+//           is shared code — with one copy of the whole loop per warp the kernel thrashed the instruction cache.
 //   tail    MM = LambdaF + alpha G goes to shared memory as 8 x 8 row-major TILES of the lower block triangle (they alias
 //           the gather ring, idle by then). Blocked right-looking LDL^T: per block column every warp factorises the diagonal
 //           tile redundantly in registers (warp shuffles, as the K = 32 kernel does) together with its share of the panel
@@ -18,13 +21,15 @@
 #include "common.cuh"
 #include "rng.cuh"
 
+#include <cstdlib>
+
 namespace bpmf {
 
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int SR = 16;   // ratings per stage
-constexpr int NS = 2;    // stages in flight
+constexpr int NS = 3;    // stages in flight
 
 struct BlockArgs {
     int from, to;
@@ -40,6 +45,7 @@ struct BlockArgs {
     const double *mu, *LambdaF;
     unsigned int *work_counter;
     unsigned long long *err;
+    int dbg;   // timing probes (BPMF_BLOCK_DBG): 1 = no factorisation / solves, 2 = no Gram DMMAs, 4 = no solves; 0 = the product
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
@@ -79,83 +85,33 @@ __device__ __forceinline__ double fast_rcp(double p)
     return fma(r, t, r);
 }
 
-// The Gram of one item for warp W (compile-time, so that the accumulators are registers): block rows W and NB-1-W.
+// The Gram of the (at most SR) ratings of one stage for warp W (compile-time: the operands of a DMMA are registers):
+// acc[0 .. W] = blocks (W, 0..W), acc[W+1 .. NB] = blocks (NB-1-W, 0..NB-1-W). Only this part of the per-item code differs
+// between the warps; everything else is shared, which keeps the instruction footprint small.
 template <int NB, int W>
-__device__ __forceinline__ void item_gram(const BlockArgs &p, unsigned char *smem, int64_t ps, int64_t pe, double *MMp, double *rr)
+__device__ __forceinline__ void gram_groups(double (&acc)[NB + 1][2], double &r0, double &r1, const unsigned char *stg, const double *swp,
+                                            const int left, const int g, const int t, const int dbg)
 {
     using C = Cfg<NB>;
-    constexpr int K = C::K, T = C::T, R0 = W, R1 = NB - 1 - W, NF = NB - W;   // fragments f[0 .. NF-1] cover both rows
-    const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(smem);
-    double *sw = reinterpret_cast<double *>(smem + C::W_OFF);
-    double c0[R0 + 1][2], c1[R1 + 1][2], r0 = 0.0, r1 = 0.0;
+    constexpr int R0 = W, R1 = NB - 1 - W, NF = NB - W;   // fragments f[0 .. NF-1] cover both rows
+#pragma unroll 1
+    for (int q = 0; q * 4 < left; ++q) {
+        const unsigned char *row = stg + (4 * q + t) * C::ROWB + g * 8;
+        double f[NF];
 #pragma unroll
-    for (int j = 0; j <= R0; ++j) { c0[j][0] = 0.0; c0[j][1] = 0.0; }
+        for (int j = 0; j < NF; ++j) f[j] = *reinterpret_cast<const double *>(row + j * 64);
+        const double w = swp[4 * q + t];
+        if (!(dbg & 2)) {
 #pragma unroll
-    for (int j = 0; j <= R1; ++j) { c1[j][0] = 0.0; c1[j][1] = 0.0; }
-
-    const int nst = (int)((pe - ps + SR - 1) / SR);
-    // this thread's four 16-byte chunks of a stage: rows rq, rq + 4, rq + 8, rq + 12, chunk cq of the row
-    const int rq = tid / (K / 2), cq = tid % (K / 2);
-    auto issue = [&](int s) {
-        if (s < nst) {
-            const int64_t p0 = ps + (int64_t)s * SR;
-            const int slot = s % NS;
+            for (int j = 0; j <= R0; ++j) dmma884(acc[j][0], acc[j][1], f[R0], f[j]);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int r = rq + 4 * j;
-                const bool live = p0 + r < pe;
-                const unsigned row = live ? (unsigned)__ldg(p.rowidx + p0 + r) : 0u;
-                cp_async16(ring_s + slot * C::STAGE + r * C::ROWB + cq * 16,
-                           reinterpret_cast<const unsigned char *>(p.other) + (size_t)row * (K * 8) + cq * 16, live ? 16 : 0);
-            }
-            if (tid < SR) sw[slot * SR + tid] = (p0 + tid < pe) ? (__ldg(p.val + p0 + tid) - p.mean_rating) * p.alpha : 0.0;
+            for (int j = 0; j <= R1; ++j) dmma884(acc[R0 + 1 + j][0], acc[R0 + 1 + j][1], f[R1], f[j]);
+        } else {
+            acc[0][0] += f[0] * f[NF - 1];
         }
-        cp_async_commit();
-    };
-#pragma unroll 1
-    for (int s = 0; s < NS; ++s) issue(s);
-#pragma unroll 1
-    for (int s = 0; s < nst; ++s) {
-        cp_async_wait<NS - 1>();
-        __syncthreads();
-        const unsigned char *stg = smem + (s % NS) * C::STAGE;
-        const int left = (int)min((int64_t)SR, pe - (ps + (int64_t)s * SR));
-#pragma unroll 1
-        for (int q = 0; q * 4 < left; ++q) {
-            const unsigned char *row = stg + (4 * q + t) * C::ROWB + g * 8;
-            double f[NF];
-#pragma unroll
-            for (int j = 0; j < NF; ++j) f[j] = *reinterpret_cast<const double *>(row + j * 64);
-            const double w = sw[(s % NS) * SR + 4 * q + t];
-#pragma unroll
-            for (int j = 0; j <= R0; ++j) dmma884(c0[j][0], c0[j][1], f[R0], f[j]);
-#pragma unroll
-            for (int j = 0; j <= R1; ++j) dmma884(c1[j][0], c1[j][1], f[R1], f[j]);
-            r0 = fma(f[R0], w, r0);
-            r1 = fma(f[R1], w, r1);
-        }
-        __syncthreads();                  // the slot is free
-        issue(s + NS);
+        r0 = fma(f[R0], w, r0);
+        r1 = fma(f[R1], w, r1);
     }
-    cp_async_wait<0>();
-    __syncthreads();                      // the ring is dead: MM may overwrite it
-    // MM = LambdaF + alpha * G (sample.cpp:297-298) into the tiles: lane (g, t) owns elements (g, 2t) and (g, 2t + 1)
-    auto put = [&](int I, int J, const double (&cc)[2]) {
-        const int i = 8 * I + g, k = 8 * J + 2 * t;
-        double2 v;
-        v.x = fma(p.alpha, cc[0], __ldg(p.LambdaF + i + (size_t)k * K));
-        v.y = fma(p.alpha, cc[1], __ldg(p.LambdaF + i + (size_t)(k + 1) * K));
-        *reinterpret_cast<double2 *>(MMp + C::tile(I, J) + 8 * g + 2 * t) = v;
-    };
-#pragma unroll
-    for (int j = 0; j <= R0; ++j) put(R0, j, c0[j]);
-#pragma unroll
-    for (int j = 0; j <= R1; ++j) put(R1, j, c1[j]);
-    // rhs: sum over the quad's four ratings-of-a-group, + LambdaF * mu (sample.cpp:285), which the caller put into rr
-    r0 += __shfl_xor_sync(FULL, r0, 1); r0 += __shfl_xor_sync(FULL, r0, 2);
-    r1 += __shfl_xor_sync(FULL, r1, 1); r1 += __shfl_xor_sync(FULL, r1, 2);
-    if (t == 0) { rr[8 * R0 + g] += r0; rr[8 * R1 + g] += r1; }
 }
 
 template <int NB>
@@ -189,17 +145,83 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB >= 6 ? 4 : 8)) 
         if (warp == NWB - 1) warp_randn((uint32_t)(((long long)idx + 1) * (long long)K * ((long long)p.iter + 1)), K, z);
         __syncthreads();
         const int64_t ps = __ldg(p.colptr + idx), pe = __ldg(p.colptr + idx + 1);
-        switch (warp) {                   // accumulators must be registers: one instantiation per warp role
-        case 0: item_gram<NB, 0>(p, smem, ps, pe, MMp, b); break;
-        case 1: if constexpr (NWB > 1) item_gram<NB, 1>(p, smem, ps, pe, MMp, b); break;
-        case 2: if constexpr (NWB > 2) item_gram<NB, 2>(p, smem, ps, pe, MMp, b); break;
-        case 3: if constexpr (NWB > 3) item_gram<NB, 3>(p, smem, ps, pe, MMp, b); break;
-        case 4: if constexpr (NWB > 4) item_gram<NB, 4>(p, smem, ps, pe, MMp, b); break;
-        case 5: if constexpr (NWB > 5) item_gram<NB, 5>(p, smem, ps, pe, MMp, b); break;
-        case 6: if constexpr (NWB > 6) item_gram<NB, 6>(p, smem, ps, pe, MMp, b); break;
-        default: if constexpr (NWB > 7) item_gram<NB, 7>(p, smem, ps, pe, MMp, b); break;
+        {
+            // ---- gather + Gram of the item (computeMuLambda, sample.cpp:251-257)
+            const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(smem);
+            double *sw = reinterpret_cast<double *>(smem + C::W_OFF);
+            double acc[NB + 1][2], r0 = 0.0, r1 = 0.0;
+#pragma unroll
+            for (int n = 0; n <= NB; ++n) { acc[n][0] = 0.0; acc[n][1] = 0.0; }
+            const int nst = (int)((pe - ps + SR - 1) / SR);
+            // this thread's four 16-byte chunks of a stage: rows rq, rq + 4, rq + 8, rq + 12, chunk cq of the row
+            const int rq = tid / (K / 2), cq = tid % (K / 2);
+            unsigned pre[4];              // row indices of the NEXT stage to be issued, loaded one stage-iteration ahead
+            auto load_rows = [&](int st) {
+                const int64_t p0 = ps + (int64_t)st * SR;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) pre[j] = (p0 + rq + 4 * j < pe) ? (unsigned)__ldg(p.rowidx + p0 + rq + 4 * j) : 0u;
+            };
+            auto issue = [&](int st) {
+                if (st < nst) {
+                    const int64_t p0 = ps + (int64_t)st * SR;
+                    const int slot = st % NS;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = rq + 4 * j;
+                        cp_async16(ring_s + slot * C::STAGE + r * C::ROWB + cq * 16,
+                                   reinterpret_cast<const unsigned char *>(p.other) + (size_t)pre[j] * (K * 8) + cq * 16, (p0 + r < pe) ? 16 : 0);
+                    }
+                    if (tid < SR) sw[slot * SR + tid] = (p0 + tid < pe) ? (__ldg(p.val + p0 + tid) - p.mean_rating) * p.alpha : 0.0;
+                }
+                cp_async_commit();
+            };
+#pragma unroll 1
+            for (int st = 0; st < NS; ++st) { load_rows(st); issue(st); }
+            load_rows(NS);
+#pragma unroll 1
+            for (int st = 0; st < nst; ++st) {
+                cp_async_wait<NS - 1>();
+                __syncthreads();
+                const unsigned char *stg = smem + (st % NS) * C::STAGE;
+                const double *swp = sw + (st % NS) * SR;
+                const int left = (int)min((int64_t)SR, pe - (ps + (int64_t)st * SR));
+                switch (warp) {           // the operands of a DMMA are registers: one small instantiation per warp role
+                case 0: gram_groups<NB, 0>(acc, r0, r1, stg, swp, left, g, t, p.dbg); break;
+                case 1: if constexpr (NWB > 1) gram_groups<NB, 1>(acc, r0, r1, stg, swp, left, g, t, p.dbg); break;
+                case 2: if constexpr (NWB > 2) gram_groups<NB, 2>(acc, r0, r1, stg, swp, left, g, t, p.dbg); break;
+                case 3: if constexpr (NWB > 3) gram_groups<NB, 3>(acc, r0, r1, stg, swp, left, g, t, p.dbg); break;
+                case 4: if constexpr (NWB > 4) gram_groups<NB, 4>(acc, r0, r1, stg, swp, left, g, t, p.dbg); break;
+                case 5: if constexpr (NWB > 5) gram_groups<NB, 5>(acc, r0, r1, stg, swp, left, g, t, p.dbg); break;
+                case 6: if constexpr (NWB > 6) gram_groups<NB, 6>(acc, r0, r1, stg, swp, left, g, t, p.dbg); break;
+                default: if constexpr (NWB > 7) gram_groups<NB, 7>(acc, r0, r1, stg, swp, left, g, t, p.dbg); break;
+                }
+                __syncthreads();          // the slot is free
+                issue(st + NS);
+                load_rows(st + NS + 1);
+            }
+            cp_async_wait<0>();
+            __syncthreads();              // the ring is dead: the tiles may overwrite it
+            // MM = LambdaF + alpha * G (sample.cpp:297-298) into the tiles: lane (g, t) owns elements (g, 2t), (g, 2t + 1).
+            // acc[n] is block (warp, n) for n <= warp and block (NB-1-warp, n-warp-1) after that.
+#pragma unroll
+            for (int n = 0; n <= NB; ++n) {
+                const int I = (n <= warp) ? warp : NB - 1 - warp, J = (n <= warp) ? n : n - warp - 1;
+                const int i = 8 * I + g, k = 8 * J + 2 * t;
+                double2 v;
+                v.x = fma(p.alpha, acc[n][0], __ldg(p.LambdaF + i + (size_t)k * K));
+                v.y = fma(p.alpha, acc[n][1], __ldg(p.LambdaF + i + (size_t)(k + 1) * K));
+                *reinterpret_cast<double2 *>(MMp + C::tile(I, J) + 8 * g + 2 * t) = v;
+            }
+            // rhs: sum over the quad's four ratings-of-a-group, on top of LambdaF * mu (sample.cpp:285) already in b
+            r0 += __shfl_xor_sync(FULL, r0, 1); r0 += __shfl_xor_sync(FULL, r0, 2);
+            r1 += __shfl_xor_sync(FULL, r1, 1); r1 += __shfl_xor_sync(FULL, r1, 2);
+            if (t == 0) { b[8 * warp + g] += r0; b[8 * (NB - 1 - warp) + g] += r1; }
         }
         __syncthreads();
+        if (p.dbg & 1) {
+            if (warp == 0 && lane < 8) p.items[(size_t)idx * K + lane] = MMp[lane] + b[lane] + z[lane];
+            continue;
+        }
         // ---- chol.compute(MM) (sample.cpp:306) as MM = Lu D Lu^T, blocked by 8, on the tiles
 #pragma unroll 1
         for (int kb = 0; kb < NB; ++kb) {
@@ -278,7 +300,7 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB >= 6 ? 4 : 8)) 
         }
         // ---- L \ rr; rr += nrandn; L^T \ rr (sample.cpp:321-323) with L = Lu D^(1/2):  x = Lu^-T (D^-1 Lu^-1 b + D^(-1/2) z)
         // by warp 0, the vector in registers: lane holds rows lane + 32 r. Lu(i,k) = tile(i / 8, k / 8)[8 (i % 8) + k % 8].
-        if (warp == 0) {
+        if (warp == 0 && !(p.dbg & 4)) {
             constexpr int R = (K + 31) / 32;
             double v[R];
             // this lane's rows i = lane + 32 r: start of tile row i / 8 (+ row inside the tile), and i's offset as a COLUMN
@@ -373,6 +395,8 @@ cudaError_t launch_items_block(bpmf_gpu_ctx *c, int side, uint32_t iter, double 
     p.npeers = s.npeers; p.peers = s.peers_dev;
     p.mu = s.hp.mu; p.LambdaF = s.hp.LambdaF;
     p.work_counter = s.work_counter; p.err = c->d_err;
+    static const int dbg = [] { const char *v = getenv("BPMF_BLOCK_DBG"); return v ? atoi(v) : 0; }();
+    p.dbg = dbg;
     cudaError_t e = cudaMemsetAsync(s.work_counter, 0, sizeof(unsigned int), c->stream);
     if (e != cudaSuccess) return e;
     const long long n = (long long)s.to - s.from;
