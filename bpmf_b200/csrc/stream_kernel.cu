@@ -1,22 +1,24 @@
 // stream_kernel.cu — the fused per-item conditional update for num_latent == 32 on sm_100a ("stream" variant):
-// c++/sample.cpp:263-336 + 248-258 as ONE persistent kernel, one warp per item. The header below describes the common
-// structure (gather ring, DMMA Gram, in-register factorisation); "Version 3" further down is what is launched.
+// c++/sample.cpp:263-336 + 248-258 as ONE persistent kernel (items_stream32v3_kernel), one warp per item, 20 warps per SM.
 //
 //   gather   Every warp owns a ring of NS shared-memory stages of SR latent rows (256 B each, padded to 288 B).
 //            The rows of the other factor named by the item's CSR entries are copied global -> shared with
 //            cp.async (LDGSTS.128, L1-bypassing, zero-fill for the ragged end), NS-1 stages ahead of the
 //            arithmetic and ACROSS item boundaries, so the HBM/L2 latency of the random 256-byte gathers is
-//            overlapped with the tensor-core work and with the Cholesky/solve tail of the previous item.
-//            Consecutive items are claimed CLAIM at a time from a global counter: their ratings are contiguous in
-//            the CSR arrays, so indices and values stream in coalesced 32-entry batches, one batch ahead.
+//            overlapped with the tensor-core work and with the factorisation / solve tail of the previous item.
+//            Consecutive items are claimed CLAIM at a time from a global counter (the last ~1 % of a sweep CLAIM_TAIL at
+//            a time): their ratings are contiguous in the CSR arrays, so the <= 16 indices and values of a stage are one
+//            coalesced load, issued a whole stage ahead.
 //   Gram     fp64 tensor cores: mma.sync.m8n8k4 (DMMA). Lane 4g+t holds f[a] = y_t[8a+g] of rating t of a group of
 //            four; f[I] is the A fragment and f[J] the B fragment of block (I,J), so ten DMMAs update the lower
 //            triangle of 8x8 blocks and every gathered value is read from shared memory exactly once. The 288-byte
 //            row stride makes those fragment loads bank-conflict free. rr += y * w is 4 DFMAs per group.
-//   tail     MM = LambdaF + alpha * G stays in the DMMA accumulator layout (20 registers per lane): blocked
-//            right-looking Cholesky, 8x8 diagonal blocks factored with warp shuffles, panel columns scaled in the
-//            same step, trailing blocks updated with DMMAs again. L is then scattered (packed, 4.1 KB) to shared
-//            memory for the two triangular solves in "lane j owns row j" form; K normals from Philox4x32-10 (rng.cuh).
+//   tail     tail32_warp: MM = LambdaF + alpha * G stays in the DMMA accumulator layout (20 registers per lane);
+//            square-root-free blocked LDL^T (8x8 diagonal blocks with warp shuffles, trailing blocks with DMMAs), the
+//            unit-lower factor goes to shared memory divided by the pivots, the two triangular solves are shuffle + FMA
+//            chains in "lane j owns row j" form; K normals from Philox4x32-10 (rng.cuh).
+//   skew     items far heavier than the rest are cut into chunks (heavy_gram32_kernel / heavy_tail32_kernel below).
+// Variants that were built and measured slower live in stream_experiments.cuh (compiled only with BPMF_STREAM_PROBES).
 //
 // Roofline: nnz * 256 B gathered per sweep against HBM; 2.5 DMMA (1280 flop) per rating against the fp64
 // tensor pipe (37 TFLOP/s measured): at K = 32 the two are co-limiting (3.9 ms vs 3.5 ms for 100M ratings).
