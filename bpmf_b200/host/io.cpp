@@ -3,6 +3,7 @@
 #include "io.h"
 
 #include <cctype>
+#include <charconv>
 #include <cerrno>
 #include <cstdio>
 #include <cstdlib>
@@ -10,6 +11,9 @@
 #include <limits>
 
 #include <zlib.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 namespace bpmf_host {
 
@@ -117,6 +121,7 @@ void read_dense_bin(const std::string &bytes, DenseMatrixD &X)
 struct TextCursor {
     const char *p, *end;
     explicit TextCursor(const std::string &s) : p(s.data()), end(s.data() + s.size()) {}
+    TextCursor(const char *b, const char *e) : p(b), end(e) {}
     bool eof() const { return p >= end; }
     std::string line()
     {
@@ -150,6 +155,10 @@ struct TextCursor {
     {
         skip_ws();
         if (p >= end) return false;
+        const char *q = (*p == '+') ? p + 1 : p;               // from_chars does not take a leading '+'
+        const std::from_chars_result r = std::from_chars(q, end, v);
+        if (r.ec == std::errc() ) { p = r.ptr; return true; }
+        // "inf" / "nan" spellings and out-of-range values: fall back to strtod on a bounded copy
         char tmp[64];
         const size_t n = std::min<size_t>(sizeof tmp - 1, (size_t)(end - p));
         memcpy(tmp, p, n);
@@ -197,14 +206,51 @@ void read_mm_sparse(const std::string &bytes, SparseMatrixD &X)
     uint64_t nrows, ncols, nnz;
     if (!c.u64(nrows) || !c.u64(ncols) || !c.u64(nnz)) fail("Could not get 'rows', 'cols', 'nnz' values for coordinate matrix format");
     const bool pattern = h.field == "PATTERN";
-    std::vector<Triplet> t((size_t)nnz);
-    for (uint64_t i = 0; i < nnz; ++i) {
-        c.skip_comments();
-        uint64_t r, col;
-        double v = 1.0;
-        if (!c.u64(r) || !c.u64(col) || (!pattern && !c.f64(v))) fail("Could not parse an entry line for coordinate matrix format");
-        t[(size_t)i].row = (int32_t)(r - 1); t[(size_t)i].col = (int32_t)(col - 1); t[(size_t)i].val = v;
+    // The entry lines are parsed in parallel: the rest of the buffer is cut at line ends into one piece per thread, every
+    // piece is parsed into its own list, and the lists are concatenated in file order (duplicates are summed in input
+    // order by from_triplets, as Eigen's setFromTriplets does).
+    const char *b = c.p, *e = c.end;
+    int nt = 1;
+#ifdef _OPENMP
+    nt = std::max(1, std::min(omp_get_max_threads(), (int)((e - b) / (1 << 20)) + 1));
+#endif
+    std::vector<const char *> cut((size_t)nt + 1, e);
+    cut[0] = b;
+    for (int i = 1; i < nt; ++i) {
+        const char *q = b + (size_t)(e - b) * (size_t)i / (size_t)nt;
+        q = (const char *)memchr(q, '\n', (size_t)(e - q));
+        cut[(size_t)i] = q ? q + 1 : e;
     }
+    std::vector<std::vector<Triplet>> part((size_t)nt);
+    std::vector<int> bad((size_t)nt, 0);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1) num_threads(nt)
+#endif
+    for (int i = 0; i < nt; ++i) {
+        TextCursor pc(cut[(size_t)i], cut[(size_t)i + 1]);
+        std::vector<Triplet> &out = part[(size_t)i];
+        out.reserve((size_t)(nnz / (uint64_t)nt) + 16);
+        for (;;) {
+            pc.skip_comments();
+            if (pc.eof()) break;
+            uint64_t r, col;
+            double v = 1.0;
+            if (!pc.u64(r) || !pc.u64(col) || (!pattern && !pc.f64(v))) { bad[(size_t)i] = 1; break; }
+            Triplet tr;
+            tr.row = (int32_t)(r - 1); tr.col = (int32_t)(col - 1); tr.val = v;
+            out.push_back(tr);
+        }
+    }
+    std::vector<Triplet> t;
+    t.reserve((size_t)nnz);
+    for (int i = 0; i < nt && t.size() < (size_t)nnz; ++i) {
+        const size_t take = std::min(part[(size_t)i].size(), (size_t)nnz - t.size());
+        t.insert(t.end(), part[(size_t)i].begin(), part[(size_t)i].begin() + (std::ptrdiff_t)take);
+        // a malformed line only matters if it comes before the nnz-th entry (the reference stops reading there)
+        if (bad[(size_t)i] && t.size() < (size_t)nnz) fail("Could not parse an entry line for coordinate matrix format");
+        std::vector<Triplet>().swap(part[(size_t)i]);
+    }
+    if (t.size() < (size_t)nnz) fail("Could not parse an entry line for coordinate matrix format");
     X.from_triplets((int64_t)nrows, (int64_t)ncols, t);
 }
 
