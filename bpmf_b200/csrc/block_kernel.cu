@@ -1,8 +1,8 @@
 // block_kernel.cu — the fused per-item conditional update (c++/sample.cpp:263-336 + 248-258) for num_latent = 16 * m
 // other than 32 (16, 48, 64, 80, 96, 112, 128) on sm_100a: ONE CTA PER ITEM, NB/2 warps (NB = K / 8).
 //
-//   gather  The K-vectors of the item's ratings are staged global -> shared with cp.async in stages of 16 rows (row pitch
-//           8K + 32 bytes: conflict-free fragment loads), three stages in flight, every thread copying four 16-byte chunks
+//   gather  The K-vectors of the item's ratings are staged global -> shared with cp.async in stages of 32 rows (row pitch
+//           8K + 32 bytes: conflict-free fragment loads), three stages in flight, every thread copying eight 16-byte chunks
 //           whose row indices were loaded one stage earlier.
 //   Gram    fp64 tensor cores (mma.sync.m8n8k4, DMMA). The lower triangle of NB x NB blocks of 8 x 8 is spread over the
 //           warps' REGISTERS: warp w owns block rows w and NB-1-w (NB + 1 blocks, 2 NB + 2 accumulator doubles per
@@ -28,7 +28,8 @@ namespace bpmf {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int SR = 16;   // ratings per stage
+constexpr int SR = 32;   // ratings per stage
+constexpr int CPT = SR / 4;   // 16-byte chunks a thread copies per stage (the CTA has 2K threads, a stage 8K * SR / 16 chunks)
 constexpr int NS = 3;    // stages in flight
 
 struct BlockArgs {
@@ -153,20 +154,20 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB >= 6 ? 4 : 8)) 
 #pragma unroll
             for (int n = 0; n <= NB; ++n) { acc[n][0] = 0.0; acc[n][1] = 0.0; }
             const int nst = (int)((pe - ps + SR - 1) / SR);
-            // this thread's four 16-byte chunks of a stage: rows rq, rq + 4, rq + 8, rq + 12, chunk cq of the row
+            // this thread's 16-byte chunks of a stage: rows rq, rq + 4, rq + 8, ..., chunk cq of the row
             const int rq = tid / (K / 2), cq = tid % (K / 2);
-            unsigned pre[4];              // row indices of the NEXT stage to be issued, loaded one stage-iteration ahead
+            unsigned pre[CPT];            // row indices of the NEXT stage to be issued, loaded one stage-iteration ahead
             auto load_rows = [&](int st) {
                 const int64_t p0 = ps + (int64_t)st * SR;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) pre[j] = (p0 + rq + 4 * j < pe) ? (unsigned)__ldg(p.rowidx + p0 + rq + 4 * j) : 0u;
+                for (int j = 0; j < CPT; ++j) pre[j] = (p0 + rq + 4 * j < pe) ? (unsigned)__ldg(p.rowidx + p0 + rq + 4 * j) : 0u;
             };
             auto issue = [&](int st) {
                 if (st < nst) {
                     const int64_t p0 = ps + (int64_t)st * SR;
                     const int slot = st % NS;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < CPT; ++j) {
                         const int r = rq + 4 * j;
                         cp_async16(ring_s + slot * C::STAGE + r * C::ROWB + cq * 16,
                                    reinterpret_cast<const unsigned char *>(p.other) + (size_t)pre[j] * (K * 8) + cq * 16, (p0 + r < pe) ? 16 : 0);
