@@ -223,22 +223,12 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB >= 6 ? 4 : 8)) 
             if (warp == 0 && lane < 8) p.items[(size_t)idx * K + lane] = MMp[lane] + b[lane] + z[lane];
             continue;
         }
-        // ---- chol.compute(MM) (sample.cpp:306) as MM = Lu D Lu^T, blocked by 8, on the tiles
-#pragma unroll 1
-        for (int kb = 0; kb < NB; ++kb) {
-            // every warp: the diagonal tile (redundantly) + its share of the panel tiles below it (I = I0, I0 + NWB)
-            const double2 d2 = *reinterpret_cast<const double2 *>(MMp + C::tile(kb, kb) + 8 * g + 2 * t);
-            double dg[2] = {d2.x, d2.y};
-            const int I0 = kb + 1 + ((warp - (kb + 1)) % NWB + NWB) % NWB;
-            double pt[2][2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int I = I0 + u * NWB;
-                double2 v = make_double2(0.0, 0.0);
-                if (I < NB) v = *reinterpret_cast<const double2 *>(MMp + C::tile(I, kb) + 8 * g + 2 * t);
-                pt[u][0] = v.x; pt[u][1] = v.y;
-            }
-            double myd = 1.0, myrinv = 1.0;   // lane k < 8 ends up with d_k and 1 / d_k of this block column
+        // ---- chol.compute(MM) (sample.cpp:306) as MM = Lu D Lu^T, blocked by 8, on the tiles, with look-ahead: the
+        // diagonal tile of block column kb + 1 is updated and factorised by warp 0 while the other warps run the rest of
+        // the trailing update of block column kb, so its 8-pivot dependent chain is off the other warps' critical path.
+        // factor_diag: one warp, the tile in registers (unscaled A~ on exit), lane k < 8 gets d_k and 1 / d_k.
+        auto factor_diag = [&](double (&dg)[2], const int kb) {
+            double myd = 1.0, myrinv = 1.0;
             bool ok = true;
 #pragma unroll 1
             for (int k2 = 0; k2 < 4; ++k2) {
@@ -249,48 +239,90 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB >= 6 ? 4 : 8)) 
                     const double pv = __shfl_sync(FULL, dg[e], 4 * k + k2);          // pivot: lane (g = k, t = k2), register e
                     double bl0 = __shfl_sync(FULL, dg[e], 4 * (2 * t) + k2);         // a[2t][k], a[2t+1][k] (unscaled)
                     double bl1 = __shfl_sync(FULL, dg[e], 4 * (2 * t + 1) + k2);
-                    const double ad = __shfl_sync(FULL, dg[e], qsrc);                // a[g][k] of the diagonal tile
-                    const double a0 = __shfl_sync(FULL, pt[0][e], qsrc), a1 = __shfl_sync(FULL, pt[1][e], qsrc);
+                    const double ad = __shfl_sync(FULL, dg[e], qsrc);                // a[g][k]
                     if (!(pv > 0.0)) ok = false;                                     // pivot <= 0 -> "Cholesky failed"
                     const double rinv = fast_rcp(pv);
                     if (lane == k) { myd = pv; myrinv = rinv; }
                     bl0 = (2 * t > k) ? -(bl0 * rinv) : 0.0;
                     bl1 = (2 * t + 1 > k) ? -(bl1 * rinv) : 0.0;
                     dg[0] = fma(ad, bl0, dg[0]); dg[1] = fma(ad, bl1, dg[1]);
-                    pt[0][0] = fma(a0, bl0, pt[0][0]); pt[0][1] = fma(a0, bl1, pt[0][1]);
-                    pt[1][0] = fma(a1, bl0, pt[1][0]); pt[1][1] = fma(a1, bl1, pt[1][1]);
                 }
             }
-            // store the unit-lower factor divided by the pivots (Lu = A~ D^-1) back into the tiles
+            // the unit-lower factor divided by the pivots (Lu = A~ D^-1) goes back into the tile; d and 1/d into the vectors
             const double rv0 = __shfl_sync(FULL, myrinv, 2 * t), rv1 = __shfl_sync(FULL, myrinv, 2 * t + 1);
-            if (warp == 0) {
-                if (lane < 8) { sd[8 * kb + lane] = myd; srinv[8 * kb + lane] = myrinv; }
-                if (!ok && lane == 0) sint[1] = 1;
-            }
+            *reinterpret_cast<double2 *>(MMp + C::tile(kb, kb) + 8 * g + 2 * t) = make_double2(dg[0] * rv0, dg[1] * rv1);
+            if (lane < 8) { sd[8 * kb + lane] = myd; srinv[8 * kb + lane] = myrinv; }
+            if (!ok && lane == 0) sint[1] = 1;
+        };
+        if (warp == 0) {
+            const double2 d2 = *reinterpret_cast<const double2 *>(MMp + C::tile(0, 0) + 8 * g + 2 * t);
+            double dg[2] = {d2.x, d2.y};
+            factor_diag(dg, 0);
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int kb = 0; kb < NB; ++kb) {
+            // ---- panel: this warp's tiles below the (already factorised) diagonal tile, I = I0, I0 + NWB
+            const int I0 = kb + 1 + ((warp - (kb + 1)) % NWB + NWB) % NWB;
+            if (I0 < NB) {
+                double pt[2][2];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int I = I0 + u * NWB;
-                if (I < NB) *reinterpret_cast<double2 *>(MMp + C::tile(I, kb) + 8 * g + 2 * t) = make_double2(pt[u][0] * rv0, pt[u][1] * rv1);
+                for (int u = 0; u < 2; ++u) {
+                    const int I = I0 + u * NWB;
+                    double2 v = make_double2(0.0, 0.0);
+                    if (I < NB) v = *reinterpret_cast<const double2 *>(MMp + C::tile(I, kb) + 8 * g + 2 * t);
+                    pt[u][0] = v.x; pt[u][1] = v.y;
+                }
+                const double *lu = MMp + C::tile(kb, kb);      // Lu(r, k) of the diagonal tile at lu[8 r + k]
+#pragma unroll 1
+                for (int k2 = 0; k2 < 4; ++k2) {
+                    const int qsrc = (lane & ~3) | k2;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int k = 2 * k2 + e;
+                        const double a0 = __shfl_sync(FULL, pt[0][e], qsrc), a1 = __shfl_sync(FULL, pt[1][e], qsrc);   // a[g][k]
+                        // -A~(c,k) / d_k = -Lu(c,k) for this lane's columns c = 2t, 2t+1 right of k
+                        const double bl0 = (2 * t > k) ? -lu[8 * (2 * t) + k] : 0.0;
+                        const double bl1 = (2 * t + 1 > k) ? -lu[8 * (2 * t + 1) + k] : 0.0;
+                        pt[0][0] = fma(a0, bl0, pt[0][0]); pt[0][1] = fma(a0, bl1, pt[0][1]);
+                        pt[1][0] = fma(a1, bl0, pt[1][0]); pt[1][1] = fma(a1, bl1, pt[1][1]);
+                    }
+                }
+                const double rv0 = srinv[8 * kb + 2 * t], rv1 = srinv[8 * kb + 2 * t + 1];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int I = I0 + u * NWB;
+                    if (I < NB) *reinterpret_cast<double2 *>(MMp + C::tile(I, kb) + 8 * g + 2 * t) = make_double2(pt[u][0] * rv0, pt[u][1] * rv1);
+                }
             }
             __syncthreads();
-            // (only now: the other warps read the unfactored diagonal tile at the top of this iteration)
-            if (warp == 0) *reinterpret_cast<double2 *>(MMp + C::tile(kb, kb) + 8 * g + 2 * t) = make_double2(dg[0] * rv0, dg[1] * rv1);
-            // trailing tiles (I, J), kb < J <= I:  A(I,J) -= Lu(I,kb) D Lu(J,kb)^T  on the tensor cores, tiles dealt round-robin
+            // ---- trailing tiles (I, J), kb < J <= I:  A(I,J) -= Lu(I,kb) D Lu(J,kb)^T  on the tensor cores
             if (kb + 1 < NB) {
                 const double dc0 = sd[8 * kb + t], dc1 = sd[8 * kb + 4 + t];
-                // tile number e (row-major over the trailing triangle) belongs to warp e % NWB: walk e = warp, warp + NWB, ...
-                int I = kb + 1, J = kb + 1 + warp;
-                while (J > I) { J -= I - kb; ++I; }          // row I holds I - kb tiles (J = kb+1 .. I)
-                while (I < NB) {
+                auto update_tile = [&](const int I, const int J) {
                     const double *ta = MMp + C::tile(I, kb) + 8 * g + t;
                     const double *tb = MMp + C::tile(J, kb) + 8 * g + t;
-                    double2 *tc = reinterpret_cast<double2 *>(MMp + C::tile(I, J) + 8 * g + 2 * t);
-                    double2 cv = *tc;
+                    double2 cv = *reinterpret_cast<const double2 *>(MMp + C::tile(I, J) + 8 * g + 2 * t);
                     dmma884(cv.x, cv.y, -ta[0], tb[0] * dc0);
                     dmma884(cv.x, cv.y, -ta[4], tb[4] * dc1);
-                    *tc = cv;
-                    J += NWB;
-                    while (I < NB && J > I) { J -= I - kb; ++I; }
+                    return cv;
+                };
+                // tile number e, row-major over the trailing triangle; e = 0 is the next diagonal tile
+                constexpr int NOTH = NWB > 1 ? NWB - 1 : 1;       // warps that share the tiles e >= 1
+                if (warp == 0) {
+                    const double2 cv = update_tile(kb + 1, kb + 1);
+                    double dg[2] = {cv.x, cv.y};
+                    factor_diag(dg, kb + 1);
+                }
+                if (warp > 0 || NWB == 1) {
+                    int I = kb + 1, J = kb + 1 + (NWB > 1 ? warp : 1);
+                    while (I < NB && J > I) { J -= I - kb; ++I; }          // row I holds I - kb tiles (J = kb+1 .. I)
+                    while (I < NB) {
+                        const double2 cv = update_tile(I, J);
+                        *reinterpret_cast<double2 *>(MMp + C::tile(I, J) + 8 * g + 2 * t) = cv;
+                        J += NOTH;
+                        while (I < NB && J > I) { J -= I - kb; ++I; }
+                    }
                 }
             }
             __syncthreads();
