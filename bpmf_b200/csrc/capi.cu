@@ -764,8 +764,18 @@ int bpmf_gpu_sample_host(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_v
     if (host_other_items)   // other.items() lives in host memory in the reference (bpmf.h:193-194)
         CU(cudaMemcpyAsync(o.items, host_other_items, sizeof(double) * K * o.num, cudaMemcpyHostToDevice, ctx->stream));
     const int from = s.from, to = s.to;
-    constexpr int P = bpmf_gpu_ctx::HOST_PARTS;
-    if (!host_items || to - from < 16384 * P) {
+    // Parts of geometrically decreasing size (ratio 0.6, below the copy : sweep time ratio of a part on PCIe 5), the
+    // last one at least MIN_PART items: part p's download hides behind part p + 1's sweep and only the last, smallest
+    // part's copy is exposed (6 parts: 3.3 % of the matrix).
+    constexpr int PMAX = bpmf_gpu_ctx::HOST_PARTS, MIN_PART = 8192;
+    constexpr double RATIO = 0.6;
+    int P = 1;
+    double wsum = 1.0;
+    for (double w = 1.0, ws = 1.0; P < PMAX; ++P, wsum = ws) {
+        w *= RATIO; ws += w;
+        if ((to - from) * (w / ws) < MIN_PART) break;
+    }
+    if (!host_items || P < 2) {
         const int rc = bpmf_gpu_sample(ctx, side, alpha, kernel_variant);
         if (rc) return rc;
         if (host_items)
@@ -781,8 +791,11 @@ int bpmf_gpu_sample_host(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_v
         CU(cudaMemcpyAsync(host_items, s.items, sizeof(double) * K * from, cudaMemcpyDeviceToHost, ctx->stream));
     if (to < s.num)
         CU(cudaMemcpyAsync(host_items + K * to, s.items + K * to, sizeof(double) * K * (s.num - to), cudaMemcpyDeviceToHost, ctx->stream));
-    for (int part = 0; part < P && !rc; ++part) {
-        const int lo = from + (int)((long long)(to - from) * part / P), hi = from + (int)((long long)(to - from) * (part + 1) / P);
+    double wdone = 0.0, w = 1.0;
+    int lo = from;
+    for (int part = 0; part < P && !rc; ++part, w *= RATIO) {
+        wdone += w;
+        const int hi = part == P - 1 ? to : from + (int)((to - from) * (wdone / wsum));
         s.from = lo; s.to = hi;
         rc = bpmf_gpu_sample_items(ctx, side, (uint32_t)s.iter, alpha, kernel_variant);
         if (rc) break;
@@ -791,6 +804,7 @@ int bpmf_gpu_sample_host(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_v
         if (e == cudaSuccess)
             e = cudaMemcpyAsync(host_items + K * lo, s.items + K * lo, sizeof(double) * K * (hi - lo), cudaMemcpyDeviceToHost, ctx->copy_stream);
         if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = BPMF_GPU_ECUDA; }
+        lo = hi;
     }
     s.from = from; s.to = to;
     if (rc) return rc;

@@ -91,7 +91,7 @@ struct bpmf_gpu_ctx {
     cudaEvent_t ev_stats[2] = {}, ev_hyper[2] = {};
     bool overlap_hyper = true;
     cudaStream_t copy_stream = nullptr;   // bpmf_gpu_sample_host: downloads finished item ranges while the rest is sampled
-    static constexpr int HOST_PARTS = 4;
+    static constexpr int HOST_PARTS = 6;   // most parts a host-destination sweep is cut into (capi.cu: bpmf_gpu_sample_host)
     cudaEvent_t ev_part[HOST_PARTS] = {}, ev_copied = nullptr;
     unsigned long long *d_err = nullptr;  // device error word
     unsigned long long *h_err = nullptr;  // pinned host copy
