@@ -162,8 +162,9 @@ def main():
     from bpmf_b200 import synthetic
     nrows, ncols, mean_nnz, K, seed = synthetic.WORKLOADS[args.workload]
     config = {"workload": args.workload, "users": nrows, "movies": ncols, "num_latent": K, "alpha": args.alpha,
-              "generator": "bpmf_b200/synthetic.py seed %d: Poisson(%g) ratings per user row, uniform distinct movies, "
-                           "planted rank-16 values" % (seed, mean_nnz),
+              "generator": "bpmf_b200/synthetic.py seed %d: Poisson(%g) ratings per user row, %s, planted rank-16 values"
+                           % (seed, mean_nnz, "movies drawn with Zipf(s=%g) popularity, duplicates dropped" % synthetic.ZIPF[args.workload]
+                              if args.workload in synthetic.ZIPF else "uniform distinct movies"),
               "l2": "inputs larger than L2: per sweep %.0f MB of latent vectors gathered at random + %.0f MB of CSR"
                     % (max(nrows, ncols) * K * 8 / 1e6, nrows * mean_nnz * 12 / 1e6)}
 

@@ -256,18 +256,30 @@ int bpmf_gpu_load_side(bpmf_gpu_ctx *ctx, int side, int num_items, int num_other
     CU(cudaMemset(s.work_counter, 0, 2 * sizeof(unsigned int)));
     // skew handling for the K == 32 stream kernel: items far heavier than the rest are sampled by the chunked path
     if (K == 32 && num_items > 0) {
-        constexpr int MAX_HEAVY = 64;
-        const long long thr = std::max<long long>(ctx->heavy_threshold, 16 * (nnz / num_items + 1));
+        // heavy = more ratings than max(threshold, 16 x the mean); the bar is doubled until at most MAX_HEAVY items and
+        // MAX_CHUNKS chunks (6 KB of partial Gram each) are above it
+        constexpr int MAX_HEAVY = 16384;
+        constexpr long long MAX_CHUNKS = 131072;
+        const int CH = heavy_chunk_size();
+        long long thr = std::max<long long>(ctx->heavy_threshold, 16 * (nnz / num_items + 1));
+        for (;; thr *= 2) {
+            long long cnt = 0, chunks = 0;
+            for (int i = 0; i < num_items; ++i) {
+                const int64_t len = colptr[i + 1] - colptr[i];
+                if (len > thr) { ++cnt; chunks += (len + CH - 1) / CH; }
+            }
+            if (cnt <= MAX_HEAVY && chunks <= MAX_CHUNKS) break;
+        }
+        s.heavy_thr = (int)std::min<long long>(thr, 0x7fffffff);
         std::vector<int> items, first(1, 0);
         std::vector<int64_t> p0, p1;
-        const int CH = heavy_chunk_size();
-        for (int i = 0; i < num_items && (int)items.size() <= MAX_HEAVY; ++i) {
-            if (colptr[i + 1] - colptr[i] <= thr) continue;
+        for (int i = 0; i < num_items; ++i) {
+            if (colptr[i + 1] - colptr[i] <= s.heavy_thr) continue;
             items.push_back(i);
             for (int64_t q = colptr[i]; q < colptr[i + 1]; q += CH) { p0.push_back(q); p1.push_back(std::min<int64_t>(q + CH, colptr[i + 1])); }
             first.push_back((int)p0.size());
         }
-        if (!items.empty() && (int)items.size() <= MAX_HEAVY) {   // more: the side is heavy everywhere, nothing to balance
+        if (!items.empty()) {
             s.n_heavy = (int)items.size();
             s.h_heavy_item = items; s.h_heavy_first = first;
             CU(cudaMalloc(&s.hv_item, sizeof(int) * items.size()));

@@ -56,6 +56,7 @@ struct SideDev {          // the device mirror of one Sys (c++/bpmf.h:112-239)
     int aggr_burnin = 0;
     // heavy items (K == 32 stream kernel): items with more than the threshold of ratings, cut into chunks (stream_kernel.cu)
     int n_heavy = 0;
+    int heavy_thr = 0x7fffffff;                       // items with more ratings than this are heavy
     std::vector<int> h_heavy_item, h_heavy_first;     // host copies: item index (ascending), first chunk (n_heavy + 1)
     int *hv_item = nullptr, *hv_first = nullptr;
     int64_t *hv_p0 = nullptr, *hv_p1 = nullptr;       // per chunk: rating range

@@ -62,6 +62,7 @@ struct StreamArgs {
     unsigned long long *err;
     const double *zero_row;   // 256 bytes of zeros in global memory (bulk-copy variant: source of the padding rows)
     int bulk_end;             // v3: items of [from, bulk_end) are claimed CLAIM at a time, [bulk_end, to) CLAIM_TAIL at a time
+    int heavy_thr;            // SKIP: items with more ratings than this belong to the chunked path and are passed over
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
@@ -328,7 +329,10 @@ __device__ __forceinline__ void tail32_warp(double (&c)[10][2], double (&rrp)[4]
 // TOK == 3 ("phased"): the warps of a CTA run their Gram phases together and their tails together (two CTA barriers
 // per item). Nobody is in a tail while DMMAs stream, so the tails' dependent scalar fp64 chains run at the uncontended
 // 8 cycles per instruction instead of 15-56, and the Gram phase keeps the DMMA pipe full with every warp.
-template <int NS, int NW, int DBG, bool BULK, int TOK>
+// SKIP: the range holds heavy items (more than p.heavy_thr ratings). They are sampled by heavy_gram32_kernel /
+// heavy_tail32_kernel, which run AFTER this kernel on the same stream; here they are gathered as if they had no ratings
+// (a prior-only draw that the heavy path overwrites), which keeps the fetch state machine contiguous.
+template <int NS, int NW, int DBG, bool BULK, int TOK, bool SKIP = false>
 __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs p)
 {
     constexpr int WARP_BYTES = warp_bytes<NS>();
@@ -401,10 +405,12 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs
         cpr = (lane <= g_n) ? (int)(__ldg(p.colptr + base + lane) - c0) : 0;
         g_idx = p.rowidx + c0;
         g_val = p.val + c0;
-        f_it = 0;
-        f_start = f_pos = 0;
-        f_end = __shfl_sync(FULL, cpr, 1);
         g_end = __shfl_sync(FULL, cpr, g_n);
+        f_it = 0;
+        f_start = 0;
+        f_end = __shfl_sync(FULL, cpr, 1);
+        if (SKIP && f_end - f_start > p.heavy_thr) f_start = f_end;     // heavy: gathered as if it had no ratings
+        f_pos = f_start;
     };
     // fill ring slot `slot` with the next (at most SR) ratings of the current item; exactly one commit_group per call
     auto issue_stage = [&](int slot) {
@@ -452,7 +458,10 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs
         if (last) {
             ++f_it;
             if (f_it >= g_n) claim();
-            else { f_start = f_end; f_end = __shfl_sync(FULL, cpr, f_it + 1); }
+            else {
+                f_start = f_end; f_end = __shfl_sync(FULL, cpr, f_it + 1);
+                if (SKIP && f_end - f_start > p.heavy_thr) { f_start = f_end; f_pos = f_start; }
+            }
         }
         if (!f_done) load_next();
     };
@@ -554,8 +563,8 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs
 // ONE warp's work in the stream kernel and set the duration of the whole sweep. Such items are cut into chunks of
 // HEAVY_CHUNK ratings: heavy_gram32_kernel computes one partial Gram per chunk (a warp per chunk, DMMA, fragments
 // straight from global memory), heavy_tail32_kernel adds an item's partials in chunk order (so the result does not
-// depend on scheduling) and runs the same tail as the stream kernel. The stream kernel is launched on the index ranges
-// between the heavy items.
+// depend on scheduling) and runs the same tail as the stream kernel. The stream kernel (SKIP instantiation) passes over
+// the heavy items of its range.
 // =====================================================================================================================
 constexpr int HEAVY_CHUNK = 1024;
 constexpr int HEAVY_PART = 24 * 32;           // doubles per partial: c[10][2] + rrp[4] per lane, in the DMMA layout
@@ -640,10 +649,10 @@ cudaError_t launch_cfg(bpmf_gpu_ctx *c, const StreamArgs &p, long long n)
     constexpr size_t smem = (size_t)NW * warp_bytes<NS>() + SHARED_BYTES;
     static_assert(smem <= 227 * 1024, "shared memory budget");
 #ifdef BPMF_STREAM_PROBES
-    auto kern = VER >= 3 ? items_stream32v3_kernel<NS, NW, DBG, VER == 6, (VER == 7 ? 1 : VER == 8 ? 2 : VER == 9 ? 3 : 0)> : items_stream32_kernel<NS, NW>;
+    auto kern = VER >= 3 ? items_stream32v3_kernel<NS, NW, DBG, VER == 6, (VER == 7 ? 1 : VER == 8 ? 2 : VER == 9 ? 3 : 0), VER == 12> : items_stream32_kernel<NS, NW>;
 #else
     static_assert(VER >= 3, "the v2 kernel is an experiment (stream_experiments.cuh)");
-    auto kern = items_stream32v3_kernel<NS, NW, DBG, VER == 6, (VER == 7 ? 1 : VER == 8 ? 2 : VER == 9 ? 3 : 0)>;
+    auto kern = items_stream32v3_kernel<NS, NW, DBG, VER == 6, (VER == 7 ? 1 : VER == 8 ? 2 : VER == 9 ? 3 : 0), VER == 12>;
 #endif
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -740,7 +749,7 @@ cudaError_t launch_stats_partial32(bpmf_gpu_ctx *c, int side)
     return cudaGetLastError();
 }
 
-static cudaError_t launch_stream_range(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha, int from, int to)
+static cudaError_t launch_stream_range(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha, int from, int to, bool skip_heavy)
 {
     SideDev &s = c->side[side];
     const SideDev &o = c->side[1 - side];
@@ -750,7 +759,7 @@ static cudaError_t launch_stream_range(bpmf_gpu_ctx *c, int side, uint32_t iter,
     p.other = o.items; p.items = s.items;
     p.npeers = s.npeers; p.peers = s.peers_dev;
     p.mu = s.hp.mu; p.LambdaF = s.hp.LambdaF;
-    p.work_counter = s.work_counter; p.err = c->d_err; p.zero_row = c->d_zero_row;
+    p.work_counter = s.work_counter; p.err = c->d_err; p.zero_row = c->d_zero_row; p.heavy_thr = s.heavy_thr;
     cudaError_t e = cudaMemsetAsync(s.work_counter, 0, 2 * sizeof(unsigned int), c->stream);
     if (e != cudaSuccess) return e;
     const long long n = (long long)to - from;
@@ -772,6 +781,11 @@ static cudaError_t launch_stream_range(bpmf_gpu_ctx *c, int side, uint32_t iter,
     // Set with bpmf_gpu_debug_set_tuning or the environment variable BPMF_STREAM_CFG.
     static const int env_cfg = [] { const char *v = getenv("BPMF_STREAM_CFG"); return v ? atoi(v) : 0; }();
     const int cfg = c->stream_cfg ? c->stream_cfg : env_cfg;
+    if (skip_heavy) {                     // v3, 2 stages x 20 warps, passing over the heavy items
+        e = launch_cfg<2, 20, 12>(c, p, n);
+        c->launches++;
+        return e;
+    }
     switch (cfg) {
     case 3218: e = launch_cfg<2, 18, 3>(c, p, n); break;
     // 11<NS><NW>: v3 "phased" (all Grams of a CTA together, all tails together)
@@ -852,20 +866,15 @@ cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, doub
 {
     SideDev &s = c->side[side];
     const SideDev &o = c->side[1 - side];
-    // heavy items of [from, to): the stream kernel runs on the ranges between them
+    // heavy items of [from, to): the stream kernel passes over them
     int first = 0, last = 0;
     while (first < s.n_heavy && s.h_heavy_item[first] < s.from) ++first;
     last = first;
     while (last < s.n_heavy && s.h_heavy_item[last] < s.to) ++last;
-    if (first == last) return launch_stream_range(c, side, iter, alpha, s.from, s.to);
-    int lo = s.from;
-    for (int h = first; h <= last; ++h) {
-        const int hi = h < last ? s.h_heavy_item[h] : s.to;
-        if (hi > lo) {
-            const cudaError_t e = launch_stream_range(c, side, iter, alpha, lo, hi);
-            if (e != cudaSuccess) return e;
-        }
-        lo = hi + 1;
+    if (first == last) return launch_stream_range(c, side, iter, alpha, s.from, s.to, false);
+    {
+        const cudaError_t e = launch_stream_range(c, side, iter, alpha, s.from, s.to, true);
+        if (e != cudaSuccess) return e;
     }
     StreamArgs p;
     p.from = s.from; p.to = s.to; p.iter = iter; p.alpha = alpha; p.mean_rating = s.mean_rating;
@@ -873,7 +882,7 @@ cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, doub
     p.other = o.items; p.items = s.items;
     p.npeers = s.npeers; p.peers = s.peers_dev;
     p.mu = s.hp.mu; p.LambdaF = s.hp.LambdaF;
-    p.work_counter = s.work_counter; p.err = c->d_err; p.zero_row = c->d_zero_row; p.bulk_end = s.to;
+    p.work_counter = s.work_counter; p.err = c->d_err; p.zero_row = c->d_zero_row; p.bulk_end = s.to; p.heavy_thr = s.heavy_thr;
     const int ch0 = s.h_heavy_first[first], ch1 = s.h_heavy_first[last];
     heavy_gram32_kernel<<<(ch1 - ch0 + 3) / 4, 128, 0, c->stream>>>(p, ch1 - ch0, s.hv_p0 + ch0, s.hv_p1 + ch0,
                                                                      s.hv_partials + (size_t)ch0 * HEAVY_PART);

@@ -24,7 +24,11 @@ WORKLOADS = {
     "synthB-200Kx200K-50Mnnz-K128": (200_000, 200_000, 250.0, 128, 20260002),
     "ml1m-shaped-6040x3952-1Mnnz-K32": (6040, 3952, 165.6, 32, 20260003),
     "small-20Kx20K-1Mnnz-K32": (20_000, 20_000, 50.0, 32, 20260004),
+    # the skewed variant of Synthetic A: movie popularity ~ Zipf(s = 1) over a random permutation of the ids
+    "synthA-zipf-1Mx1M-K32": (1_000_000, 1_000_000, 100.0, 32, 20260005),
+    "small-zipf-50Kx50K-K32": (50_000, 50_000, 60.0, 32, 20260006),
 }
+ZIPF = {"synthA-zipf-1Mx1M-K32": 1.0, "small-zipf-50Kx50K-K32": 1.0}
 
 
 class Ratings:
@@ -59,14 +63,26 @@ def _planted_values(rng, rows, cols, U, V, chunk=4_000_000):
     return out
 
 
-def generate(nrows, ncols, mean_nnz_row, seed, rank=16, test_frac=0.01, verbose=False):
+def generate(nrows, ncols, mean_nnz_row, seed, rank=16, test_frac=0.01, verbose=False, zipf=None):
     t0 = time.time()
     rng = np.random.Generator(np.random.PCG64(seed))
     counts = rng.poisson(mean_nnz_row, nrows).astype(np.int64)
     total = int(counts.sum())
     key = np.repeat(np.arange(nrows, dtype=np.int64), counts)
     key *= ncols
-    key += rng.integers(0, ncols, total, dtype=np.int64)
+    if zipf is None:
+        key += rng.integers(0, ncols, total, dtype=np.int64)
+    else:
+        # column popularity ~ 1 / rank^s, ranks assigned to a random permutation of the columns; duplicates inside a row
+        # are dropped below, so the hottest columns saturate (rated by nearly every row) and nnz ends below the nominal
+        cdf = np.cumsum(1.0 / np.arange(1, ncols + 1, dtype=np.float64) ** zipf)
+        cdf /= cdf[-1]
+        perm = rng.permutation(ncols).astype(np.int64)
+        for s0 in range(0, total, 8_000_000):
+            e0 = min(total, s0 + 8_000_000)
+            rk = np.searchsorted(cdf, rng.random(e0 - s0), side="right")
+            np.minimum(rk, ncols - 1, out=rk)
+            key[s0:e0] += perm[rk]
     key.sort()
     keep = np.empty(total, bool)
     keep[0] = True
@@ -134,7 +150,7 @@ def workload(name, cache_dir=None, verbose=False):
         r = load(d)
         if r is not None:
             return r, K
-    r = generate(nrows, ncols, mean, seed, verbose=verbose)
+    r = generate(nrows, ncols, mean, seed, verbose=verbose, zipf=ZIPF.get(name))
     if cache_dir:
         try:
             save(r, d)

@@ -64,8 +64,8 @@ int bpmf_gpu_sync(bpmf_gpu_ctx *ctx);
  * zeroed, iter = -1, cov = 0, norm = 0, range = [0, num_items). */
 int bpmf_gpu_load_side(bpmf_gpu_ctx *ctx, int side, int num_items, int num_other, const int64_t *colptr,
                        const int32_t *rowidx, const double *val, double mean_rating);
-/* Skew handling (K == 32): an item with more than num_ratings ratings (and more than 16x the side's average; at most 64
- * such items per side) is cut into chunks whose partial Gram matrices are computed by separate warps and added in a fixed
+/* Skew handling (K == 32): an item with more than num_ratings ratings (and more than 16x the side's average; the bar
+ * is doubled until at most 16384 items per side are above it) is cut into chunks whose partial Gram matrices are computed by separate warps and added in a fixed
  * order, instead of being one warp's work (ChEMBL's hottest target has 110 118 ratings; the reference only has OpenMP's
  * schedule(guided), c++/sample.cpp:352). Default 4096. Takes effect at the next bpmf_gpu_load_side. */
 int bpmf_gpu_set_heavy_threshold(bpmf_gpu_ctx *ctx, int64_t num_ratings);

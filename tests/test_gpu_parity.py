@@ -386,7 +386,7 @@ def test_propagated_posterior_priors(gpu, K):
 
 def test_heavy_items_chunked_path(gpu):
     """Skew handling: items far heavier than the rest are cut into chunks (partial Grams by separate warps, added in a
-    fixed order) and the stream kernel runs on the index ranges between them. Two hot movies of ~5000 and ~2600 ratings
+    fixed order) and the stream kernel passes over them. Two hot movies of ~5000 and ~2600 ratings
     (threshold lowered to 2100 so that both take the chunked path: 3 and 2 chunks), against the oracle and against the
     plain path (threshold out of reach)."""
     K = 32
@@ -428,5 +428,45 @@ def test_heavy_items_chunked_path(gpu):
     orc.sample_range(MOVIES, 3, 200)
     got, ref = chunked.get_items(MOVIES), orc.items(MOVIES)
     assert np.abs(got - ref).max() <= TOL_ITEMS * max(1.0, np.abs(ref).max())
+    for ctx in (chunked, plain):
+        ctx.close()
+
+
+def test_many_heavy_items_skipped_in_claim_groups(gpu):
+    """Zipf-like skew: ~150 heavy movies among 40 000 (a sweep large enough for 16-item claim groups), placed so that a
+    whole claim group is heavy (items 32..47), the first and the last item are heavy, and the rest are scattered. Against
+    the oracle, and bit-identical to the plain path for every item that is not heavy."""
+    K = 32
+    rng = np.random.default_rng(18)
+    nr, nc = 3000, 40000
+    heavy = np.unique(np.concatenate([[0, nc - 1], np.arange(32, 48), [63, 64, 65], rng.choice(nc, size=130, replace=False)]))
+    rows = [rng.integers(0, nr, size=200000)]; cols = [rng.integers(0, nc, size=200000)]
+    for h in heavy:
+        n = int(rng.integers(520, 1400))
+        rows.append(rng.choice(nr, size=n, replace=False)); cols.append(np.full(n, h))
+    rows = np.concatenate(rows); cols = np.concatenate(cols)
+    key = rows.astype(np.int64) * nc + cols
+    _, first = np.unique(key, return_index=True)
+    rows, cols = rows[first].astype(np.int32), cols[first].astype(np.int32)
+    vals = rng.normal(3.5, 1.0, size=len(rows))
+    train = ((nr, nc), rows, cols, vals)
+    test = ((nr, nc), rows[:50].copy(), cols[:50].copy(), vals[:50].copy())
+    orc = util.make_oracle(K, train, test)
+    chunked = util.make_gpu_from_oracle(orc, K, heavy_threshold=500)
+    plain = util.make_gpu_from_oracle(orc, K, heavy_threshold=1 << 40)
+    for ctx in (chunked, plain):
+        _prime(orc, ctx, K, 5)
+    orc.set_iter(MOVIES, 1)
+    orc.sample_range(MOVIES, 0, nc)
+    ref = orc.items(MOVIES)
+    outs = []
+    for ctx in (chunked, plain):
+        ctx.sample_items(MOVIES, 1, 2.0, gpu.KERNEL_STREAM)
+        got = ctx.get_items(MOVIES)
+        assert np.abs(got - ref).max() <= TOL_ITEMS * max(1.0, np.abs(ref).max())
+        outs.append(got)
+    mask = np.ones(nc, bool); mask[heavy] = False
+    assert outs[0][mask].tobytes() == outs[1][mask].tobytes()
+    assert chunked.launch_count() == plain.launch_count() + 2      # + partial Grams + heavy tails
     for ctx in (chunked, plain):
         ctx.close()
