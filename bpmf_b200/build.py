@@ -21,6 +21,7 @@ UNITS = [
     ("exact_kernels.cu", ["-fmad=false"]),
     ("fast_kernels.cu", []),
     ("block_kernel.cu", []),
+    ("build_kernels.cu", []),
     ("stream_kernel.cu", ["-DBPMF_STREAM_PROBES"] if os.environ.get("BPMF_STREAM_PROBES") else []),
 ]
 HEADERS = ["common.cuh", "rng.cuh", "stream_experiments.cuh", os.path.join(ROOT, "include", "bpmf_gpu.h")]

@@ -29,6 +29,10 @@ SYMBOLS = {
     "bpmf_gpu_load_side": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _i64p, _i32p, _f64p, C.c_double]),
     "bpmf_gpu_set_heavy_threshold": (C.c_int, [C.c_void_p, C.c_int64]),
     "bpmf_gpu_load_test": (C.c_int, [C.c_void_p, C.c_int, _i64p, _i32p, _f64p]),
+    "bpmf_gpu_load_coo": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, _i32p, _i32p, _f64p]),
+    "bpmf_gpu_load_test_coo": (C.c_int, [C.c_void_p, C.c_int64, _i32p, _i32p, _f64p]),
+    "bpmf_gpu_get_side": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
     "bpmf_gpu_set_range": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "bpmf_gpu_bind_items": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "bpmf_gpu_set_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
@@ -144,6 +148,32 @@ class Context:
         self._ck(self.L.bpmf_gpu_load_test(self.h, side, colptr, np.ascontiguousarray(rowidx, np.int32),
                                            np.ascontiguousarray(val, np.float64)))
         self.nnz_test[side] = int(colptr[-1])
+
+    def load_coo(self, num_rows, num_cols, row, col, val):
+        """both sides from one coordinate list, built on the device (rows = users, cols = movies)"""
+        row, col = np.ascontiguousarray(row, np.int32), np.ascontiguousarray(col, np.int32)
+        val = np.ascontiguousarray(val, np.float64)
+        assert row.shape == col.shape == val.shape
+        self._ck(self.L.bpmf_gpu_load_coo(self.h, num_rows, num_cols, len(val), row, col, val))
+        self.num[0], self.num[1] = num_cols, num_rows
+
+    def load_test_coo(self, row, col, val):
+        row, col = np.ascontiguousarray(row, np.int32), np.ascontiguousarray(col, np.int32)
+        val = np.ascontiguousarray(val, np.float64)
+        self._ck(self.L.bpmf_gpu_load_test_coo(self.h, len(val), row, col, val))
+        for side in (0, 1):
+            self.nnz_test[side] = self.get_side(side, test=True, arrays=False)[0]
+
+    def get_side(self, side, test=False, arrays=True):
+        """(nnz, mean_rating, colptr, rowidx, val) of a side's (test) matrix as it sits on the device"""
+        nnz, mean = C.c_int64(), C.c_double()
+        self._ck(self.L.bpmf_gpu_get_side(self.h, side, int(test), C.byref(nnz), C.byref(mean), None, None, None))
+        if not arrays:
+            return nnz.value, mean.value
+        colptr = np.empty(self.num[side] + 1, np.int64)
+        rowidx, val = np.empty(nnz.value, np.int32), np.empty(nnz.value, np.float64)
+        self._ck(self.L.bpmf_gpu_get_side(self.h, side, int(test), None, None, colptr.ctypes.data, rowidx.ctypes.data, val.ctypes.data))
+        return nnz.value, mean.value, colptr, rowidx, val
 
     def set_range(self, side, lo, hi): self._ck(self.L.bpmf_gpu_set_range(self.h, side, lo, hi))
     def bind_items(self, side, dev_ptr): self._ck(self.L.bpmf_gpu_bind_items(self.h, side, C.c_void_p(dev_ptr)))

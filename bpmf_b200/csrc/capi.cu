@@ -200,6 +200,9 @@ int bpmf_gpu_sync(bpmf_gpu_ctx *ctx)
     return check_device_error(ctx);
 }
 
+static int setup_side(bpmf_gpu_ctx *ctx, SideDev &s, const int64_t *colptr);
+static int finish_test(bpmf_gpu_ctx *ctx, SideDev &s);
+
 int bpmf_gpu_load_side(bpmf_gpu_ctx *ctx, int side, int num_items, int num_other, const int64_t *colptr, const int32_t *rowidx,
                        const double *val, double mean_rating)
 {
@@ -215,8 +218,7 @@ int bpmf_gpu_load_side(bpmf_gpu_ctx *ctx, int side, int num_items, int num_other
     CU(cudaStreamSynchronize(ctx->aux_stream));
     SideDev &s = ctx->side[side];
     free_side(s);
-    const int K = ctx->K, KK = K * K;
-    s.num = num_items; s.num_other = num_other; s.nnz = nnz; s.from = 0; s.to = num_items; s.iter = -1;
+    s.num = num_items; s.num_other = num_other; s.nnz = nnz;
     s.mean_rating = mean_rating;
     CU(cudaMalloc(&s.colptr, sizeof(int64_t) * ((size_t)num_items + 1)));
     CU(cudaMalloc(&s.rowidx, sizeof(int32_t) * (size_t)(nnz + 32)));  // +32: the DMMA kernel reads index chunks of 32
@@ -228,6 +230,17 @@ int bpmf_gpu_load_side(bpmf_gpu_ctx *ctx, int side, int num_items, int num_other
         CU(cudaMemcpy(s.rowidx, rowidx, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(s.val, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice));
     }
+    return setup_side(ctx, s, colptr);
+}
+
+// Everything of a side but the compressed matrix itself: s.colptr / rowidx / val are on the device, s.num, num_other, nnz
+// and mean_rating are set; colptr is the host copy of the column pointers.
+static int setup_side(bpmf_gpu_ctx *ctx, SideDev &s, const int64_t *colptr)
+{
+    const int K = ctx->K, KK = K * K;
+    const int num_items = s.num;
+    const int64_t nnz = s.nnz;
+    s.from = 0; s.to = num_items; s.iter = -1;
     const size_t nitems = (size_t)K * (size_t)(num_items > 0 ? num_items : 1);
     CU(cudaMalloc(&s.items_own, sizeof(double) * nitems));
     CU(cudaMemset(s.items_own, 0, sizeof(double) * nitems));  // items().setZero() (sample.cpp:185)
@@ -321,18 +334,137 @@ int bpmf_gpu_load_test(bpmf_gpu_ctx *ctx, int side, const int64_t *colptr, const
     CU(cudaMalloc(&s.t_rowidx, sizeof(int32_t) * n1));
     CU(cudaMalloc(&s.t_col, sizeof(int32_t) * n1));
     CU(cudaMalloc(&s.t_val, sizeof(double) * n1));
-    CU(cudaMalloc(&s.pavg, sizeof(double) * n1));
-    CU(cudaMalloc(&s.pm2, sizeof(double) * n1));
     CU(cudaMemcpy(s.t_colptr, colptr, sizeof(int64_t) * ((size_t)s.num + 1), cudaMemcpyHostToDevice));
     if (nnz) {
         CU(cudaMemcpy(s.t_rowidx, rowidx, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(s.t_col, col.data(), sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(s.t_val, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(s.pavg, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice));  // Pm2 = Pavg = T (sample.cpp:123)
-        CU(cudaMemcpy(s.pm2, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice));
+    }
+    return finish_test(ctx, s);
+}
+
+// Pm2 = Pavg = T (sample.cpp:123) and the reduction scratch of predict; the test matrix itself is on the device
+static int finish_test(bpmf_gpu_ctx *ctx, SideDev &s)
+{
+    const size_t n1 = (size_t)(s.nnz_test > 0 ? s.nnz_test : 1);
+    CU(cudaMalloc(&s.pavg, sizeof(double) * n1));
+    CU(cudaMalloc(&s.pm2, sizeof(double) * n1));
+    if (s.nnz_test) {
+        CU(cudaMemcpy(s.pavg, s.t_val, sizeof(double) * (size_t)s.nnz_test, cudaMemcpyDeviceToDevice));
+        CU(cudaMemcpy(s.pm2, s.t_val, sizeof(double) * (size_t)s.nnz_test, cudaMemcpyDeviceToDevice));
     }
     s.pred_blocks = ctx->sm_count * 8;
     CU(cudaMalloc(&s.pred_partials, sizeof(double) * (2 * (size_t)s.pred_blocks + 2)));
+    return BPMF_GPU_OK;
+}
+
+// ---- N4: both factors' matrices built on the device from one coordinate list (build_kernels.cu) ----------------------
+namespace {
+struct DevCoo {
+    int32_t *row = nullptr, *col = nullptr;
+    double *val = nullptr;
+    ~DevCoo() { cudaFree(row); cudaFree(col); cudaFree(val); }
+};
+int upload_coo(bpmf_gpu_ctx *ctx, DevCoo &d, int64_t nnz, const int32_t *row, const int32_t *col, const double *val)
+{
+    const size_t n1 = (size_t)(nnz > 0 ? nnz : 1);
+    CU(cudaMalloc(&d.row, sizeof(int32_t) * n1));
+    CU(cudaMalloc(&d.col, sizeof(int32_t) * n1));
+    CU(cudaMalloc(&d.val, sizeof(double) * n1));
+    if (nnz) {
+        CU(cudaMemcpy(d.row, row, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d.col, col, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d.val, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice));
+    }
+    return BPMF_GPU_OK;
+}
+}  // namespace
+
+int bpmf_gpu_load_coo(bpmf_gpu_ctx *ctx, int num_rows, int num_cols, int64_t nnz, const int32_t *row, const int32_t *col,
+                      const double *val)
+{
+    if (!ctx || num_rows < 1 || num_cols < 1 || nnz < 1 || !row || !col || !val) return BPMF_GPU_EINVAL;
+    if (nnz > 0x7fffffffll) return fail(ctx, BPMF_GPU_EINVAL, "more than 2^31 - 1 entries");   // int storage indices, like Eigen's
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->aux_stream));
+    DevCoo d;
+    int rc = upload_coo(ctx, d, nnz, row, col, val);
+    if (rc) return rc;
+    std::vector<double> hval;
+    for (int side = 0; side < 2; ++side) {                 // movies: columns of the matrix; users: its rows
+        SideDev &s = ctx->side[side];
+        free_side(s);
+        const bool mv = side == BPMF_GPU_MOVIES;
+        const int num = mv ? num_cols : num_rows, num_other = mv ? num_rows : num_cols;
+        int64_t n_out = 0;
+        bool bad = false;
+        const cudaError_t e = build_compressed(ctx, nnz, num, num_other, mv ? d.col : d.row, mv ? d.row : d.col, d.val, &s.colptr,
+                                               &s.rowidx, nullptr, &s.val, &n_out, &bad);
+        if (e != cudaSuccess || bad) {
+            free_side(s);
+            return e != cudaSuccess ? fail(ctx, BPMF_GPU_ECUDA, cudaGetErrorString(e)) : fail(ctx, BPMF_GPU_EINVAL, "matrix entry out of range");
+        }
+        s.num = num; s.num_other = num_other; s.nnz = n_out;
+        // mean_rating = M.sum() / M.nonZeros() (sample.cpp:183): the sum runs over the stored values in storage order, per
+        // side, so it is taken on the host from the built array (load time; 8 bytes per entry over PCIe)
+        hval.resize((size_t)n_out);
+        CU(cudaMemcpy(hval.data(), s.val, sizeof(double) * (size_t)n_out, cudaMemcpyDeviceToHost));
+        double sum = 0.0;
+        for (double x : hval) sum += x;
+        s.mean_rating = sum / (double)n_out;
+        std::vector<int64_t> hptr((size_t)num + 1);
+        CU(cudaMemcpy(hptr.data(), s.colptr, sizeof(int64_t) * hptr.size(), cudaMemcpyDeviceToHost));
+        rc = setup_side(ctx, s, hptr.data());
+        if (rc) return rc;
+    }
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_load_test_coo(bpmf_gpu_ctx *ctx, int64_t nnz, const int32_t *row, const int32_t *col, const double *val)
+{
+    if (!ctx || nnz < 0 || (nnz > 0 && (!row || !col || !val))) return BPMF_GPU_EINVAL;
+    if (!ctx->side[0].loaded || !ctx->side[1].loaded) return fail(ctx, BPMF_GPU_EINVAL, "the train matrix must be loaded first");
+    if (nnz > 0x7fffffffll) return fail(ctx, BPMF_GPU_EINVAL, "more than 2^31 - 1 entries");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    DevCoo d;
+    int rc = upload_coo(ctx, d, nnz, row, col, val);
+    if (rc) return rc;
+    for (int side = 0; side < 2; ++side) {
+        SideDev &s = ctx->side[side];
+        dfree(s.t_colptr); dfree(s.t_rowidx); dfree(s.t_col); dfree(s.t_val); dfree(s.pavg); dfree(s.pm2); dfree(s.pred_partials);
+        const bool mv = side == BPMF_GPU_MOVIES;
+        int64_t n_out = 0;
+        bool bad = false;
+        const cudaError_t e = build_compressed(ctx, nnz, s.num, s.num_other, mv ? d.col : d.row, mv ? d.row : d.col, d.val, &s.t_colptr,
+                                               &s.t_rowidx, &s.t_col, &s.t_val, &n_out, &bad);
+        if (e != cudaSuccess || bad) {
+            dfree(s.t_colptr); dfree(s.t_rowidx); dfree(s.t_col); dfree(s.t_val);
+            s.nnz_test = 0;
+            return e != cudaSuccess ? fail(ctx, BPMF_GPU_ECUDA, cudaGetErrorString(e)) : fail(ctx, BPMF_GPU_EINVAL, "test entry out of range");
+        }
+        s.nnz_test = n_out;
+        rc = finish_test(ctx, s);
+        if (rc) return rc;
+    }
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_get_side(bpmf_gpu_ctx *ctx, int side, int test, int64_t *nnz, double *mean_rating, int64_t *colptr, int32_t *rowidx,
+                      double *val)
+{
+    if (!ctx || !side_ok(side)) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded || (test && !s.t_colptr)) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const int64_t n = test ? s.nnz_test : s.nnz;
+    if (nnz) *nnz = n;
+    if (mean_rating) *mean_rating = s.mean_rating;
+    if (colptr) CU(cudaMemcpy(colptr, test ? s.t_colptr : s.colptr, sizeof(int64_t) * ((size_t)s.num + 1), cudaMemcpyDeviceToHost));
+    if (rowidx && n) CU(cudaMemcpy(rowidx, test ? s.t_rowidx : s.rowidx, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+    if (val && n) CU(cudaMemcpy(val, test ? s.t_val : s.val, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
     return BPMF_GPU_OK;
 }
 

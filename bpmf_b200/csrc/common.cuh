@@ -131,4 +131,8 @@ cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, doub
 cudaError_t launch_stats_partial32(bpmf_gpu_ctx *c, int side);
 int heavy_chunk_size();
 int heavy_partial_doubles();
+// build_kernels.cu
+cudaError_t build_compressed(bpmf_gpu_ctx *c, int64_t n, int num_major, int num_minor, const int32_t *d_major, const int32_t *d_minor,
+                             const double *d_val, int64_t **colptr_out, int32_t **idx_out, int32_t **major_out, double **val_out,
+                             int64_t *nnz_out, bool *bad_index);
 }  // namespace bpmf

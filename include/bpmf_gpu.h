@@ -71,6 +71,20 @@ int bpmf_gpu_load_side(bpmf_gpu_ctx *ctx, int side, int num_items, int num_other
 int bpmf_gpu_set_heavy_threshold(bpmf_gpu_ctx *ctx, int64_t num_ratings);
 /* Test matrix T of one side, same layout; Pavg = Pm2 = T (c++/sample.cpp:123). */
 int bpmf_gpu_load_test(bpmf_gpu_ctx *ctx, int side, const int64_t *colptr, const int32_t *rowidx, const double *val);
+/* Both factors' matrices built ON THE DEVICE from one coordinate list: replaces Eigen's
+ * setFromTriplets (c++/io.cpp:282,521: compressed columns, inner indices ascending, duplicate entries summed in input
+ * order) and the transpose that gives the other factor its matrix (c++/sample.cpp:133-134). row[i] in [0, num_rows)
+ * indexes users, col[i] in [0, num_cols) movies, like the reference's train file. Afterwards both sides are loaded as
+ * by bpmf_gpu_load_side (bit-identical arrays), each with mean_rating = sum of its stored values in storage order /
+ * nnz (c++/sample.cpp:183). At most 2^31 - 1 entries (Eigen's int storage index). */
+int bpmf_gpu_load_coo(bpmf_gpu_ctx *ctx, int num_rows, int num_cols, int64_t nnz, const int32_t *row, const int32_t *col,
+                      const double *val);
+/* The test matrix of both sides from one coordinate list (same shape as the train matrix, c++/sample.cpp:119-123). */
+int bpmf_gpu_load_test_coo(bpmf_gpu_ctx *ctx, int64_t nnz, const int32_t *row, const int32_t *col, const double *val);
+/* Read a side's matrix back (test != 0: its test matrix): what a host needs for Sys::nnz(), the work-balanced ranges
+ * (c++/assign.cpp:111) and the report of Sys::init. Every output pointer may be NULL. */
+int bpmf_gpu_get_side(bpmf_gpu_ctx *ctx, int side, int test, int64_t *nnz, double *mean_rating, int64_t *colptr, int32_t *rowidx,
+                      double *val);
 /* Sys::from()/to() (c++/bpmf.h:171-172): the items this context samples; others are left to peers. */
 int bpmf_gpu_set_range(bpmf_gpu_ctx *ctx, int side, int from, int to);
 /* Use caller-owned device storage (K * num_items doubles) for a side's latent matrix, e.g. a

@@ -470,3 +470,76 @@ def test_many_heavy_items_skipped_in_claim_groups(gpu):
     assert chunked.launch_count() == plain.launch_count() + 2      # + partial Grams + heavy tails
     for ctx in (chunked, plain):
         ctx.close()
+
+
+def _host_build(n_major, major, minor, val):
+    """compressed columns the way the host build does it (bpmf_b200/host/matrix.h from_triplets, after Eigen's
+    setFromTriplets): stable order by (major, minor), duplicates summed sequentially in input order"""
+    order = np.lexsort((minor, major))               # stable: equal keys keep input order
+    M, m, v = major[order], minor[order], val[order]
+    head = np.ones(len(v), bool)
+    head[1:] = (M[1:] != M[:-1]) | (m[1:] != m[:-1])
+    out_val = []
+    for i in np.flatnonzero(head):
+        acc, j = v[i], i + 1
+        while j < len(v) and not head[j]:
+            acc = acc + v[j]; j += 1
+        out_val.append(acc)
+    colptr = np.zeros(n_major + 1, np.int64)
+    np.cumsum(np.bincount(M[head], minlength=n_major), out=colptr[1:])
+    return colptr, m[head].astype(np.int32), np.array(out_val, np.float64)
+
+
+@pytest.mark.parametrize("dups", [False, True])
+def test_device_build_from_coordinates(gpu, dups):
+    """bpmf_gpu_load_coo / _load_test_coo: both sides' compressed matrices built on the device from one
+    shuffled coordinate list are bit-identical to the host build — indices, values (duplicates summed in input order),
+    column pointers, mean_rating (sequential sum in storage order) — and a chain sampled from them is bit-identical to
+    one loaded through bpmf_gpu_load_side."""
+    K = 32
+    rng = np.random.default_rng(5 + dups)
+    nr, nc, n = 700, 450, 30000
+    rows = rng.integers(0, nr, size=n).astype(np.int32); cols = rng.integers(0, nc, size=n).astype(np.int32)
+    keep = (cols != 18) & (rows != 3)                # an empty column and an empty row
+    rows, cols = rows[keep], cols[keep]
+    if not dups:
+        _, first = np.unique(rows.astype(np.int64) * nc + cols, return_index=True)
+        first = rng.permutation(first)               # file order is arbitrary
+        rows, cols = rows[first], cols[first]
+    else:                                            # triples of the same entry far apart in the input
+        rows = np.concatenate([rows, rows[:500], rows[:200]]); cols = np.concatenate([cols, cols[:500], cols[:200]])
+    vals = rng.normal(3.5, 1.0, size=len(rows))
+    t_rows = rng.integers(0, nr, size=800).astype(np.int32); t_cols = rng.integers(0, nc, size=800).astype(np.int32)
+    _, first = np.unique(t_rows.astype(np.int64) * nc + t_cols, return_index=True)
+    first = rng.permutation(first)
+    t_rows, t_cols = t_rows[first], t_cols[first]
+    t_vals = rng.normal(3.5, 1.0, size=len(t_rows))
+
+    dev = gpu.Context(K)
+    dev.load_coo(nr, nc, rows, cols, vals)
+    dev.load_test_coo(t_rows, t_cols, t_vals)
+    host = gpu.Context(K)
+    for side, (n_major, major, minor, tmaj, tmin) in ((MOVIES, (nc, cols, rows, t_cols, t_rows)), (USERS, (nr, rows, cols, t_rows, t_cols))):
+        colptr, idx, val = _host_build(n_major, major, minor, vals)
+        mean = float(np.cumsum(val)[-1] / len(val))  # sequential sum in storage order (sample.cpp:183)
+        nnz, dmean, dptr, didx, dval = dev.get_side(side)
+        assert nnz == len(val) and dmean == mean
+        assert np.array_equal(dptr, colptr) and np.array_equal(didx, idx) and dval.tobytes() == val.tobytes()
+        tptr, tidx, tval = _host_build(n_major, tmaj, tmin, t_vals)
+        tn, _, dtptr, dtidx, dtval = dev.get_side(side, test=True)
+        assert tn == len(tval) and np.array_equal(dtptr, tptr) and np.array_equal(dtidx, tidx) and dtval.tobytes() == tval.tobytes()
+        host.load_side(side, n_major, nr if side == MOVIES else nc, colptr, idx, val, mean)
+        host.load_test(side, tptr, tidx, tval)
+    for it in range(3):
+        for side in (MOVIES, USERS):
+            dev.sample(side, 2.0, gpu.KERNEL_AUTO)
+            host.sample(side, 2.0, gpu.KERNEL_AUTO)
+            assert dev.get_items(side).tobytes() == host.get_items(side).tobytes()
+        assert dev.predict(MOVIES, 1) == host.predict(MOVIES, 1)
+    # an index out of range is refused, and the context stays usable
+    bad = rows.copy(); bad[5] = nr
+    with pytest.raises(Exception):
+        dev.load_coo(nr, nc, bad, cols, vals)
+    dev.load_coo(nr, nc, rows, cols, vals)
+    for ctx in (dev, host):
+        ctx.close()
