@@ -10,12 +10,13 @@
 //           inner part is instantiated per warp role (the operands of a DMMA must be registers); the stage loop around it
 //           is shared code — with one copy of the whole loop per warp the kernel thrashed the instruction cache.
 //   tail    MM = LambdaF + alpha G goes to shared memory as 8 x 8 row-major TILES of the lower block triangle (they alias
-//           the gather ring, idle by then). Blocked right-looking LDL^T: per block column every warp factorises the diagonal
-//           tile redundantly in registers (warp shuffles, as the K = 32 kernel does) together with its share of the panel
-//           tiles, the trailing tiles are updated with DMMAs (fragments straight from the tiles: a row-major tile IS the
-//           C fragment layout, and its rows are A/B fragments). The unit-lower factor is stored divided by the pivots, so
-//           the two triangular solves (warp 0, right-hand side in registers) are shuffle + FMA chains; K normals from
-//           Philox4x32-10 (rng.cuh).
+//           the gather ring, idle by then), with the right-hand side as one more block row. Blocked right-looking LDL^T
+//           with look-ahead: warp 0 updates and factorises the next diagonal tile in registers (warp shuffles; the inverse
+//           of its unit-lower factor comes out of the same row operations) while the other warps finish the trailing
+//           update; a panel tile is then ONE 8x8x8 product with that inverse and the trailing tiles are DMMA updates
+//           (fragments straight from the tiles: a row-major tile IS the C fragment layout, and its rows are A/B
+//           fragments). Factorising the extra block row leaves D^-1 Lu^-1 b in it, i.e. the forward solve; the backward
+//           solve (warp 0, vector in registers) is a shuffle + FMA chain; K normals from Philox4x32-10 (rng.cuh).
 // Algorithmic bytes: 8K per rating. The Gram needs (NB+1) NB / 2 DMMAs per four ratings: at K = 128 that is 16.4 kflop per
 // gathered KB, so the kernel is bound by the fp64 tensor pipe (37 TFLOP/s), not by HBM.
 #include "common.cuh"
@@ -69,7 +70,11 @@ struct Cfg {
     static constexpr int ROWB = 8 * K + 32;                       // bytes per staged row
     static constexpr int STAGE = SR * ROWB;                       // rows only; weights live apart
     static constexpr int NTILE = NB * (NB + 1) / 2;               // 8 x 8 tiles of the lower block triangle, 512 B each
-    static constexpr int BIG = (NS * STAGE > NTILE * 512) ? NS * STAGE : NTILE * 512;   // ring and tiles alias each other
+    // + block row NB (the right-hand side as one more row of the matrix: tile (NB, J) holds b[8J .. 8J+7] in its row 0)
+    // + the inverses of the unit-lower diagonal tiles
+    static constexpr int LINV = (NTILE + NB) * 64;                // doubles: inverse of diagonal tile kb at LINV + 64 kb
+    static constexpr int NTILE_ALL = NTILE + 2 * NB;
+    static constexpr int BIG = (NS * STAGE > NTILE_ALL * 512) ? NS * STAGE : NTILE_ALL * 512;   // ring and tiles alias each other
     // layout: [BIG][w: NS*SR][z: K][b: K][rr0: K][d: K][rinv: K][ints: 4]
     static constexpr int W_OFF = BIG, Z_OFF = W_OFF + NS * SR * 8, B_OFF = Z_OFF + K * 8, RR0_OFF = B_OFF + K * 8;
     static constexpr int D_OFF = RR0_OFF + K * 8, RI_OFF = D_OFF + K * 8, INT_OFF = RI_OFF + K * 8, SMEM = INT_OFF + 16;
@@ -229,6 +234,7 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB >= 6 ? 4 : 8)) 
         // factor_diag: one warp, the tile in registers (unscaled A~ on exit), lane k < 8 gets d_k and 1 / d_k.
         auto factor_diag = [&](double (&dg)[2], const int kb) {
             double myd = 1.0, myrinv = 1.0;
+            double li[2] = {g == 2 * t ? 1.0 : 0.0, g == 2 * t + 1 ? 1.0 : 0.0};   // becomes Lu^-1 (row operations on I)
             bool ok = true;
 #pragma unroll 1
             for (int k2 = 0; k2 < 4; ++k2) {
@@ -240,9 +246,12 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB >= 6 ? 4 : 8)) 
                     double bl0 = __shfl_sync(FULL, dg[e], 4 * (2 * t) + k2);         // a[2t][k], a[2t+1][k] (unscaled)
                     double bl1 = __shfl_sync(FULL, dg[e], 4 * (2 * t + 1) + k2);
                     const double ad = __shfl_sync(FULL, dg[e], qsrc);                // a[g][k]
+                    const double wk0 = __shfl_sync(FULL, li[0], 4 * k + t), wk1 = __shfl_sync(FULL, li[1], 4 * k + t);   // row k of W
                     if (!(pv > 0.0)) ok = false;                                     // pivot <= 0 -> "Cholesky failed"
                     const double rinv = fast_rcp(pv);
                     if (lane == k) { myd = pv; myrinv = rinv; }
+                    const double mg = (g > k) ? -(ad * rinv) : 0.0;                  // W[g][:] -= Lu(g,k) W[k][:]
+                    li[0] = fma(mg, wk0, li[0]); li[1] = fma(mg, wk1, li[1]);
                     bl0 = (2 * t > k) ? -(bl0 * rinv) : 0.0;
                     bl1 = (2 * t + 1 > k) ? -(bl1 * rinv) : 0.0;
                     dg[0] = fma(ad, bl0, dg[0]); dg[1] = fma(ad, bl1, dg[1]);
@@ -251,9 +260,13 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB >= 6 ? 4 : 8)) 
             // the unit-lower factor divided by the pivots (Lu = A~ D^-1) goes back into the tile; d and 1/d into the vectors
             const double rv0 = __shfl_sync(FULL, myrinv, 2 * t), rv1 = __shfl_sync(FULL, myrinv, 2 * t + 1);
             *reinterpret_cast<double2 *>(MMp + C::tile(kb, kb) + 8 * g + 2 * t) = make_double2(dg[0] * rv0, dg[1] * rv1);
+            *reinterpret_cast<double2 *>(MMp + C::LINV + 64 * kb + 8 * g + 2 * t) = make_double2(li[0], li[1]);
             if (lane < 8) { sd[8 * kb + lane] = myd; srinv[8 * kb + lane] = myrinv; }
             if (!ok && lane == 0) sint[1] = 1;
         };
+        // the right-hand side as block row NB: row 0 of tile (NB, J) = b[8J .. 8J+7], rows 1..7 zero. Factorising the
+        // matrix with this extra row leaves D^-1 Lu^-1 b in it (the forward solve, sample.cpp:321, for free).
+        for (int e = tid; e < NB * 64; e += T) MMp[C::tile(NB, 0) + e] = ((e & 63) < 8) ? b[(e >> 6) * 8 + (e & 7)] : 0.0;
         if (warp == 0) {
             const double2 d2 = *reinterpret_cast<const double2 *>(MMp + C::tile(0, 0) + 8 * g + 2 * t);
             double dg[2] = {d2.x, d2.y};
@@ -262,37 +275,24 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB >= 6 ? 4 : 8)) 
         __syncthreads();
 #pragma unroll 1
         for (int kb = 0; kb < NB; ++kb) {
-            // ---- panel: this warp's tiles below the (already factorised) diagonal tile, I = I0, I0 + NWB
+            // ---- panel: this warp's tiles below the (already factorised) diagonal tile, I = I0, I0 + NWB (block row NB is
+            // the right-hand side):  Lu(I,kb) = A(I,kb) Lu(kb,kb)^-T D^-1, one 8x8x8 product on the tensor cores
             const int I0 = kb + 1 + ((warp - (kb + 1)) % NWB + NWB) % NWB;
-            if (I0 < NB) {
-                double pt[2][2];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int I = I0 + u * NWB;
-                    double2 v = make_double2(0.0, 0.0);
-                    if (I < NB) v = *reinterpret_cast<const double2 *>(MMp + C::tile(I, kb) + 8 * g + 2 * t);
-                    pt[u][0] = v.x; pt[u][1] = v.y;
-                }
-                const double *lu = MMp + C::tile(kb, kb);      // Lu(r, k) of the diagonal tile at lu[8 r + k]
-#pragma unroll 1
-                for (int k2 = 0; k2 < 4; ++k2) {
-                    const int qsrc = (lane & ~3) | k2;
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int k = 2 * k2 + e;
-                        const double a0 = __shfl_sync(FULL, pt[0][e], qsrc), a1 = __shfl_sync(FULL, pt[1][e], qsrc);   // a[g][k]
-                        // -A~(c,k) / d_k = -Lu(c,k) for this lane's columns c = 2t, 2t+1 right of k
-                        const double bl0 = (2 * t > k) ? -lu[8 * (2 * t) + k] : 0.0;
-                        const double bl1 = (2 * t + 1 > k) ? -lu[8 * (2 * t + 1) + k] : 0.0;
-                        pt[0][0] = fma(a0, bl0, pt[0][0]); pt[0][1] = fma(a0, bl1, pt[0][1]);
-                        pt[1][0] = fma(a1, bl0, pt[1][0]); pt[1][1] = fma(a1, bl1, pt[1][1]);
-                    }
-                }
+            if (I0 <= NB) {
+                const double *li = MMp + C::LINV + 64 * kb + 8 * g + t;     // B fragment: B[k][n] = Linv[n][k]
+                const double lb0 = li[0], lb1 = li[4];
                 const double rv0 = srinv[8 * kb + 2 * t], rv1 = srinv[8 * kb + 2 * t + 1];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int I = I0 + u * NWB;
-                    if (I < NB) *reinterpret_cast<double2 *>(MMp + C::tile(I, kb) + 8 * g + 2 * t) = make_double2(pt[u][0] * rv0, pt[u][1] * rv1);
+                    if (I <= NB) {
+                        double *tp = MMp + C::tile(I, kb);
+                        double c0 = 0.0, c1 = 0.0;
+                        dmma884(c0, c1, tp[8 * g + t], lb0);
+                        dmma884(c0, c1, tp[8 * g + t + 4], lb1);
+                        __syncwarp();                  // every lane has read the tile before it is overwritten
+                        *reinterpret_cast<double2 *>(tp + 8 * g + 2 * t) = make_double2(c0 * rv0, c1 * rv1);
+                    }
                 }
             }
             __syncthreads();
@@ -323,6 +323,10 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB >= 6 ? 4 : 8)) 
                         J += NOTH;
                         while (I < NB && J > I) { J -= I - kb; ++I; }
                     }
+                    for (; J < NB; J += NOTH) {       // block row NB (the right-hand side): tiles J = kb+1 .. NB-1
+                        const double2 cv = update_tile(NB, J);
+                        *reinterpret_cast<double2 *>(MMp + C::tile(NB, J) + 8 * g + 2 * t) = cv;
+                    }
                 }
             }
             __syncthreads();
@@ -331,40 +335,18 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB >= 6 ? 4 : 8)) 
             if (tid == 0) atomicMax(p.err, ERR_CHOLESKY | (unsigned)idx);
             continue;
         }
-        // ---- L \ rr; rr += nrandn; L^T \ rr (sample.cpp:321-323) with L = Lu D^(1/2):  x = Lu^-T (D^-1 Lu^-1 b + D^(-1/2) z)
-        // by warp 0, the vector in registers: lane holds rows lane + 32 r. Lu(i,k) = tile(i / 8, k / 8)[8 (i % 8) + k % 8].
+        // ---- L \ rr; rr += nrandn; L^T \ rr (sample.cpp:321-323) with L = Lu D^(1/2):  x = Lu^-T (D^-1 Lu^-1 b + D^(-1/2) z).
+        // D^-1 Lu^-1 b is row 0 of block row NB; the backward solve runs on warp 0 with the vector in registers: lane holds
+        // rows lane + 32 r. Lu(i,k) = tile(i / 8, k / 8)[8 (i % 8) + k % 8].
         if (warp == 0 && !(p.dbg & 4)) {
             constexpr int R = (K + 31) / 32;
             double v[R];
-            // this lane's rows i = lane + 32 r: start of tile row i / 8 (+ row inside the tile), and i's offset as a COLUMN
-            const double *rowp[R];
-            int colo[R];
+            int colo[R];                  // this lane's rows i = lane + 32 r as COLUMN offsets inside a tile row
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int i = lane + 32 * r, I = i >> 3;
-                v[r] = (i < K) ? b[i] : 0.0;
-                rowp[r] = MMp + (I * (I + 1) / 2) * 64 + 8 * (i & 7);
                 colo[r] = I * 64 + (i & 7);
-            }
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-#pragma unroll 4
-                for (int kk = 0; kk < 32; ++kk) {
-                    const int k = 32 * r + kk;
-                    if (k >= K) break;
-                    const double yk = __shfl_sync(FULL, v[r], kk);
-                    const int ko = (k >> 3) * 64 + (k & 7);                  // Lu(i,k) = rowp(i)[ko]
-#pragma unroll
-                    for (int r2 = r; r2 < R; ++r2) {
-                        const int i = lane + 32 * r2;
-                        if (i > k && i < K) v[r2] = fma(-rowp[r2][ko], yk, v[r2]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int i = lane + 32 * r;
-                if (i < K) v[r] = fma(v[r], srinv[i], rsqrt(sd[i]) * z[i]);
+                v[r] = (i < K) ? fma(rsqrt(sd[i]), z[i], MMp[C::tile(NB, I) + (i & 7)]) : 0.0;
             }
 #pragma unroll
             for (int r = R - 1; r >= 0; --r) {
