@@ -20,7 +20,7 @@ UNITS = [
     ("capi.cu", []),
     ("exact_kernels.cu", ["-fmad=false"]),
     ("fast_kernels.cu", []),
-    ("block_kernel.cu", []),
+    ("block_kernel.cu", ["-DBPMF_BLOCK_PROF"] if os.environ.get("BPMF_BLOCK_PROF") else []),
     ("build_kernels.cu", []),
     ("stream_kernel.cu", ["-DBPMF_STREAM_PROBES"] if os.environ.get("BPMF_STREAM_PROBES") else []),
 ]

@@ -22,7 +22,10 @@
 #include "common.cuh"
 #include "rng.cuh"
 
+#include <cstdio>
 #include <cstdlib>
+#include <mutex>
+#include <vector>
 
 namespace bpmf {
 
@@ -32,6 +35,11 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int SR = 32;   // ratings per stage
 constexpr int CPT = SR / 4;   // 16-byte chunks a thread copies per stage (the CTA has 2K threads, a stage 8K * SR / 16 chunks)
 constexpr int NS = 3;    // stages in flight
+#ifdef BPMF_BLOCK_PROF       // BPMF_BLOCK_PROF=1 python -m bpmf_b200.build --force: phase timestamps (BPMF_BLOCK_DBG=8)
+constexpr bool BLOCK_PROF = true;
+#else
+constexpr bool BLOCK_PROF = false;
+#endif
 
 struct BlockArgs {
     int from, to;
@@ -47,7 +55,8 @@ struct BlockArgs {
     const double *mu, *LambdaF;
     unsigned int *work_counter;
     unsigned long long *err;
-    int dbg;   // timing probes (BPMF_BLOCK_DBG): 1 = no factorisation / solves, 2 = no Gram DMMAs, 4 = no solves; 0 = the product
+    int dbg;   // timing probes (BPMF_BLOCK_DBG): 1 = no factorisation / solves, 2 = no Gram DMMAs, 4 = no solves, 8 = block 0 prints
+               // the cycles of its phases for a few items; 0 = the product
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
@@ -63,6 +72,13 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int sr
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// The trailing-update schedules of every supported NB (build_schedules below), in constant memory: every lane of a warp
+// reads the same entry.
+constexpr int MAX_QUADS = 900, MAX_SPANS = 7 * 16 * 8;
+__constant__ int4 c_ttab[2 * MAX_QUADS];
+__constant__ int2 c_tspan[MAX_SPANS];
+__constant__ int c_spanbase[17];          // [NB]: first entry of c_tspan for that NB
 
 template <int NB>
 struct Cfg {
@@ -80,6 +96,11 @@ struct Cfg {
     static constexpr int D_OFF = RR0_OFF + K * 8, RI_OFF = D_OFF + K * 8, INT_OFF = RI_OFF + K * 8, SMEM = INT_OFF + 16;
     __host__ __device__ static constexpr int tile(int I, int J) { return (I * (I + 1) / 2 + J) * 64; }   // doubles
 };
+
+// Tile storage: element (r, c) of an 8 x 8 tile sits at 8 r + (c ^ swz(r)). Without the swizzle the fragment loads of a
+// DMMA (lane (g, t) reads element (g, t) and (g, t + 4)) touch only half of the banks: 4 wavefronts instead of 2, and the
+// tail of this kernel is bound by shared-memory wavefronts. Pairs (c, c + 1) with c even stay adjacent and 16-byte aligned.
+__host__ __device__ __forceinline__ constexpr int swz(int r) { return (r & 2) << 1; }
 
 // 1 / p for a positive normal p: MUFU.RCP64H seed + one cubic step (same as the K = 32 kernel)
 __device__ __forceinline__ double fast_rcp(double p)
@@ -121,7 +142,7 @@ __device__ __forceinline__ void gram_groups(double (&acc)[NB + 1][2], double &r0
 }
 
 template <int NB>
-__global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB >= 6 ? 4 : 8)) items_block_kernel(BlockArgs p)
+__global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB == 10 ? 3 : NB >= 6 ? 4 : 8)) items_block_kernel(BlockArgs p)
 {
     using C = Cfg<NB>;
     constexpr int K = C::K, T = C::T, NWB = C::NWB;
@@ -132,6 +153,8 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB >= 6 ? 4 : 8)) 
     double *rr0 = reinterpret_cast<double *>(smem + C::RR0_OFF);
     double *sd = reinterpret_cast<double *>(smem + C::D_OFF), *srinv = reinterpret_cast<double *>(smem + C::RI_OFF);
     const int g = lane >> 2, t = lane & 3;
+    const int fpos = 8 * g + (t ^ swz(g));          // A / B fragment element (g, t); (g, t + 4) is at fpos ^ 4
+    const int cpos = 8 * g + ((2 * t) ^ swz(g));    // C fragment pair (g, 2t), (g, 2t + 1)
     int *sint = reinterpret_cast<int *>(smem + C::INT_OFF);   // [0] item, [1] failed
 
     for (int a = tid; a < K; a += T) {    // LambdaF * hp.mu, the same for every item
@@ -146,6 +169,9 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB >= 6 ? 4 : 8)) 
         __syncthreads();
         const int idx = sint[0];
         if (idx >= p.to) break;
+        const bool prof = BLOCK_PROF && (p.dbg & 8) && blockIdx.x == 0 && tid == 0;
+        long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (prof) tk[0] = clock64();
         for (int a = tid; a < K; a += T) b[a] = rr0[a];
         // the K normals of this item: rng_set_pos((idx+1) * K * (iter+1)) (sample.cpp:266)
         if (warp == NWB - 1) warp_randn((uint32_t)(((long long)idx + 1) * (long long)K * ((long long)p.iter + 1)), K, z);
@@ -216,7 +242,7 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB >= 6 ? 4 : 8)) 
                 double2 v;
                 v.x = fma(p.alpha, acc[n][0], __ldg(p.LambdaF + i + (size_t)k * K));
                 v.y = fma(p.alpha, acc[n][1], __ldg(p.LambdaF + i + (size_t)(k + 1) * K));
-                *reinterpret_cast<double2 *>(MMp + C::tile(I, J) + 8 * g + 2 * t) = v;
+                *reinterpret_cast<double2 *>(MMp + C::tile(I, J) + cpos) = v;
             }
             // rhs: sum over the quad's four ratings-of-a-group, on top of LambdaF * mu (sample.cpp:285) already in b
             r0 += __shfl_xor_sync(FULL, r0, 1); r0 += __shfl_xor_sync(FULL, r0, 2);
@@ -224,6 +250,7 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB >= 6 ? 4 : 8)) 
             if (t == 0) { b[8 * warp + g] += r0; b[8 * (NB - 1 - warp) + g] += r1; }
         }
         __syncthreads();
+        if (prof) tk[1] = clock64();
         if (p.dbg & 1) {
             if (warp == 0 && lane < 8) p.items[(size_t)idx * K + lane] = MMp[lane] + b[lane] + z[lane];
             continue;
@@ -231,106 +258,159 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB >= 6 ? 4 : 8)) 
         // ---- chol.compute(MM) (sample.cpp:306) as MM = Lu D Lu^T, blocked by 8, on the tiles, with look-ahead: the
         // diagonal tile of block column kb + 1 is updated and factorised by warp 0 while the other warps run the rest of
         // the trailing update of block column kb, so its 8-pivot dependent chain is off the other warps' critical path.
-        // factor_diag: one warp, the tile in registers (unscaled A~ on exit), lane k < 8 gets d_k and 1 / d_k.
-        auto factor_diag = [&](double (&dg)[2], const int kb) {
-            double myd = 1.0, myrinv = 1.0;
-            double li[2] = {g == 2 * t ? 1.0 : 0.0, g == 2 * t + 1 ? 1.0 : 0.0};   // becomes Lu^-1 (row operations on I)
-            bool ok = true;
-#pragma unroll 1
-            for (int k2 = 0; k2 < 4; ++k2) {
-                const int qsrc = (lane & ~3) | k2;
+        // factor_diag: EVERY lane of the warp holds the whole lower triangle of the tile in registers and runs the same
+        // fully unrolled 8 x 8 factorisation — no shuffles, the pivot chain is rcp seed -> 2 DFMA -> multiplier -> update,
+        // everything else is independent work. The inverse of the unit-lower factor (the panel's operand) comes out of
+        // the same row operations applied to I. All lanes store the same values (the tile is lane-uniform).
+        // The right-hand side is block row NB of the matrix: row 0 of tile (NB, J) = b[8J .. 8J+7], rows 1..7 zero.
+        // Factorising the matrix with this extra row leaves D^-1 Lu^-1 b in it (the forward solve, sample.cpp:321).
+        for (int e = tid; e < NB * 64; e += T) {
+            MMp[C::tile(NB, 0) + e] = ((e & 63) < 8) ? b[(e >> 6) * 8 + (e & 7)] : 0.0;
+            const int er = (e >> 3) & 7, ec = e & 7;                                 // diagonal and upper part of the inverses
+            if (ec >= er) MMp[C::LINV + (e & ~7) + (ec ^ swz(er))] = (ec == er) ? 1.0 : 0.0;
+        }
+        auto factor_diag = [&](const int kb) {
+            double *tp = MMp + C::tile(kb, kb), *lp = MMp + C::LINV + 64 * kb;
+            double a[8][8], W[8][8];
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int k = 2 * k2 + e;
-                    const double pv = __shfl_sync(FULL, dg[e], 4 * k + k2);          // pivot: lane (g = k, t = k2), register e
-                    double bl0 = __shfl_sync(FULL, dg[e], 4 * (2 * t) + k2);         // a[2t][k], a[2t+1][k] (unscaled)
-                    double bl1 = __shfl_sync(FULL, dg[e], 4 * (2 * t + 1) + k2);
-                    const double ad = __shfl_sync(FULL, dg[e], qsrc);                // a[g][k]
-                    const double wk0 = __shfl_sync(FULL, li[0], 4 * k + t), wk1 = __shfl_sync(FULL, li[1], 4 * k + t);   // row k of W
-                    if (!(pv > 0.0)) ok = false;                                     // pivot <= 0 -> "Cholesky failed"
-                    const double rinv = fast_rcp(pv);
-                    if (lane == k) { myd = pv; myrinv = rinv; }
-                    const double mg = (g > k) ? -(ad * rinv) : 0.0;                  // W[g][:] -= Lu(g,k) W[k][:]
-                    li[0] = fma(mg, wk0, li[0]); li[1] = fma(mg, wk1, li[1]);
-                    bl0 = (2 * t > k) ? -(bl0 * rinv) : 0.0;
-                    bl1 = (2 * t + 1 > k) ? -(bl1 * rinv) : 0.0;
-                    dg[0] = fma(ad, bl0, dg[0]); dg[1] = fma(ad, bl1, dg[1]);
+            for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                for (int j = 0; j <= i; j += 2) {
+                    const double2 v2 = *reinterpret_cast<const double2 *>(tp + 8 * i + (j ^ swz(i)));
+                    a[i][j] = v2.x;
+                    if (j + 1 <= i) a[i][j + 1] = v2.y;
                 }
             }
-            // the unit-lower factor divided by the pivots (Lu = A~ D^-1) goes back into the tile; d and 1/d into the vectors
-            const double rv0 = __shfl_sync(FULL, myrinv, 2 * t), rv1 = __shfl_sync(FULL, myrinv, 2 * t + 1);
-            *reinterpret_cast<double2 *>(MMp + C::tile(kb, kb) + 8 * g + 2 * t) = make_double2(dg[0] * rv0, dg[1] * rv1);
-            *reinterpret_cast<double2 *>(MMp + C::LINV + 64 * kb + 8 * g + 2 * t) = make_double2(li[0], li[1]);
-            if (lane < 8) { sd[8 * kb + lane] = myd; srinv[8 * kb + lane] = myrinv; }
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const double d = a[k][k];
+                ok = ok && (d > 0.0);                                                // pivot <= 0 -> "Cholesky failed"
+                double r;
+                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+                const double e1 = fma(-d, r, 1.0);
+                const double e2 = fma(e1, e1, e1);                                   // 1 / d = r + r e2
+                if (lane == 0) { sd[8 * kb + k] = d; srinv[8 * kb + k] = fma(r, e2, r); }
+                double l[8];
+#pragma unroll
+                for (int i = k + 1; i < 8; ++i) { const double u = a[i][k] * r; l[i] = fma(u, e2, u); }   // Lu(i,k) = a(i,k) / d
+#pragma unroll
+                for (int j = k + 1; j < 8; ++j) {
+#pragma unroll
+                    for (int i = j; i < 8; ++i) a[i][j] = fma(-l[i], a[j][k], a[i][j]);
+                }
+#pragma unroll
+                for (int i = k + 1; i < 8; ++i) {                                    // W <- (I - l e_k^T) W
+#pragma unroll
+                    for (int j = 0; j < k; ++j) W[i][j] = fma(-l[i], W[k][j], W[i][j]);
+                    W[i][k] = -l[i];
+                    tp[8 * i + (k ^ swz(i))] = l[i];
+                }
+            }
+#pragma unroll
+            for (int i = 1; i < 8; ++i) {
+#pragma unroll
+                for (int j = 0; j < i; ++j) lp[8 * i + (j ^ swz(i))] = W[i][j];
+            }
             if (!ok && lane == 0) sint[1] = 1;
         };
-        // the right-hand side as block row NB: row 0 of tile (NB, J) = b[8J .. 8J+7], rows 1..7 zero. Factorising the
-        // matrix with this extra row leaves D^-1 Lu^-1 b in it (the forward solve, sample.cpp:321, for free).
-        for (int e = tid; e < NB * 64; e += T) MMp[C::tile(NB, 0) + e] = ((e & 63) < 8) ? b[(e >> 6) * 8 + (e & 7)] : 0.0;
-        if (warp == 0) {
-            const double2 d2 = *reinterpret_cast<const double2 *>(MMp + C::tile(0, 0) + 8 * g + 2 * t);
-            double dg[2] = {d2.x, d2.y};
-            factor_diag(dg, 0);
-        }
+        if (warp == 0) factor_diag(0);
         __syncthreads();
+        if (prof) tk[2] = clock64();
+        const bool prof1 = BLOCK_PROF && (p.dbg & 8) && blockIdx.x == 0 && tid == 32;
+        long long w1_trail = 0, w1_first = 0;
+        int w1_tiles = 0;
 #pragma unroll 1
         for (int kb = 0; kb < NB; ++kb) {
+            long long c0 = 0, c1 = 0, c2 = 0;
+            if (prof) c0 = clock64();
             // ---- panel: this warp's tiles below the (already factorised) diagonal tile, I = I0, I0 + NWB (block row NB is
             // the right-hand side):  Lu(I,kb) = A(I,kb) Lu(kb,kb)^-T D^-1, one 8x8x8 product on the tensor cores
             const int I0 = kb + 1 + ((warp - (kb + 1)) % NWB + NWB) % NWB;
             if (I0 <= NB) {
-                const double *li = MMp + C::LINV + 64 * kb + 8 * g + t;     // B fragment: B[k][n] = Linv[n][k]
-                const double lb0 = li[0], lb1 = li[4];
+                const double *li = MMp + C::LINV + 64 * kb;                 // B fragment: B[k][n] = Linv[n][k]
+                const double lb0 = li[fpos], lb1 = li[fpos ^ 4];
                 const double rv0 = srinv[8 * kb + 2 * t], rv1 = srinv[8 * kb + 2 * t + 1];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int I = I0 + u * NWB;
-                    if (I <= NB) {
-                        double *tp = MMp + C::tile(I, kb);
-                        double c0 = 0.0, c1 = 0.0;
-                        dmma884(c0, c1, tp[8 * g + t], lb0);
-                        dmma884(c0, c1, tp[8 * g + t + 4], lb1);
-                        __syncwarp();                  // every lane has read the tile before it is overwritten
-                        *reinterpret_cast<double2 *>(tp + 8 * g + 2 * t) = make_double2(c0 * rv0, c1 * rv1);
-                    }
-                }
+                const bool two = I0 + NWB <= NB;
+                double *tp0 = MMp + C::tile(I0, kb), *tp1 = MMp + C::tile(two ? I0 + NWB : I0, kb);
+                const double a00 = tp0[fpos], a01 = tp0[fpos ^ 4], a10 = tp1[fpos], a11 = tp1[fpos ^ 4];
+                double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0, e00 = 0.0, e01 = 0.0, e10 = 0.0, e11 = 0.0;
+                dmma884(c00, c01, a00, lb0);   // four independent DMMAs: the k-halves are added afterwards
+                dmma884(c10, c11, a10, lb0);
+                dmma884(e00, e01, a01, lb1);
+                dmma884(e10, e11, a11, lb1);
+                __syncwarp();                  // every lane has read the tiles before they are overwritten
+                *reinterpret_cast<double2 *>(tp0 + cpos) = make_double2((c00 + e00) * rv0, (c01 + e01) * rv1);
+                if (two) *reinterpret_cast<double2 *>(tp1 + cpos) = make_double2((c10 + e10) * rv0, (c11 + e11) * rv1);
             }
             __syncthreads();
+            if (prof) c1 = clock64();
             // ---- trailing tiles (I, J), kb < J <= I:  A(I,J) -= Lu(I,kb) D Lu(J,kb)^T  on the tensor cores
             if (kb + 1 < NB) {
                 const double dc0 = sd[8 * kb + t], dc1 = sd[8 * kb + 4 + t];
-                auto update_tile = [&](const int I, const int J) {
-                    const double *ta = MMp + C::tile(I, kb) + 8 * g + t;
-                    const double *tb = MMp + C::tile(J, kb) + 8 * g + t;
-                    double2 cv = *reinterpret_cast<const double2 *>(MMp + C::tile(I, J) + 8 * g + 2 * t);
-                    dmma884(cv.x, cv.y, -ta[0], tb[0] * dc0);
-                    dmma884(cv.x, cv.y, -ta[4], tb[4] * dc1);
-                    return cv;
-                };
-                // tile number e, row-major over the trailing triangle; e = 0 is the next diagonal tile
-                constexpr int NOTH = NWB > 1 ? NWB - 1 : 1;       // warps that share the tiles e >= 1
-                if (warp == 0) {
-                    const double2 cv = update_tile(kb + 1, kb + 1);
-                    double dg[2] = {cv.x, cv.y};
-                    factor_diag(dg, kb + 1);
+                if (warp == 0) {               // the next diagonal tile first, then its factorisation
+                    double *tc = MMp + C::tile(kb + 1, kb + 1) + cpos;
+                    const double *ta = MMp + C::tile(kb + 1, kb);
+                    const double ta0 = ta[fpos], ta1 = ta[fpos ^ 4];
+                    double2 cv = *reinterpret_cast<const double2 *>(tc);
+                    double y0 = 0.0, y1 = 0.0;
+                    dmma884(cv.x, cv.y, -ta0, ta0 * dc0);
+                    dmma884(y0, y1, -ta1, ta1 * dc1);
+                    *reinterpret_cast<double2 *>(tc) = make_double2(cv.x + y0, cv.y + y1);
+                    __syncwarp();
+                    factor_diag(kb + 1);
+                    if (prof) c2 = clock64();
                 }
                 if (warp > 0 || NWB == 1) {
-                    int I = kb + 1, J = kb + 1 + (NWB > 1 ? warp : 1);
-                    while (I < NB && J > I) { J -= I - kb; ++I; }          // row I holds I - kb tiles (J = kb+1 .. I)
-                    while (I < NB) {
-                        const double2 cv = update_tile(I, J);
-                        *reinterpret_cast<double2 *>(MMp + C::tile(I, J) + 8 * g + 2 * t) = cv;
-                        J += NOTH;
-                        while (I < NB && J > I) { J -= I - kb; ++I; }
+                    // the other tiles (rest of the trailing triangle, then block row NB = the right-hand side), dealt
+                    // round-robin to the warps by a schedule built on the host (it does not depend on the item). U tiles
+                    // in flight per warp; the two k-halves of a tile go to separate accumulators so that no DMMA waits
+                    // for another one.
+                    // schedule: two int4 per QUAD (offsets of Lu(I0,kb), Lu(I1,kb), Lu(J0,kb), Lu(J1,kb); of the four tiles, -1 = none)
+                    const int2 span = c_tspan[c_spanbase[NB] + kb * NWB + warp];
+                    long long q0 = 0;
+                    if (prof1) q0 = clock64();
+                    int4 ea = make_int4(0, 0, 0, 0), ec = make_int4(-1, -1, -1, -1);
+                    if (span.x < span.y) { ea = c_ttab[2 * span.x]; ec = c_ttab[2 * span.x + 1]; }
+#pragma unroll 1
+                    for (int n = span.x; n < span.y; ++n) {
+                        // a QUAD of tiles (I0|I1, J0|J1): two A and two B fragments pairs serve four tiles
+                        const int4 qa = ea, qc = ec;
+                        if (n + 1 < span.y) { ea = c_ttab[2 * n + 2]; ec = c_ttab[2 * n + 3]; }
+                        const double a00 = MMp[qa.x + fpos], a01 = MMp[qa.x + (fpos ^ 4)], a10 = MMp[qa.y + fpos], a11 = MMp[qa.y + (fpos ^ 4)];
+                        const double b00 = MMp[qa.z + fpos] * dc0, b01 = MMp[qa.z + (fpos ^ 4)] * dc1;
+                        const double b10 = MMp[qa.w + fpos] * dc0, b11 = MMp[qa.w + (fpos ^ 4)] * dc1;
+                        const int co[4] = {qc.x, qc.y, qc.z, qc.w};               // (I0,J0) (I0,J1) (I1,J0) (I1,J1); < 0: not a tile
+                        double2 cv[4];
+                        double x0[4], x1[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            cv[u] = co[u] >= 0 ? *reinterpret_cast<const double2 *>(MMp + co[u] + cpos) : make_double2(0.0, 0.0);
+                            x0[u] = 0.0; x1[u] = 0.0;
+                        }
+                        dmma884(cv[0].x, cv[0].y, -a00, b00);
+                        dmma884(cv[1].x, cv[1].y, -a00, b10);
+                        dmma884(cv[2].x, cv[2].y, -a10, b00);
+                        dmma884(cv[3].x, cv[3].y, -a10, b10);
+                        dmma884(x0[0], x1[0], -a01, b01);
+                        dmma884(x0[1], x1[1], -a01, b11);
+                        dmma884(x0[2], x1[2], -a11, b01);
+                        dmma884(x0[3], x1[3], -a11, b11);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (co[u] >= 0) {
+                                *reinterpret_cast<double2 *>(MMp + co[u] + cpos) = make_double2(cv[u].x + x0[u], cv[u].y + x1[u]);
+                                if (prof1) ++w1_tiles;
+                            }
                     }
-                    for (; J < NB; J += NOTH) {       // block row NB (the right-hand side): tiles J = kb+1 .. NB-1
-                        const double2 cv = update_tile(NB, J);
-                        *reinterpret_cast<double2 *>(MMp + C::tile(NB, J) + 8 * g + 2 * t) = cv;
-                    }
+                    if (prof1) { const long long q1 = clock64(); w1_trail += q1 - q0; if (kb == 0) w1_first = q1 - q0; }
                 }
             }
             __syncthreads();
+            if (prof) { const long long c3 = clock64(); tk[3] += c1 - c0; if (c2) { tk[4] += c2 - c1; tk[5] += c3 - c2; } else tk[5] += c3 - c1; }
         }
+        if (prof) tk[6] = clock64();
+        if (prof1 && idx < p.from + 1500) printf("  warp 1 of item %d: %d trailing tiles in %lld cycles (block column 0: %lld)\n", idx, w1_tiles, w1_trail, w1_first);
         if (sint[1]) {                    // THROWERROR("Cholesky failed") (sample.cpp:308)
             if (tid == 0) atomicMax(p.err, ERR_CHOLESKY | (unsigned)idx);
             continue;
@@ -348,21 +428,35 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB >= 6 ? 4 : 8)) 
                 colo[r] = I * 64 + (i & 7);
                 v[r] = (i < K) ? fma(rsqrt(sd[i]), z[i], MMp[C::tile(NB, I) + (i & 7)]) : 0.0;
             }
+            // one tile row (8 columns) at a time: its Lu values are loaded up front, so that the chain per column is
+            // shuffle -> DFMA only
 #pragma unroll
             for (int r = R - 1; r >= 0; --r) {
-#pragma unroll 4
-                for (int kk = 31; kk >= 0; --kk) {
-                    const int k = 32 * r + kk;
-                    if (k >= K) continue;
-                    const double xk = __shfl_sync(FULL, v[r], kk);
-                    const double *krow = MMp + ((k >> 3) * ((k >> 3) + 1) / 2) * 64 + 8 * (k & 7);   // Lu(k,i) = krow[colo(i)]
+#pragma unroll 1
+                for (int q = 3; q >= 0; --q) {
+                    const int kb = 4 * r + q;
+                    if (kb >= NB) continue;
+                    const double *krow = MMp + (kb * (kb + 1) / 2) * 64;          // Lu(8 kb + c, i) = krow[8 c + colo(i)]
+                    double Lv[8][R];
 #pragma unroll
-                    for (int r2 = 0; r2 <= r; ++r2) {
-                        const int i = lane + 32 * r2;
-                        if (i < k) v[r2] = fma(-krow[colo[r2]], xk, v[r2]);
+                    for (int c = 0; c < 8; ++c) {
+#pragma unroll
+                        for (int r2 = 0; r2 <= r; ++r2) Lv[c][r2] = krow[8 * c + (colo[r2] ^ swz(c))];
+                    }
+#pragma unroll
+                    for (int c = 7; c >= 0; --c) {
+                        const int k = 8 * kb + c;
+                        const double xk = __shfl_sync(FULL, v[r], 8 * q + c);
+#pragma unroll
+                        for (int r2 = 0; r2 <= r; ++r2) {
+                            if (lane + 32 * r2 < k) v[r2] = fma(-Lv[c][r2], xk, v[r2]);
+                        }
                     }
                 }
             }
+            if (prof && idx < p.from + 1500)
+                printf("item %d nnz %d: gram %lld  init+diag0 %lld  panels %lld  diag %lld  wait_trailing %lld  solves %lld\n", idx, (int)(pe - ps),
+                       tk[1] - tk[0], tk[2] - tk[1], tk[3], tk[4], tk[5], clock64() - tk[6]);
             // items().col(idx) = rr (sample.cpp:324), and into every peer replica (replaces send_item)
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -377,21 +471,79 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB >= 6 ? 4 : 8)) 
     }
 }
 
+// The trailing-update schedule of block column kb: the trailing triangle plus block row NB (the right-hand side), minus
+// the next diagonal tile (warp 0's), cut into 2 x 2 QUADS of tiles that share their A / B fragments; the quads go
+// round-robin to warps 1 .. NWB-1 (to the only warp when NWB == 1). It does not depend on the item.
+static cudaError_t build_schedules(int device)
+{
+    static std::mutex mu;
+    static std::vector<int> done;
+    std::lock_guard<std::mutex> lock(mu);
+    for (int d : done) if (d == device) return cudaSuccess;
+    auto tile = [](int I, int J) { return (I * (I + 1) / 2 + J) * 64; };
+    std::vector<int4> tab;
+    std::vector<int2> span;
+    int spanbase[17] = {0};
+    for (int NB : {2, 6, 8, 10, 12, 14, 16}) {
+        const int NWB = NB / 2;
+        spanbase[NB] = (int)span.size();
+        std::vector<std::vector<int4>> per((size_t)NB * NWB);        // two int4 per quad
+        for (int kb = 0; kb + 1 < NB; ++kb) {
+            // a tile (I, J) of this block column's trailing update: kb < J <= I < NB, or block row NB (the right-hand
+            // side) with kb < J < NB; the next diagonal tile is warp 0's
+            auto live = [&](int I, int J) {
+                if (J <= kb || J >= NB || I > NB || J > I) return false;
+                return !(I == kb + 1 && J == kb + 1);
+            };
+            int q = 0;
+            for (int I0 = kb + 1; I0 <= NB; I0 += 2)
+                for (int J0 = kb + 1; J0 < NB && J0 <= I0 + 1; J0 += 2) {
+                    const int I1 = I0 + 1, J1 = J0 + 1;
+                    const bool l00 = live(I0, J0), l01 = live(I0, J1), l10 = live(I1, J0), l11 = live(I1, J1);
+                    if (!(l00 || l01 || l10 || l11)) continue;
+                    const int w = NWB > 1 ? 1 + q % (NWB - 1) : 0;
+                    ++q;
+                    const int a0 = tile(I0, kb), a1 = I1 <= NB ? tile(I1, kb) : a0;
+                    const int b0 = tile(J0, kb), b1 = J1 < NB ? tile(J1, kb) : b0;
+                    auto &v = per[(size_t)kb * NWB + w];
+                    v.push_back(make_int4(a0, a1, b0, b1));
+                    v.push_back(make_int4(l00 ? tile(I0, J0) : -1, l01 ? tile(I0, J1) : -1, l10 ? tile(I1, J0) : -1, l11 ? tile(I1, J1) : -1));
+                }
+        }
+        for (size_t i = 0; i < per.size(); ++i) {
+            span.push_back(make_int2((int)(tab.size() / 2), (int)((tab.size() + per[i].size()) / 2)));    // in quads
+            tab.insert(tab.end(), per[i].begin(), per[i].end());
+        }
+    }
+    if (tab.size() > 2 * (size_t)MAX_QUADS || span.size() > (size_t)MAX_SPANS) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemcpyToSymbol(c_ttab, tab.data(), sizeof(int4) * tab.size());
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(c_tspan, span.data(), sizeof(int2) * span.size());
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(c_spanbase, spanbase, sizeof spanbase);
+    if (e != cudaSuccess) return e;
+    done.push_back(device);
+    return cudaSuccess;
+}
+
 template <int NB>
 cudaError_t launch_nb(bpmf_gpu_ctx *c, const BlockArgs &p, long long n)
 {
     using C = Cfg<NB>;
     static_assert(C::SMEM <= 227 * 1024, "shared memory budget");
     auto kern = items_block_kernel<NB>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    // BPMF_BLOCK_1CTA (timing probe): pad the shared memory request so that only one CTA fits an SM
+    static const bool one_cta = getenv("BPMF_BLOCK_1CTA") != nullptr;
+    const int smem = one_cta && C::SMEM < 120 * 1024 ? 120 * 1024 : C::SMEM;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::T, C::SMEM);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::T, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     long long grid = (long long)c->sm_count * per_sm;
     if (grid > n) grid = n;
-    kern<<<(unsigned)grid, C::T, C::SMEM, c->stream>>>(p);
+    kern<<<(unsigned)grid, C::T, smem, c->stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -412,7 +564,9 @@ cudaError_t launch_items_block(bpmf_gpu_ctx *c, int side, uint32_t iter, double 
     p.work_counter = s.work_counter; p.err = c->d_err;
     static const int dbg = [] { const char *v = getenv("BPMF_BLOCK_DBG"); return v ? atoi(v) : 0; }();
     p.dbg = dbg;
-    cudaError_t e = cudaMemsetAsync(s.work_counter, 0, sizeof(unsigned int), c->stream);
+    cudaError_t e = cudaSuccess;
+    if ((e = build_schedules(c->device)) != cudaSuccess) return e;     // once per device
+    e = cudaMemsetAsync(s.work_counter, 0, sizeof(unsigned int), c->stream);
     if (e != cudaSuccess) return e;
     const long long n = (long long)s.to - s.from;
     if (n < 1) return cudaSuccess;
