@@ -68,6 +68,7 @@ SYMBOLS = {
     "bpmf_gpu_last_items_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "bpmf_gpu_items_kernel_time": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "bpmf_gpu_debug_set_tuning": (C.c_int, [C.c_void_p, C.c_int]),
+    "bpmf_gpu_debug_block_schedule": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "bpmf_gpu_debug_randn": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, _f64p]),
 }
 

@@ -102,16 +102,6 @@ struct Cfg {
 // tail of this kernel is bound by shared-memory wavefronts. Pairs (c, c + 1) with c even stay adjacent and 16-byte aligned.
 __host__ __device__ __forceinline__ constexpr int swz(int r) { return (r & 2) << 1; }
 
-// 1 / p for a positive normal p: MUFU.RCP64H seed + one cubic step (same as the K = 32 kernel)
-__device__ __forceinline__ double fast_rcp(double p)
-{
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(p));
-    const double e = fma(-p, r, 1.0);
-    const double t = fma(e, e, e);
-    return fma(r, t, r);
-}
-
 // The Gram of the (at most SR) ratings of one stage for warp W (compile-time: the operands of a DMMA are registers):
 // acc[0 .. W] = blocks (W, 0..W), acc[W+1 .. NB] = blocks (NB-1-W, 0..NB-1-W). Only this part of the per-item code differs
 // between the warps; everything else is shared, which keeps the instruction footprint small.
@@ -474,19 +464,19 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB == 10 ? 3 : NB 
 // The trailing-update schedule of block column kb: the trailing triangle plus block row NB (the right-hand side), minus
 // the next diagonal tile (warp 0's), cut into 2 x 2 QUADS of tiles that share their A / B fragments; the quads go
 // round-robin to warps 1 .. NWB-1 (to the only warp when NWB == 1). It does not depend on the item.
-static cudaError_t build_schedules(int device)
-{
-    static std::mutex mu;
-    static std::vector<int> done;
-    std::lock_guard<std::mutex> lock(mu);
-    for (int d : done) if (d == device) return cudaSuccess;
-    auto tile = [](int I, int J) { return (I * (I + 1) / 2 + J) * 64; };
+struct Schedules {
     std::vector<int4> tab;
     std::vector<int2> span;
     int spanbase[17] = {0};
+};
+
+static Schedules make_schedules()
+{
+    Schedules S;
+    auto tile = [](int I, int J) { return (I * (I + 1) / 2 + J) * 64; };
     for (int NB : {2, 6, 8, 10, 12, 14, 16}) {
         const int NWB = NB / 2;
-        spanbase[NB] = (int)span.size();
+        S.spanbase[NB] = (int)S.span.size();
         std::vector<std::vector<int4>> per((size_t)NB * NWB);        // two int4 per quad
         for (int kb = 0; kb + 1 < NB; ++kb) {
             // a tile (I, J) of this block column's trailing update: kb < J <= I < NB, or block row NB (the right-hand
@@ -511,16 +501,26 @@ static cudaError_t build_schedules(int device)
                 }
         }
         for (size_t i = 0; i < per.size(); ++i) {
-            span.push_back(make_int2((int)(tab.size() / 2), (int)((tab.size() + per[i].size()) / 2)));    // in quads
-            tab.insert(tab.end(), per[i].begin(), per[i].end());
+            S.span.push_back(make_int2((int)(S.tab.size() / 2), (int)((S.tab.size() + per[i].size()) / 2)));    // in quads
+            S.tab.insert(S.tab.end(), per[i].begin(), per[i].end());
         }
     }
-    if (tab.size() > 2 * (size_t)MAX_QUADS || span.size() > (size_t)MAX_SPANS) return cudaErrorInvalidValue;
-    cudaError_t e = cudaMemcpyToSymbol(c_ttab, tab.data(), sizeof(int4) * tab.size());
+    return S;
+}
+
+static cudaError_t build_schedules(int device)
+{
+    static std::mutex mu;
+    static std::vector<int> done;
+    std::lock_guard<std::mutex> lock(mu);
+    for (int d : done) if (d == device) return cudaSuccess;
+    const Schedules S = make_schedules();
+    if (S.tab.size() > 2 * (size_t)MAX_QUADS || S.span.size() > (size_t)MAX_SPANS) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemcpyToSymbol(c_ttab, S.tab.data(), sizeof(int4) * S.tab.size());
     if (e != cudaSuccess) return e;
-    e = cudaMemcpyToSymbol(c_tspan, span.data(), sizeof(int2) * span.size());
+    e = cudaMemcpyToSymbol(c_tspan, S.span.data(), sizeof(int2) * S.span.size());
     if (e != cudaSuccess) return e;
-    e = cudaMemcpyToSymbol(c_spanbase, spanbase, sizeof spanbase);
+    e = cudaMemcpyToSymbol(c_spanbase, S.spanbase, sizeof S.spanbase);
     if (e != cudaSuccess) return e;
     done.push_back(device);
     return cudaSuccess;
@@ -550,6 +550,25 @@ cudaError_t launch_nb(bpmf_gpu_ctx *c, const BlockArgs &p, long long n)
 }  // namespace
 
 bool block_kernel_supports(int K) { return K % 16 == 0 && K >= 16 && K <= 128 && K != 32; }
+
+// Host-only view of the trailing-update schedule (tests): the quads warp `warp` takes in block column kb, eight ints per
+// quad (tile offsets in doubles: Lu(I0,kb), Lu(I1,kb), Lu(J0,kb), Lu(J1,kb), A(I0,J0), A(I0,J1), A(I1,J0), A(I1,J1); -1 =
+// not a tile). Returns the number of quads, or -1.
+int block_schedule(int K, int kb, int warp, int *out, int cap_quads)
+{
+    if (!block_kernel_supports(K)) return -1;
+    const int NB = K / 8, NWB = NB / 2;
+    if (kb < 0 || kb >= NB || warp < 0 || warp >= NWB) return -1;
+    static const Schedules S = make_schedules();
+    const int2 sp = S.span[(size_t)S.spanbase[NB] + (size_t)kb * NWB + warp];
+    const int n = sp.y - sp.x;
+    for (int q = 0; q < n && q < cap_quads; ++q) {
+        const int4 a = S.tab[2 * (size_t)(sp.x + q)], c = S.tab[2 * (size_t)(sp.x + q) + 1];
+        const int v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+        for (int i = 0; i < 8; ++i) out[8 * q + i] = v[i];
+    }
+    return n;
+}
 
 cudaError_t launch_items_block(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha)
 {

@@ -980,6 +980,12 @@ int bpmf_gpu_debug_set_tuning(bpmf_gpu_ctx *ctx, int stream_cfg)
     return BPMF_GPU_OK;
 }
 
+int bpmf_gpu_debug_block_schedule(int num_latent, int block_column, int warp, int *out, int cap_quads)
+{
+    if (!out || cap_quads < 0) return -1;
+    return block_schedule(num_latent, block_column, warp, out, cap_quads);
+}
+
 int bpmf_gpu_debug_randn(bpmf_gpu_ctx *ctx, uint32_t c, int n, double *host_out)
 {
     if (!ctx || n < 1 || n > 4096 || !host_out) return BPMF_GPU_EINVAL;

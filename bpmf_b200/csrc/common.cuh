@@ -125,6 +125,7 @@ size_t exact_items_smem_bytes(int K);
 cudaError_t launch_items_dmma32(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha);
 // block_kernel.cu
 bool block_kernel_supports(int K);
+int block_schedule(int K, int kb, int warp, int *out, int cap_quads);
 cudaError_t launch_items_block(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha);
 // stream_kernel.cu
 cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha);

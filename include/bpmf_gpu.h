@@ -182,6 +182,11 @@ int bpmf_gpu_items_kernel_time(bpmf_gpu_ctx *ctx, double *total_ms, int *count);
 int bpmf_gpu_debug_set_tuning(bpmf_gpu_ctx *ctx, int stream_cfg);
 /* device RNG probes for known-answer tests: n normals of the stream rng_set_pos(c) */
 int bpmf_gpu_debug_randn(bpmf_gpu_ctx *ctx, uint32_t c, int n, double *host_out);
+/* Host only, no GPU needed (tests): the trailing-update schedule of the CTA-per-item kernel (K = 16 m, K != 32) — the
+ * quads of 8 x 8 tiles warp `warp` updates in block column `block_column` of the blocked LDL^T, eight ints per quad
+ * (offsets in doubles of Lu(I0,kb), Lu(I1,kb), Lu(J0,kb), Lu(J1,kb), A(I0,J0), A(I0,J1), A(I1,J0), A(I1,J1); -1 = no
+ * tile). Returns the number of quads (writes at most cap_quads of them), -1 for a bad argument. */
+int bpmf_gpu_debug_block_schedule(int num_latent, int block_column, int warp, int *out, int cap_quads);
 
 #ifdef __cplusplus
 }
