@@ -2,7 +2,8 @@
 // other than 32 (16, 48, 64, 80, 96, 112, 128) on sm_100a: ONE CTA PER ITEM, NB/2 warps (NB = K / 8).
 //
 //   gather  The K-vectors of the item's ratings are staged global -> shared with cp.async in stages of 32 rows (row pitch
-//           8K + 32 bytes: conflict-free fragment loads), three stages in flight, every thread copying eight 16-byte chunks
+//           8K + 32 bytes: conflict-free fragment loads), a ring of three stages (two in flight while one is consumed, ONE CTA
+//           barrier per stage), every thread copying eight 16-byte chunks
 //           whose row indices were loaded one stage earlier.
 //   Gram    fp64 tensor cores (mma.sync.m8n8k4, DMMA). The lower triangle of NB x NB blocks of 8 x 8 is spread over the
 //           warps' REGISTERS: warp w owns block rows w and NB-1-w (NB + 1 blocks, 2 NB + 2 accumulator doubles per
@@ -198,12 +199,17 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB == 10 ? 3 : NB 
                 cp_async_commit();
             };
 #pragma unroll 1
-            for (int st = 0; st < NS; ++st) { load_rows(st); issue(st); }
-            load_rows(NS);
+            for (int st = 0; st < NS - 1; ++st) { load_rows(st); issue(st); }
+            load_rows(NS - 1);
 #pragma unroll 1
             for (int st = 0; st < nst; ++st) {
-                cp_async_wait<NS - 1>();
+                // ONE barrier per stage: stage st has landed (for everyone), and everyone is done with stage st - 1, whose
+                // slot is refilled right away with stage st + NS - 1 (so NS - 1 stages are in flight while st is consumed;
+                // refilling after this stage's DMMAs instead measured the same)
+                cp_async_wait<NS - 2>();
                 __syncthreads();
+                issue(st + NS - 1);
+                load_rows(st + NS);
                 const unsigned char *stg = smem + (st % NS) * C::STAGE;
                 const double *swp = sw + (st % NS) * SR;
                 const int left = (int)min((int64_t)SR, pe - (ps + (int64_t)st * SR));
@@ -217,9 +223,6 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB == 10 ? 3 : NB 
                 case 6: if constexpr (NWB > 6) gram_groups<NB, 6>(acc, r0, r1, stg, swp, left, g, t, p.dbg); break;
                 default: if constexpr (NWB > 7) gram_groups<NB, 7>(acc, r0, r1, stg, swp, left, g, t, p.dbg); break;
                 }
-                __syncthreads();          // the slot is free
-                issue(st + NS);
-                load_rows(st + NS + 1);
             }
             cp_async_wait<0>();
             __syncthreads();              // the ring is dead: the tiles may overwrite it
