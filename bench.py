@@ -270,6 +270,13 @@ def main():
                            "items_dmma32_kernel" if args.variant == "dmma" else "items_stream32v3_kernel<2,20>"),
                 "kernel_ms_avg": k_avg_ms, "kernel_launches_timed": k_n, "kernel_share_of_step": k_ms / ms,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src + " (of measured, burst)"}
+    if K != 32:
+        # above K = 32 the Gram (nnz * K (K + 1) / 2 FMAs on the fp64 tensor cores) outweighs the gather: report it against the
+        # measured DMMA peak too (bench_micro/fp64_pipes.cu, profiles/r01_fp64_pipes_microbench.txt: 37.0 TFLOP/s)
+        gram_flop = ratings.nnz / world * (K * (K + 1) / 2 + K) * 2.0
+        roofline["fp64_tensor"] = {"achieved": gram_flop / (k_avg_ms / 1e3) / 1e12, "peak": 37.0, "unit": "TFLOP/s",
+                                   "frac": gram_flop / (k_avg_ms / 1e3) / 1e12 / 37.0,
+                                   "peak_source": "profiles/r01_fp64_pipes_microbench.txt (DMMA m8n8k4, measured on B200)"}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
