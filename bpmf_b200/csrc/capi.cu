@@ -75,11 +75,14 @@ int check_device_error(bpmf_gpu_ctx *ctx)
     return fail(ctx, BPMF_GPU_ECUDA, b);
 }
 
+static bool prop_on_stream(const bpmf_gpu_ctx *ctx, int side) { return ctx->K == 32 && ctx->side[side].n_heavy == 0; }
+
 int pick_variant(const bpmf_gpu_ctx *ctx, int side, int v)
 {
-    // per-item prior precisions (propagated posterior) are only read by the any-K kernel
+    // per-item prior precisions (propagated posterior) are read by the any-K kernel and, for K = 32 on a side without
+    // heavy items, by the PROP instantiation of the stream kernel
     if (v == BPMF_GPU_KERNEL_AUTO) {
-        if (ctx->side[side].propLambda) return BPMF_GPU_KERNEL_EXACT;
+        if (ctx->side[side].propLambda) return prop_on_stream(ctx, side) ? BPMF_GPU_KERNEL_STREAM : BPMF_GPU_KERNEL_EXACT;
         if (ctx->K == 32) return BPMF_GPU_KERNEL_STREAM;
         return block_kernel_supports(ctx->K) ? BPMF_GPU_KERNEL_BLOCK : BPMF_GPU_KERNEL_EXACT;
     }
@@ -706,7 +709,8 @@ int bpmf_gpu_sample_items(bpmf_gpu_ctx *ctx, int side, uint32_t iter, double alp
     if (s.num_other != o.num) return fail(ctx, BPMF_GPU_EINVAL, "sides disagree on dimensions");
     CU(cudaSetDevice(ctx->device));
     const int v = pick_variant(ctx, side, kernel_variant);
-    if (s.propLambda && v != BPMF_GPU_KERNEL_EXACT) return fail(ctx, BPMF_GPU_EINVAL, "a propagated posterior needs the EXACT (or AUTO) kernel variant");
+    if (s.propLambda && v != BPMF_GPU_KERNEL_EXACT && !(v == BPMF_GPU_KERNEL_STREAM && prop_on_stream(ctx, side)))
+        return fail(ctx, BPMF_GPU_EINVAL, "a propagated posterior needs the EXACT, AUTO or (K = 32, no heavy items) STREAM kernel variant");
     const int slot = (int)(ctx->ev_count % bpmf_gpu_ctx::EV_RING);
     CU(cudaEventRecord(ctx->ev0[slot], ctx->stream));
     if (v == BPMF_GPU_KERNEL_EXACT) CU(launch_items_exact(ctx, side, iter, alpha));

@@ -63,6 +63,7 @@ struct StreamArgs {
     const double *zero_row;   // 256 bytes of zeros in global memory (bulk-copy variant: source of the padding rows)
     int bulk_end;             // v3: items of [from, bulk_end) are claimed CLAIM at a time, [bulk_end, to) CLAIM_TAIL at a time
     int heavy_thr;            // SKIP: items with more ratings than this belong to the chunked path and are passed over
+    const double *propLambda; // PROP: K*K x num per-item prior precisions (-m / -l, sample.cpp:272-277)
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
@@ -209,10 +210,20 @@ __device__ __forceinline__ void chol3_block_column(double (&c)[10][2], double &m
 // The tail of one item for one warp (shared by the stream kernel and the heavy-item kernel): on entry the accumulators
 // hold the item's Gram (DMMA layout) and rrp the quad-partial right-hand side; `stg` is TSCRATCH bytes of the warp's
 // shared memory. Normals, MM = LambdaF + alpha G, LDL^T, solves, store (sample.cpp:266,297-324). Resets c and rrp.
-template <int DBG>
+// PROP: the item has its own prior precision (propagated posterior, sample.cpp:272-283): LambdaF is read from
+// p.propLambda instead of shared memory, and rr starts from LambdaF_i * hp.mu with the GLOBAL hp.mu (quirk Q5), which the
+// caller keeps in srr0.
+template <int DBG, bool PROP = false>
 __device__ __forceinline__ void tail32_warp(double (&c)[10][2], double (&rrp)[4], const int idx, unsigned char *stg, const double *sLF,
                                             const double *srr0, const StreamArgs &p, const int lane)
 {
+    const double *LF = PROP ? p.propLambda + (size_t)idx * 1024 : sLF;   // LambdaF(i,k) at LF[k * LS + i]
+    constexpr int LS = PROP ? 32 : LFS;
+    double rr0 = 0.0;
+    if (PROP) {
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) rr0 = fma(__ldg(LF + j * 32 + lane), srr0[j], rr0);   // rr = hp_LambdaF * hp.mu (sample.cpp:285)
+    }
     const int g = lane >> 2, t = lane & 3;
     double *zy = reinterpret_cast<double *>(stg + V3_ZY_OFF), *zr = reinterpret_cast<double *>(stg + V3_ZR_OFF);
     double *wb = reinterpret_cast<double *>(stg + V3_B_OFF), *Lp = reinterpret_cast<double *>(stg);
@@ -238,11 +249,12 @@ __device__ __forceinline__ void tail32_warp(double (&c)[10][2], double (&rrp)[4]
     }
     if (t == 0) {
 #pragma unroll
-        for (int a = 0; a < 4; ++a) wb[8 * a + g] = srr0[8 * a + g] + rrp[a];
+        for (int a = 0; a < 4; ++a) wb[8 * a + g] = (PROP ? 0.0 : srr0[8 * a + g]) + rrp[a];
     }
     __syncwarp();
     const double z = (DBG & 8) ? 0.25 * lane : __dmul_rn(zy[lane], polar_mult(zr[lane]));
     double bb = wb[lane];
+    if (PROP) bb += rr0;
     // MM = LambdaF + alpha * G (sample.cpp:297-298), in place in the accumulator layout
 #pragma unroll
     for (int I = 0; I < 4; ++I)
@@ -250,7 +262,7 @@ __device__ __forceinline__ void tail32_warp(double (&c)[10][2], double (&rrp)[4]
         for (int J = 0; J <= I; ++J)
 #pragma unroll
             for (int e = 0; e < 2; ++e)
-                c[blk(I, J)][e] = fma(p.alpha, c[blk(I, J)][e], sLF[(8 * J + 2 * t + e) * LFS + 8 * I + g]);   // LambdaF(i,k), i >= k
+                c[blk(I, J)][e] = fma(p.alpha, c[blk(I, J)][e], LF[(8 * J + 2 * t + e) * LS + 8 * I + g]);   // LambdaF(i,k), i >= k
     // chol.compute(MM) (sample.cpp:306) as MM = Lu D Lu^T; lane k ends up with d_k and 1 / d_k
     double myd = 1.0, myrinv = 1.0;
     bool ok = true;
@@ -332,7 +344,7 @@ __device__ __forceinline__ void tail32_warp(double (&c)[10][2], double (&rrp)[4]
 // SKIP: the range holds heavy items (more than p.heavy_thr ratings). They are sampled by heavy_gram32_kernel /
 // heavy_tail32_kernel, which run AFTER this kernel on the same stream; here they are gathered as if they had no ratings
 // (a prior-only draw that the heavy path overwrites), which keeps the fetch state machine contiguous.
-template <int NS, int NW, int DBG, bool BULK, int TOK, bool SKIP = false>
+template <int NS, int NW, int DBG, bool BULK, int TOK, bool SKIP = false, bool PROP = false>
 __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs p)
 {
     constexpr int WARP_BYTES = warp_bytes<NS>();
@@ -353,7 +365,7 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs
     if (tid < 32) {
         double s = 0.0;
         for (int j = 0; j < 32; ++j) s += sLF[j * LFS + tid] * p.mu[j];   // rr = LambdaF * hp.mu (sample.cpp:285)
-        srr0[tid] = s;
+        srr0[tid] = PROP ? p.mu[tid] : s;                                 // PROP: per-item LambdaF, the tail needs hp.mu itself
     }
     __syncthreads();
 
@@ -549,7 +561,7 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs
             h = (h + 1 == NS) ? 0 : h + 1;
             continue;
         }
-        tail32_warp<DBG>(c, rrp, idx, stg, sLF, srr0, p, lane);
+        tail32_warp<DBG, PROP>(c, rrp, idx, stg, sLF, srr0, p, lane);
         __syncwarp();                     // the scratch is free again
         issue_stage(h);
         h = (h + 1 == NS) ? 0 : h + 1;
@@ -649,10 +661,10 @@ cudaError_t launch_cfg(bpmf_gpu_ctx *c, const StreamArgs &p, long long n)
     constexpr size_t smem = (size_t)NW * warp_bytes<NS>() + SHARED_BYTES;
     static_assert(smem <= 227 * 1024, "shared memory budget");
 #ifdef BPMF_STREAM_PROBES
-    auto kern = VER >= 3 ? items_stream32v3_kernel<NS, NW, DBG, VER == 6, (VER == 7 ? 1 : VER == 8 ? 2 : VER == 9 ? 3 : 0), VER == 12> : items_stream32_kernel<NS, NW>;
+    auto kern = VER >= 3 ? items_stream32v3_kernel<NS, NW, DBG, VER == 6, (VER == 7 ? 1 : VER == 8 ? 2 : VER == 9 ? 3 : 0), VER == 12, VER == 13> : items_stream32_kernel<NS, NW>;
 #else
     static_assert(VER >= 3, "the v2 kernel is an experiment (stream_experiments.cuh)");
-    auto kern = items_stream32v3_kernel<NS, NW, DBG, VER == 6, (VER == 7 ? 1 : VER == 8 ? 2 : VER == 9 ? 3 : 0), VER == 12>;
+    auto kern = items_stream32v3_kernel<NS, NW, DBG, VER == 6, (VER == 7 ? 1 : VER == 8 ? 2 : VER == 9 ? 3 : 0), VER == 12, VER == 13>;
 #endif
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -759,7 +771,7 @@ static cudaError_t launch_stream_range(bpmf_gpu_ctx *c, int side, uint32_t iter,
     p.other = o.items; p.items = s.items;
     p.npeers = s.npeers; p.peers = s.peers_dev;
     p.mu = s.hp.mu; p.LambdaF = s.hp.LambdaF;
-    p.work_counter = s.work_counter; p.err = c->d_err; p.zero_row = c->d_zero_row; p.heavy_thr = s.heavy_thr;
+    p.work_counter = s.work_counter; p.err = c->d_err; p.zero_row = c->d_zero_row; p.heavy_thr = s.heavy_thr; p.propLambda = s.propLambda;
     cudaError_t e = cudaMemsetAsync(s.work_counter, 0, 2 * sizeof(unsigned int), c->stream);
     if (e != cudaSuccess) return e;
     const long long n = (long long)to - from;
@@ -781,6 +793,11 @@ static cudaError_t launch_stream_range(bpmf_gpu_ctx *c, int side, uint32_t iter,
     // Set with bpmf_gpu_debug_set_tuning or the environment variable BPMF_STREAM_CFG.
     static const int env_cfg = [] { const char *v = getenv("BPMF_STREAM_CFG"); return v ? atoi(v) : 0; }();
     const int cfg = c->stream_cfg ? c->stream_cfg : env_cfg;
+    if (s.propLambda) {                   // per-item prior precisions (propagated posterior): v3, 2 stages x 16 warps
+        e = launch_cfg<2, 16, 13>(c, p, n);
+        c->launches++;
+        return e;
+    }
     if (skip_heavy) {                     // v3, 2 stages x 20 warps, passing over the heavy items
         e = launch_cfg<2, 20, 12>(c, p, n);
         c->launches++;
@@ -883,6 +900,7 @@ cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, doub
     p.npeers = s.npeers; p.peers = s.peers_dev;
     p.mu = s.hp.mu; p.LambdaF = s.hp.LambdaF;
     p.work_counter = s.work_counter; p.err = c->d_err; p.zero_row = c->d_zero_row; p.bulk_end = s.to; p.heavy_thr = s.heavy_thr;
+    p.propLambda = nullptr;
     const int ch0 = s.h_heavy_first[first], ch1 = s.h_heavy_first[last];
     heavy_gram32_kernel<<<(ch1 - ch0 + 3) / 4, 128, 0, c->stream>>>(p, ch1 - ch0, s.hv_p0 + ch0, s.hv_p1 + ch0,
                                                                      s.hv_partials + (size_t)ch0 * HEAVY_PART);

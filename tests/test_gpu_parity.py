@@ -356,7 +356,8 @@ def test_sample_host_matches_device_resident_sample(gpu):
 @pytest.mark.parametrize("K", [16, 32])
 def test_propagated_posterior_priors(gpu, K):
     """-m / -l (c++/sample.cpp:152-174,272-283): per-item prior precisions replace hp.LambdaF, the rhs still uses the
-    GLOBAL hp.mu (quirk Q5). Device (any-K kernel, picked by KERNEL_AUTO) against the oracle."""
+    GLOBAL hp.mu (quirk Q5). Against the oracle: the kernel KERNEL_AUTO picks (K = 32: the PROP instantiation of the
+    stream kernel, otherwise the any-K kernel) and, for K = 32, the any-K kernel asked for explicitly."""
     train, test = util.synth_ratings(120, 90, 2500, 5 + K)
     orc = util.make_oracle(K, train, test)
     ctx = util.make_gpu_from_oracle(orc, K)
@@ -371,14 +372,19 @@ def test_propagated_posterior_priors(gpu, K):
     for side, it in ((MOVIES, 2), (USERS, 2), (MOVIES, 3)):
         orc.set_iter(side, it)
         orc.sample_range(side, 0, orc.num(side))
-        ctx.sample_items(side, it, 2.0, gpu.KERNEL_AUTO)
-        got, ref = ctx.get_items(side), orc.items(side)
-        assert np.abs(got - ref).max() <= TOL_EXACT * 50 * max(1.0, np.abs(ref).max()), (side, it)
+        ref = orc.items(side)
+        for variant in ([gpu.KERNEL_AUTO, gpu.KERNEL_EXACT, gpu.KERNEL_STREAM] if K == 32 else [gpu.KERNEL_AUTO]):
+            before = ctx.get_items(side)
+            ctx.sample_items(side, it, 2.0, variant)
+            got = ctx.get_items(side)
+            tol = (TOL_ITEMS if variant != gpu.KERNEL_EXACT else TOL_EXACT * 50) * max(1.0, np.abs(ref).max())
+            assert np.abs(got - ref).max() <= tol, (side, it, variant)
+            ctx.set_items(side, before)
         ctx.set_items(side, ref)
-    if K == 32:   # the tensor-core kernels read the shared LambdaF only: asking for them with a prior is an error
+    if K == 32:   # the first tensor-core kernel reads the shared LambdaF only: asking for it with a prior is an error
         with pytest.raises(gpu.BpmfGpuError):
-            ctx.sample_items(MOVIES, 4, 2.0, gpu.KERNEL_STREAM)
-    ctx.set_prop_posterior(MOVIES, None, None)          # priors removed: back to the fast kernel
+            ctx.sample_items(MOVIES, 4, 2.0, gpu.KERNEL_DMMA)
+    ctx.set_prop_posterior(MOVIES, None, None)          # priors removed: back to the shared hyper-parameters
     ctx.sample_items(MOVIES, 4, 2.0, gpu.KERNEL_STREAM if K == 32 else gpu.KERNEL_AUTO)
     ctx.sync()
     ctx.close()
