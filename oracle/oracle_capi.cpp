@@ -1,5 +1,5 @@
 // oracle_capi.cpp — extern "C" surface of the CPU oracle for ctypes. TEST INFRASTRUCTURE ONLY
-// (see bpmf_oracle.hpp header: parity unpinned against reference outputs; pinned at the Philox KAT
+// (see bpmf_oracle.hpp header: pinned against the reference's own hot-path sources built with stand-in headers, and at the Philox KAT
 // and libstdc++ distribution level).
 #include "bpmf_oracle.hpp"
 
