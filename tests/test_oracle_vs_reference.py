@@ -128,3 +128,52 @@ def test_cholesky_failure_is_reported_by_both():
         ref.sample(MOVIES)
     with pytest.raises(RuntimeError):
         orc.sweep(MOVIES)
+
+
+@pytest.mark.parametrize("name", ["tiny_k10", "synth_k32"])
+def test_reference_executable_fixtures(name, tmp_path):
+    """tests/golden/refexe_chain_*.json were produced by the REFERENCE EXECUTABLE — every translation unit of its `bpmf`
+    target compiled unmodified against the stand-in headers (tests/golden/make_ref_exe_golden.py) — on the reference's
+    own data/tiny with run_test.sh's arguments and on the synthetic K = 32 problem. The oracle (one thread, like that
+    build) must reproduce them exactly: the -v dumps bit for bit, and the log's RMSE / avg RMSE / FU / FM / "Final Avg
+    RMSE" fields as printed. Where the executable is available (this container) it is also re-run: the committed
+    fixture must be what it produces."""
+    import importlib.util
+    import json
+    import os
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+    def load(modname):
+        spec_mod = importlib.util.spec_from_file_location(modname, os.path.join(gdir, modname + ".py"))
+        mod = importlib.util.module_from_spec(spec_mod)
+        spec_mod.loader.exec_module(mod)
+        return mod
+
+    gold = json.load(open(os.path.join(gdir, "refexe_chain_%s.json" % name)))
+    spec = gold["spec"]
+    train, test = load("make_chain_golden").problem(spec)
+    m = util.make_oracle(spec["K"], train, test, alpha=2.0, burnin=spec["burnin"], nthreads=1)
+    for it, g in enumerate(gold["iterations"]):
+        m.iterate()
+        V, U = m.items(MOVIES), m.items(USERS)
+        assert [float(x) for x in V.mean(0)] == g["V_mean"] and [float(x) for x in U.mean(0)] == g["U_mean"], it
+        assert [float(x) for x in V[0]] == g["V_first"] and [float(x) for x in U[-1]] == g["U_last"], it
+        assert float(np.sqrt((V * V).sum())) == g["V_norm"] and float(np.sqrt((U * U).sum())) == g["U_norm"], it
+        r = m.rmse(MOVIES)
+        log = g["log"]
+        assert log["iter"] == it and log["phase"] == ("Burnin" if it < spec["burnin"] else "Sampling")
+        assert "%.4f" % r[0] == log["rmse"] and "%.4f" % r[1] == log["rmse_avg"], (it, r, log)
+        assert "%.2f" % np.sqrt(m.stats(USERS)[3]) == log["FU"] and "%.2f" % np.sqrt(m.stats(MOVIES)[3]) == log["FM"], (it, log)
+    m.finish()
+    assert "%g" % m.rmse(MOVIES)[1] == gold["final_avg_rmse_printed"]
+    # the oracle's own fixture (made with all threads: the sweep reductions then add in another order, as the
+    # reference's do under OpenMP) agrees to round-off
+    own = json.load(open(os.path.join(gdir, "chain_%s.json" % name)))
+    for a, b in zip(own["iterations"], gold["iterations"]):
+        for k in ("V_mean", "U_mean", "V_first", "U_last"):
+            assert np.abs(np.array(a[k]) - np.array(b[k])).max() <= 1e-12
+    exe = os.path.join(os.path.dirname(gdir), "..", "oracle", "_ref", "bpmf_ref_k%d" % spec["K"])
+    if os.path.exists(exe) and os.path.exists("/root/reference/c++/bpmf.cpp"):
+        gen = load("make_ref_exe_golden")
+        log, out = gen.run_reference_exe(spec, str(tmp_path))
+        assert gen.summarise(spec, log, out) == gold
