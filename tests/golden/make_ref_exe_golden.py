@@ -43,7 +43,7 @@ def read_ddm(path):
 
 def run_reference_exe(spec, workdir):
     """-> (stdout, output directory) of the reference executable on the problem of `spec`"""
-    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "ref"])
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "ref-core"])
     exe = os.path.join(ROOT, "oracle", "_ref", "bpmf_ref_k%d" % spec["K"])
     if spec["data"] == "tiny" and os.path.exists("/root/reference/data/tiny/train.mtx"):
         train_path, test_path = "/root/reference/data/tiny/train.mtx", "/root/reference/data/tiny/test.mtx"   # the files themselves
