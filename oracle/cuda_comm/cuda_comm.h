@@ -5,7 +5,7 @@
 //
 // oracle/Makefile (target `ref`) builds the reference executable with it — every translation unit of the reference
 // unmodified, except that c++/bpmf.cpp gets the one extra branch of its `#if` ladder that INTEGRATION.md names (applied
-// on the fly into oracle/_ref/gen/, never stored in the repository) — as oracle/_ref/bpmf_ref_cuda_k<K>, against the
+// on the fly, sed into the compiler's standard input, never stored) — as oracle/_ref/bpmf_ref_cuda_k<K>, against the
 // stand-in Eigen / Random123 headers of oracle/shim/. The reference's own main loop, its own host `predict`
 // (c++/sample.cpp:48-96, non-virtual there) and its own file formats then run around the CUDA sweep.
 //
