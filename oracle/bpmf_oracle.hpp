@@ -11,7 +11,7 @@
 // c++/sample.cpp and c++/mvnormal.cpp — are compiled UNMODIFIED from /root/reference into oracle/_ref/ against minimal
 // stand-in headers for those two libraries (oracle/shim/, oracle/Makefile target `ref`, oracle/ref_harness.cpp), and
 // tests/test_oracle_vs_reference.py holds this restatement to them EXACTLY (latents, hyper-parameters, cov, norm,
-// RMSEs, Pavg / Pm2, aggregates, propagated posterior, Cholesky failure; K = 10, 16, 32). That pins everything the
+// RMSEs, Pavg / Pm2, aggregates, propagated posterior, Cholesky failure; K = 10, 16, 32, 48, 64, 128). That pins everything the
 // reference's text decides: RNG keying and consumption, the quirks, the averaging of predict. Also pinned
 // (tests/test_oracle_kat.py):
 //   * Philox4x32-10 against the Random123 kat_vectors and the C++26 [rand.predef] philox4x32

@@ -11,7 +11,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = os.environ.get("BPMF_REFERENCE_SRC", "/root/reference/c++")
-KS = (10, 16, 32)
+KS = (10, 16, 32, 48, 64, 128)
 
 _f64 = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 _i32 = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")

@@ -33,7 +33,7 @@ def _same(a, b):
     return a.shape == b.shape and a.tobytes() == b.tobytes()
 
 
-@pytest.mark.parametrize("K", [10, 16, 32])
+@pytest.mark.parametrize("K", [10, 16, 32, 128])
 def test_rng_streams(K):
     """rng_set_pos + randn of c++/mvnormal.cpp on the MicroURNG / Philox stand-in = the oracle's, for the counters the path
     uses: iter (hyper draw) and (idx + 1) * K * (iter + 1) (items), including a 32-bit wrap."""
@@ -47,6 +47,9 @@ def test_rng_streams(K):
     (10, (40, 30), 300, {}),
     (16, (120, 90), 1500, dict(skew=1.0, empty_rows=10, heavy_col=100)),
     (32, (150, 110), 4000, dict(skew=0.8, empty_rows=12)),
+    (48, (90, 70), 2500, dict(skew=1.0, heavy_col=60)),
+    (64, (90, 70), 2500, {}),
+    (128, (60, 50), 1800, dict(heavy_col=55)),
 ])
 def test_chain_matches_reference_sources_bit_for_bit(K, shape, nnz, kw):
     """8 iterations of the reference's main loop (movies.sample(users); users.sample(movies); both predicts,
