@@ -78,6 +78,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
+def host_threads():
+    """the host cores this process may use. Explicit, because torch.distributed.run exports OMP_NUM_THREADS=1 to its workers and
+    the OpenMP runtime of the CPU arm would silently run on one core."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -91,17 +100,30 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle on a bounded sample of the same matrix
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_baseline(ratings, K, alpha, budget_s=12.0, threads=0, max_rows=None):
+class CpuBaseline:
     """Times the oracle's per-item loop (sample.cpp:352-372: OpenMP over items, schedule(guided)) on the first S user
     rows and the first S movie columns of the workload, the other side's full-size latent matrix resident in host
-    memory, so every item does exactly the work it does in the full job. Returns samples/s and what was sampled."""
-    from oracle import oracle as o
-    ncores = o.lib().bpmf_oracle_max_threads() if threads <= 0 else threads
-    rng = np.random.Generator(np.random.PCG64(7))
+    memory, so every item does exactly the work it does in the full job. S is sized once from a calibration pass so that
+    one step() is about budget_s seconds of CPU work (the whole matrix if that fits); the sub-models are built once and
+    re-sampled by every step()."""
 
-    def sub_model(side, S):
+    def __init__(self, ratings, K, alpha, budget_s=12.0, threads=0):
+        from oracle import oracle as o
+        self.o, self.ratings, self.K, self.alpha = o, ratings, K, alpha
+        # always passed explicitly (num_threads clause of the oracle): torchrun exports OMP_NUM_THREADS=1
+        self.threads = host_threads() if threads <= 0 else threads
+        self.rng = np.random.Generator(np.random.PCG64(7))
+        cal = [self._sub_model(side, 4000) for side in (0, 1)]
+        t, items, _ = self._run(cal)                  # calibration pass (also warms the OpenMP team)
+        rate = items / t
+        self.S = int(max(4000, min(rate * budget_s / 2, max(ratings.nrows, ratings.ncols))))
+        self.models = cal if self.S == 4000 else [self._sub_model(side, self.S) for side in (0, 1)]
+        self.iter = 3
+
+    def _sub_model(self, side, S):
         # users sample: rows [0,S) of R against all movies; movies sample: columns [0,S) of R against all users
-        n, n_other, ptr, idx, val = ratings.side(side)
+        o, K = self.o, self.K
+        n, n_other, ptr, idx, val = self.ratings.side(side)
         S = min(S, n)
         e = int(ptr[S])
         own = np.repeat(np.arange(S, dtype=np.int32), np.diff(ptr[:S + 1]))
@@ -111,36 +133,139 @@ def cpu_baseline(ratings, K, alpha, budget_s=12.0, threads=0, max_rows=None):
             shape, rows, cols = (S, n_other), own, oth
         else:
             shape, rows, cols = (n_other, S), oth, own
-        m = o.Oracle(K, shape, rows, cols, v, shape, rows[:1], cols[:1], v[:1], alpha=alpha, burnin=0, nthreads=threads)
-        m.set_items(1 - side, rng.normal(0, 0.3, size=(m.num(1 - side), K)))
-        m.set_hyper(side, rng.normal(0, 0.1, size=K), np.eye(K) * 2.0)
-        m.set_iter(side, 3)
+        m = o.Oracle(K, shape, rows, cols, v, shape, rows[:1], cols[:1], v[:1], alpha=self.alpha, burnin=0, nthreads=self.threads)
+        m.set_items(1 - side, self.rng.normal(0, 0.3, size=(m.num(1 - side), K)))
+        m.set_hyper(side, self.rng.normal(0, 0.1, size=K), np.eye(K) * 2.0)
         return m, S, e
 
-    def timed(S):
+    def _run(self, models, it=3):
         tot, items, nnz = 0.0, 0, 0
         for side in (0, 1):
-            m, s, e = sub_model(side, S)
+            m, s, e = models[side]
+            m.set_iter(side, it)
             t0 = time.perf_counter()
             m.sample_range(side, 0, s)
             tot += time.perf_counter() - t0
             items += s; nnz += e
-            del m
         return tot, items, nnz
 
-    S = 4000
-    t, items, nnz = timed(S)                  # calibration pass (also warms the OpenMP team)
-    rate = items / t
-    S = int(max(S, min(rate * budget_s / 2, max_rows or 10**9, max(ratings.nrows, ratings.ncols))))
-    t, items, nnz = timed(S)
-    return {"value": items / t, "unit": UNIT, "cores": int(ncores), "kind": "port",
-            "sample": "first %d user rows + first %d movie columns of the workload (%d ratings), per-item loop of the "
-                      "restated reference (oracle/, OpenMP schedule(guided), %d threads), other side's full latent matrix "
-                      "in host memory; %.1f s of CPU time" % (min(S, ratings.nrows), min(S, ratings.ncols), nnz, ncores, t),
-            "seconds": t}
+    def step(self):
+        """one bounded sample of a U+V sweep pair -> dict(value, seconds, ...)"""
+        self.iter += 1
+        t, items, nnz = self._run(self.models, self.iter)
+        S, r = self.S, self.ratings
+        whole = S >= max(r.nrows, r.ncols)
+        return {"value": items / t, "unit": UNIT, "cores": int(self.threads), "kind": "port",
+                "sample": "%s (%d ratings), per-item loop of the restated reference (oracle/, OpenMP schedule(guided), %d threads), "
+                          "other side's full latent matrix in host memory; %.1f s of CPU time"
+                          % ("the WHOLE workload: all %d user rows + all %d movie columns" % (r.nrows, r.ncols) if whole else
+                             "first %d user rows + first %d movie columns of the workload" % (min(S, r.nrows), min(S, r.ncols)), nnz, self.threads, t),
+                "seconds": t, "items": items, "whole_workload": whole}
+
+
+def cpu_baseline(ratings, K, alpha, budget_s=12.0, threads=0):
+    return CpuBaseline(ratings, K, alpha, budget_s, threads).step()
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def make_config(args):
+    from bpmf_b200 import synthetic
+    nrows, ncols, mean_nnz, K, seed = synthetic.WORKLOADS[args.workload]
+    return {"workload": args.workload, "users": nrows, "movies": ncols, "num_latent": K, "alpha": args.alpha,
+            "generator": "bpmf_b200/synthetic.py seed %d: Poisson(%g) ratings per user row, %s, planted rank-16 values"
+                         % (seed, mean_nnz, "movies drawn with Zipf(s=%g) popularity, duplicates dropped" % synthetic.ZIPF[args.workload]
+                            if args.workload in synthetic.ZIPF else "uniform distinct movies"),
+            "l2": "%s: per sweep %.0f MB of latent vectors gathered at random + %.0f MB of CSR"
+                  % ("inputs larger than L2" if max(nrows, ncols) * K * 8 + nrows * mean_nnz * 12 > 126e6 else
+                     "inputs FIT in the 126 MB L2 (no flush between steps: a cache-resident configuration, not the headline one)",
+                     max(nrows, ncols) * K * 8 / 1e6, nrows * mean_nnz * 12 / 1e6)}
+
+
+def reference_arm(args, config):
+    """--impl reference: the reference's CPU path (kind "port": the OpenMP restatement in oracle/; the reference itself needs
+    Eigen3 + Random123, absent here) on ALL host cores, each step one bounded sample of the workload. Rank 0 only."""
+    from bpmf_b200 import synthetic
+    nrows, ncols = config["users"], config["movies"]
+    ratings, K = synthetic.workload(args.workload, cache_dir=args.cache_dir, verbose=True)
+    config["nnz"] = int(ratings.nnz)
+    per_step_budget = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    cb = CpuBaseline(ratings, K, args.alpha, budget_s=per_step_budget)
+    vals, base = [], None
+    for i in range(args.warmup + args.steps):
+        base = cb.step()
+        log("reference step %d: %.0f samples/s in %.2f s (%s)" % (i, base["value"], base["seconds"], base["sample"][:70]))
+        if i >= args.warmup:
+            vals.append(base)
+    tot_items = sum(b["items"] for b in vals)
+    tot_s = sum(b["seconds"] for b in vals)
+    v = tot_items / tot_s
+    base = dict(base, value=v)
+    base.pop("items", None)
+    full_ms = 1e3 * (nrows + ncols) / v
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(1, len(vals)), "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "cpu_baseline": base,
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+           "ms_per_whole_workload_step": full_ms,
+           "note": "restated reference (oracle/, kind=port): the reference needs Eigen3 + Random123, absent here. ms_per_step is the "
+                   "measured time of one step's sample (%s); %d host threads set explicitly"
+                   % ("the whole workload" if base["whole_workload"] else "a bounded part of the workload; ms_per_whole_workload_step extrapolates it",
+                      base["cores"])}
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+def latents_witness(gs, sides):
+    """N-invariance witness of the chain state: the run is bit-identical for any GPU count iff these agree"""
+    import hashlib
+    w = {}
+    h = hashlib.sha1()
+    for name, side in sides:
+        x = gs.items_host(side)
+        h.update(np.ascontiguousarray(x).tobytes())
+        w[name + "_abs_colmean_sum"] = float(np.abs(x.mean(0)).sum())
+        w[name + "_frobenius"] = float(np.sqrt((x * x).sum()))
+    w["sha1_V_then_U"] = h.hexdigest()
+    return w
+
+
+def secondary_block(args, rank, local_rank, world, timed_region, dist, workload="synthB-200Kx200K-50Mnnz-K128", steps=3, warmup=2):
+    """BASELINE.json configs[4] in the same run: Synthetic B (200K x 200K, 50M ratings, K = 128) through the CTA-per-item
+    kernel — ms per U+V step, the item kernel's time, and its fraction of the HBM roofline and of the fp64 tensor (DMMA) rate."""
+    import bpmf_b200
+    from bpmf_b200 import synthetic
+    from bpmf_b200.sampler import GibbsSampler
+    nrows, ncols, _, K, _ = synthetic.WORKLOADS[workload]
+    if world > 1:
+        if rank == 0:
+            ratings, K = synthetic.workload(workload, cache_dir=args.cache_dir, verbose=True)
+        dist.barrier(device_ids=[local_rank])
+        if rank != 0:
+            ratings, K = synthetic.workload(workload, cache_dir=args.cache_dir)
+    else:
+        ratings, K = synthetic.workload(workload, cache_dir=args.cache_dir, verbose=True)
+    gs = GibbsSampler(ratings, K, device=local_rank, alpha=args.alpha, variant=bpmf_b200.KERNEL_AUTO, exchange=args.exchange, with_test=False)
+    for _ in range(warmup):
+        gs.step()
+    gs.ctx.sync()
+    gs.ctx.items_kernel_time()
+    ms = timed_region(gs.step, steps)
+    gs.ctx.sync()
+    k_ms, k_n = gs.ctx.items_kernel_time()
+    k_avg = k_ms / max(1, k_n)
+    peak, _ = measured_peaks()
+    gbs = ratings.nnz / world * K * 8.0 / (k_avg / 1e3) / 1e9
+    tfl = ratings.nnz / world * (K * (K + 1) / 2 + K) * 2.0 / (k_avg / 1e3) / 1e12
+    out = {"workload": workload, "num_latent": K, "nnz": int(ratings.nnz), "n_gpus": world, "steps": steps, "warmup": warmup,
+           "ms_per_step": ms / steps, "value": (nrows + ncols) * steps / (ms / 1e3), "unit": UNIT,
+           "kernel": "items_block_kernel<%d>" % (K // 8), "kernel_ms_avg": k_avg, "kernel_launches_timed": k_n,
+           "hbm": {"achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak},
+           "fp64_tensor": {"achieved": tfl, "peak": 37.0, "unit": "TFLOP/s", "frac": tfl / 37.0,
+                           "peak_source": "profiles/r01_fp64_pipes_microbench.txt (DMMA m8n8k4, measured on B200)"}}
+    gs.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -153,6 +278,7 @@ def main():
     ap.add_argument("--alpha", type=float, default=2.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the Synthetic B / K=128 block of the JSON line")
     ap.add_argument("--cache-dir", default="/dev/shm")
     args = ap.parse_args()
 
@@ -161,41 +287,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     from bpmf_b200 import synthetic
     nrows, ncols, mean_nnz, K, seed = synthetic.WORKLOADS[args.workload]
-    config = {"workload": args.workload, "users": nrows, "movies": ncols, "num_latent": K, "alpha": args.alpha,
-              "generator": "bpmf_b200/synthetic.py seed %d: Poisson(%g) ratings per user row, %s, planted rank-16 values"
-                           % (seed, mean_nnz, "movies drawn with Zipf(s=%g) popularity, duplicates dropped" % synthetic.ZIPF[args.workload]
-                              if args.workload in synthetic.ZIPF else "uniform distinct movies"),
-              "l2": "%s: per sweep %.0f MB of latent vectors gathered at random + %.0f MB of CSR"
-                    % ("inputs larger than L2" if max(nrows, ncols) * K * 8 + nrows * mean_nnz * 12 > 126e6 else
-                       "inputs FIT in the 126 MB L2 (no flush between steps: a cache-resident configuration, not the headline one)",
-                       max(nrows, ncols) * K * 8 / 1e6, nrows * mean_nnz * 12 / 1e6)}
+    config = make_config(args)       # the same keys in both arms
 
     # ---------------------------------------------------------------- reference arm: CPU only, rank 0 only
     if args.impl == "reference":
-        if rank != 0:
-            return 0
-        ratings, K = synthetic.workload(args.workload, cache_dir=args.cache_dir, verbose=True)
-        config["nnz"] = int(ratings.nnz)
-        vals = []
-        per_step_budget = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
-        base = None
-        for i in range(args.warmup + args.steps):
-            base = cpu_baseline(ratings, K, args.alpha, budget_s=per_step_budget)
-            log("reference step %d: %.0f samples/s (%s)" % (i, base["value"], base["sample"][:60]))
-            if i >= args.warmup:
-                vals.append(base)
-        tot_items = sum(b["value"] * b["seconds"] for b in vals)
-        tot_s = sum(b["seconds"] for b in vals)
-        v = tot_items / tot_s
-        base["value"] = v
-        out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-               "warmup": args.warmup, "ms_per_step": 1e3 * (nrows + ncols) / v, "higher_is_better": True, "scaling": "strong",
-               "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "cpu_baseline": base,
-               "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
-               "note": "restated reference (oracle/, kind=port): the reference needs Eigen3 + Random123, absent here; "
-                       "ms_per_step is extrapolated from the bounded sample to the whole matrix"}
-        print(json.dumps(out), flush=True)
-        return 0
+        return reference_arm(args, config) if rank == 0 else 0
 
     # ---------------------------------------------------------------- B200 arm
     import torch
@@ -223,7 +319,7 @@ def main():
     variant = {"auto": bpmf_b200.KERNEL_AUTO, "exact": bpmf_b200.KERNEL_EXACT, "dmma": bpmf_b200.KERNEL_DMMA,
                "stream": bpmf_b200.KERNEL_STREAM}[args.variant]
     gs = GibbsSampler(ratings, K, device=local_rank, alpha=args.alpha, variant=variant, exchange=args.exchange, with_test=True)
-    config["parallelism"] = "1 gpu" if world == 1 else "items of both factors split over %d gpus, %s exchange" % (world, gs.exchange)
+    parallelism = "1 gpu" if world == 1 else "items of both factors split over %d gpus, %s exchange" % (world, gs.exchange)
     n_samples = nrows + ncols
 
     def barrier():
@@ -260,6 +356,13 @@ def main():
     k_ms, k_n = gs.ctx.items_kernel_time()
     clk = clocks.stop(t0, t1) if clocks else None
     value = n_samples * args.steps / (ms / 1e3)
+
+    # ---- the reference's loop body also predicts every iteration (c++/bpmf.cpp:184-190): the same steps with both predict calls
+    def step_with_predict():
+        gs.step()
+        gs.predict(burnin=args.warmup)
+    p_steps = max(2, min(args.steps, 5))
+    ms_pred = timed_region(step_with_predict, p_steps)
     rmse = gs.predict(burnin=args.warmup)[0]
 
     # ---- roofline of the fused item kernel (both sides' launches averaged)
@@ -269,7 +372,7 @@ def main():
     achieved = bytes_per_launch / (k_avg_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "kernel": ("items_exact_kernel" if args.variant == "exact" or K % 16 else "items_block_kernel<%d>" % (K // 8) if K != 32 else
-                           "items_dmma32_kernel" if args.variant == "dmma" else "items_stream32v3_kernel<2,20>"),
+                           "items_dmma32_kernel" if args.variant == "dmma" else bpmf_b200.STREAM_KERNEL_NAME),
                 "kernel_ms_avg": k_avg_ms, "kernel_launches_timed": k_n, "kernel_share_of_step": k_ms / ms,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src + " (of measured, burst)"}
     if K != 32:
@@ -279,10 +382,16 @@ def main():
         roofline["fp64_tensor"] = {"achieved": gram_flop / (k_avg_ms / 1e3) / 1e12, "peak": 37.0, "unit": "TFLOP/s",
                                    "frac": gram_flop / (k_avg_ms / 1e3) / 1e12 / 37.0,
                                    "peak_source": "profiles/r01_fp64_pipes_microbench.txt (DMMA m8n8k4, measured on B200)"}
+    # DRAM bytes of one launch from the committed `ncu --set full` capture: valid for the launch it was taken on (N = 1, this
+    # workload, this kernel); at N > 1 a launch covers 1/N of the ratings and no capture exists, so it stays null
     tr = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tr):
+    roofline["traffic_note"] = "null: no ncu capture for this (workload, n_gpus)"
+    if world == 1 and os.path.exists(tr):
         try:
-            roofline["traffic"] = json.load(open(tr)).get(args.workload, {}).get("dram_bytes_per_launch")
+            ent = json.load(open(tr)).get(args.workload, {})
+            if ent.get("kernel", roofline["kernel"]) == roofline["kernel"] or "kernel" not in ent:
+                roofline["traffic"] = ent.get("dram_bytes_per_launch")
+                roofline["traffic_note"] = "dram__bytes_read.sum + dram__bytes_write.sum of one launch, %s" % ent.get("source", "profiles/traffic.json")
         except ValueError:
             pass
 
@@ -296,15 +405,7 @@ def main():
 
         def e2e_step():
             for side in (MOVIES, USERS):
-                if world == 1:
-                    gs.ctx.sample_host(side, host[1 - side].data_ptr(), host[side].data_ptr(), args.alpha, variant)
-                else:
-                    # every rank's host memory holds ITS slice of each latent matrix: upload the slice of the other side,
-                    # hand it to the peers over NVLink, sample, download the freshly sampled slice of this side
-                    gs.upload_slice(1 - side, host[1 - side].data_ptr())
-                    gs.sample(side)
-                    lo, hi, _ = gs.range[side]
-                    gs.ctx.get_items_range_ptr(side, lo, hi, host[side].data_ptr())
+                gs.sample_host(side, host[1 - side].data_ptr(), host[side].data_ptr())
 
         # iteration counters continue; the latents uploaded are the ones just downloaded, so the chain is unchanged
         e2e_step()
@@ -314,28 +415,48 @@ def main():
         e2e = {"value": n_samples * e_steps / (e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": hb,
                "d2h_bytes_per_step": hb, "ms_per_step": e_ms / e_steps, "steps": e_steps,
                "api": "bpmf_gpu_sample_host (C ABI) with pinned host latent matrices" if world == 1 else
-                      "per rank: bpmf_gpu_set_items_range (its slice of the other side) + NVLink exchange, sample stages, "
-                      "bpmf_gpu_get_items_range (its fresh slice); host latent matrices pinned, one slice per rank"}
+                      "per rank: its slice of the other side uploaded in chunks and pushed to the peers over NVLink while the upload "
+                      "continues, sample stages, its fresh slice downloaded in parts while the rest is sampled; host latent matrices "
+                      "pinned, one slice per rank (the sum over ranks is the bytes shown)"}
 
     total_launches = launches
     if world > 1:
         t = torch.tensor([launches], dtype=torch.int64, device="cuda")
         dist.all_reduce(t)
         total_launches = int(t.item())
+    witness = latents_witness(gs, (("V", MOVIES), ("U", USERS))) if rank == 0 else None
+    gs.close()
+    del gs
+
+    secondary = None
+    if not args.no_secondary and args.workload == DEFAULT_WORKLOAD:
+        try:
+            secondary = secondary_block(args, rank, local_rank, world, timed_region, dist)
+        except Exception as e:                       # the headline line must not be lost to the second workload
+            secondary = {"error": repr(e)[:300]}
+            if world > 1:
+                raise
 
     if rank == 0:
         base = None
-        if world == 1 and not args.no_cpu_baseline:
-            base = cpu_baseline(ratings, K, args.alpha)
-            base.pop("seconds", None)
+        if not args.no_cpu_baseline:
+            # rank 0's host cores (at N > 1 the other ranks wait at the barrier below); a shorter sample when other ranks wait
+            base = cpu_baseline(ratings, K, args.alpha, budget_s=12.0 if world == 1 else 5.0)
+            base.pop("seconds", None); base.pop("items", None)
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-               "dtype": "f64", "data": "synthetic", "config": config, "roofline": roofline, "cpu_baseline": base, "e2e": e2e,
-               "gpu_launches": total_launches, "clocks": clk,
-               "rmse_after_run": rmse[0], "ratings_per_s": 2.0 * ratings.nnz * args.steps / (ms / 1e3)}
+               "dtype": "f64", "data": "synthetic", "config": config, "parallelism": parallelism, "roofline": roofline,
+               "cpu_baseline": base, "e2e": e2e, "gpu_launches": total_launches, "clocks": clk,
+               "rmse_after_run": rmse[0], "ratings_per_s": 2.0 * ratings.nnz * args.steps / (ms / 1e3),
+               "incl_predict": {"value": n_samples * p_steps / (ms_pred / 1e3), "unit": UNIT, "ms_per_step": ms_pred / p_steps, "steps": p_steps,
+                                "what": "the same step plus movies.predict(users); users.predict(movies) — the reference's whole loop body "
+                                        "(c++/bpmf.cpp:184-190), which its items/sec counts"},
+               "witness": witness, "secondary": secondary,
+               "note": "`value` times movies.sample(users); users.sample(movies) only (the U+V sweep pair BASELINE.json's metric names); "
+                       "`incl_predict` adds both predict calls; cpu_baseline / --impl reference time the per-item loop of the sweeps without predict"}
         print(json.dumps(out), flush=True)
-    gs.close()
     if world > 1:
+        dist.barrier(device_ids=[local_rank])
         dist.destroy_process_group()
     return 0
 

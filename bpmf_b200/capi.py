@@ -12,6 +12,7 @@ SO_PATH = os.path.join(_HERE, "libbpmf_b200.so")
 
 MOVIES, USERS = 0, 1
 KERNEL_AUTO, KERNEL_EXACT, KERNEL_DMMA, KERNEL_STREAM, KERNEL_BLOCK = 0, 1, 2, 3, 4
+STREAM_KERNEL_NAME = "items_stream32v3_kernel<2,20>"   # what KERNEL_AUTO launches at K = 32 (csrc/stream_kernel.cu)
 
 _f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 _i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
@@ -68,6 +69,13 @@ SYMBOLS = {
     "bpmf_gpu_last_items_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "bpmf_gpu_items_kernel_time": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "bpmf_gpu_debug_set_tuning": (C.c_int, [C.c_void_p, C.c_int]),
+    "bpmf_gpu_reduce_stats_partial": (C.c_int, [C.c_void_p, C.c_int]),
+    "bpmf_gpu_reduce_stats_final": (C.c_int, [C.c_void_p, C.c_int]),
+    "bpmf_gpu_stats_block_items": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    "bpmf_gpu_stats_device_ptr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "bpmf_gpu_ipc_export_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p]),
+    "bpmf_gpu_set_stats_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "bpmf_gpu_debug_set_roles": (C.c_int, [C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_int]),
     "bpmf_gpu_debug_block_schedule": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "bpmf_gpu_debug_randn": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, _f64p]),
 }
@@ -200,6 +208,29 @@ class Context:
 
     def enable_peer_access(self, peer): self._ck(self.L.bpmf_gpu_enable_peer_access(self.h, peer.h))
 
+    # ---- sliced sweep statistics (multi-GPU): every rank reduces the blocks of its own range into all ranks' buffers
+    def stats_block_items(self, side):
+        n = C.c_int()
+        self._ck(self.L.bpmf_gpu_stats_block_items(self.h, side, C.byref(n)))
+        return n.value
+
+    def stats_device_ptr(self, side):
+        p = C.c_void_p()
+        self._ck(self.L.bpmf_gpu_stats_device_ptr(self.h, side, C.byref(p)))
+        return p.value
+
+    def ipc_export_stats(self, side):
+        buf = C.create_string_buffer(64)
+        self._ck(self.L.bpmf_gpu_ipc_export_stats(self.h, side, buf))
+        return buf.raw
+
+    def set_stats_peers(self, side, ptrs):
+        arr = (C.c_void_p * max(1, len(ptrs)))(*[C.c_void_p(p) for p in ptrs])
+        self._ck(self.L.bpmf_gpu_set_stats_peers(self.h, side, len(ptrs), arr))
+
+    def reduce_stats_partial(self, side): self._ck(self.L.bpmf_gpu_reduce_stats_partial(self.h, side))
+    def reduce_stats_final(self, side): self._ck(self.L.bpmf_gpu_reduce_stats_final(self.h, side))
+
     def set_items(self, side, a):
         a = np.ascontiguousarray(a, np.float64)
         assert a.size == self.K * self.num[side]
@@ -306,6 +337,7 @@ class Context:
         return t.value, n.value
 
     def set_tuning(self, cfg): self._ck(self.L.bpmf_gpu_debug_set_tuning(self.h, cfg))
+    def set_roles(self, gram_mask, stages, slots, warps=20): self._ck(self.L.bpmf_gpu_debug_set_roles(self.h, gram_mask, stages, slots, warps))
 
     def debug_randn(self, c, n):
         out = np.empty(n)

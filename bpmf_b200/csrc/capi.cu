@@ -47,7 +47,7 @@ void free_side(SideDev &s)
     dfree(s.colptr); dfree(s.rowidx); dfree(s.val);
     dfree(s.t_colptr); dfree(s.t_rowidx); dfree(s.t_col); dfree(s.t_val); dfree(s.pavg); dfree(s.pm2);
     dfree(s.items_own); s.items = nullptr;
-    dfree(s.peers_dev);
+    dfree(s.peers_dev); dfree(s.stat_peers_dev);
     dfree(s.hp.mu); dfree(s.hp.LambdaU); dfree(s.hp.LambdaF);
     dfree(s.hp_next.mu); dfree(s.hp_next.LambdaU); dfree(s.hp_next.LambdaF);
     dfree(s.sum); dfree(s.prod); dfree(s.cov); dfree(s.norm); dfree(s.partials); dfree(s.pred_partials);
@@ -268,6 +268,9 @@ static int setup_side(bpmf_gpu_ctx *ctx, SideDev &s, const int64_t *colptr)
     CU(cudaMemset(s.cov, 0, sizeof(double) * KK));
     CU(cudaMemset(s.norm, 0, sizeof(double)));
     CU(cudaMalloc(&s.partials, sizeof(double) * (size_t)STATS_BLOCKS * (KK + K + 1)));
+    CU(cudaMemset(s.partials, 0, sizeof(double) * (size_t)STATS_BLOCKS * (KK + K + 1)));
+    CU(cudaMalloc(&s.stat_peers_dev, sizeof(double *) * MAX_PEERS));
+    CU(cudaMemset(s.stat_peers_dev, 0, sizeof(double *) * MAX_PEERS));
     CU(cudaMalloc(&s.work_counter, 2 * sizeof(unsigned int)));
     CU(cudaMemset(s.work_counter, 0, 2 * sizeof(unsigned int)));
     // skew handling for the K == 32 stream kernel: items far heavier than the rest are sampled by the chunked path
@@ -729,13 +732,67 @@ int bpmf_gpu_sample_items(bpmf_gpu_ctx *ctx, int side, uint32_t iter, double alp
     return BPMF_GPU_OK;
 }
 
-int bpmf_gpu_reduce_stats(bpmf_gpu_ctx *ctx, int side)
+int bpmf_gpu_stats_block_items(bpmf_gpu_ctx *ctx, int side, int *items_per_block)
+{
+    if (!ctx || !side_ok(side) || !items_per_block) return BPMF_GPU_EINVAL;
+    if (!ctx->side[side].loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
+    *items_per_block = stats_block_items(ctx->K, ctx->side[side].num);
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_stats_device_ptr(bpmf_gpu_ctx *ctx, int side, double **dev_partials)
+{
+    if (!ctx || !side_ok(side) || !dev_partials) return BPMF_GPU_EINVAL;
+    *dev_partials = ctx->side[side].partials;
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_ipc_export_stats(bpmf_gpu_ctx *ctx, int side, unsigned char handle[BPMF_GPU_IPC_HANDLE_BYTES])
+{
+    if (!ctx || !side_ok(side) || !handle) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, s.partials));
+    memcpy(handle, &h, sizeof h);
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_set_stats_peers(bpmf_gpu_ctx *ctx, int side, int npeers, double *const *dev_peer_partials)
+{
+    if (!ctx || !side_ok(side) || npeers < 0 || npeers > MAX_PEERS || (npeers > 0 && !dev_peer_partials)) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
+    CU(cudaSetDevice(ctx->device));
+    double *tmp[MAX_PEERS] = {nullptr};
+    for (int i = 0; i < npeers; ++i) tmp[i] = dev_peer_partials[i];
+    CU(cudaMemcpyAsync(s.stat_peers_dev, tmp, sizeof(tmp), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    s.n_stat_peers = npeers;
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_reduce_stats_partial(bpmf_gpu_ctx *ctx, int side)
 {
     if (!ctx || !side_ok(side)) return BPMF_GPU_EINVAL;
     SideDev &s = ctx->side[side];
     if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
     CU(cudaSetDevice(ctx->device));
-    CU(launch_stats(ctx, side));
+    const cudaError_t e = launch_stats_partial(ctx, side);
+    if (e == cudaErrorInvalidValue && s.n_stat_peers > 0)
+        return fail(ctx, BPMF_GPU_EINVAL, "with statistics peers the item range must be aligned to bpmf_gpu_stats_block_items");
+    CU(e);
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_reduce_stats_final(bpmf_gpu_ctx *ctx, int side)
+{
+    if (!ctx || !side_ok(side)) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
+    CU(cudaSetDevice(ctx->device));
+    CU(launch_stats_final(ctx, side));
     if (ctx->overlap_hyper && s.num >= 1) {
         // hp.sample of the NEXT iteration needs only this cov (c++/sample.cpp:350): start it now on the auxiliary stream
         CU(cudaEventRecord(ctx->ev_stats[side], ctx->stream));
@@ -746,6 +803,12 @@ int bpmf_gpu_reduce_stats(bpmf_gpu_ctx *ctx, int side)
         s.pre_iter = s.iter + 1;
     }
     return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_reduce_stats(bpmf_gpu_ctx *ctx, int side)
+{
+    const int rc = bpmf_gpu_reduce_stats_partial(ctx, side);
+    return rc ? rc : bpmf_gpu_reduce_stats_final(ctx, side);
 }
 
 int bpmf_gpu_get_stats(bpmf_gpu_ctx *ctx, int side, double *sum, double *prod, double *cov, double *norm)
@@ -979,8 +1042,19 @@ int bpmf_gpu_debug_set_tuning(bpmf_gpu_ctx *ctx, int stream_cfg)
     if (!ctx) return BPMF_GPU_EINVAL;
     // the knob carries two fields: cfg % 1000000 is the kernel configuration, cfg / 1000000 - 1 (when >= 0) the number
     // of items per warp that are claimed in small groups at the end of a sweep
+    // cfg / 100000000 (when > 0): guided self-scheduling of the claims, a claim = remaining items / (that many quarters of the
+    // resident warp count)
+    ctx->stream_guided = stream_cfg / 100000000;
+    stream_cfg %= 100000000;
     ctx->stream_cfg = stream_cfg % 1000000;
     ctx->stream_tail = stream_cfg / 1000000 - 1;
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_debug_set_roles(bpmf_gpu_ctx *ctx, unsigned gram_mask, int stages, int slots, int warps)
+{
+    if (!ctx || (warps != 16 && warps != 20 && warps != 24)) return BPMF_GPU_EINVAL;
+    ctx->v5_gram_mask = gram_mask; ctx->v5_ns = stages; ctx->v5_nslot = slots; ctx->v5_nw = warps;
     return BPMF_GPU_OK;
 }
 

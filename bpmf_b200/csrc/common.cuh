@@ -47,6 +47,10 @@ struct SideDev {          // the device mirror of one Sys (c++/bpmf.h:112-239)
     // reductions
     double *sum = nullptr, *prod = nullptr, *cov = nullptr, *norm = nullptr;
     double *partials = nullptr;     // STATS_BLOCKS x (K*K + K + 1)
+    // multi-GPU: every rank reduces only the statistics blocks of ITS item range and stores them into every rank's
+    // `partials` (peer-mapped pointers, bpmf_gpu_set_stats_peers); 0 = reduce the full replica locally
+    int n_stat_peers = 0;
+    double **stat_peers_dev = nullptr;    // device array[MAX_PEERS]
     double *pred_partials = nullptr;
     int pred_blocks = 0;
     // propagated posterior (-m / -l): per-item prior precision K*K x num, nullptr = none (bpmf_gpu_set_prop_posterior)
@@ -107,6 +111,9 @@ struct bpmf_gpu_ctx {
     long long heavy_threshold = 4096;    // items with more ratings go through the chunked path (K == 32)
     int stream_cfg = 0;                   // 0 = default; see launch_items_stream32
     int stream_tail = -1;                 // items per warp claimed in small groups at the end of a sweep; -1 = default
+    int stream_guided = 0;                // > 0: guided claims, a claim = remaining / (stream_guided / 4 x resident warps) items
+    unsigned v5_gram_mask = 0;            // != 0: the warp-role kernel (stream_kernel.cu, v5) with these Gram warps
+    int v5_ns = 2, v5_nslot = 6, v5_nw = 20;
     std::string err;
     std::vector<void *> ipc_mapped;       // peer allocations opened with cudaIpcOpenMemHandle
 };
@@ -117,6 +124,9 @@ namespace bpmf {
 cudaError_t launch_hyper(bpmf_gpu_ctx *c, int side, uint32_t iter, const double *d_sum, const double *d_cov, bool ahead);
 cudaError_t launch_items_exact(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha);
 cudaError_t launch_stats(bpmf_gpu_ctx *c, int side);
+cudaError_t launch_stats_partial(bpmf_gpu_ctx *c, int side);   // per-block partial sums (own blocks only when stat peers are set)
+cudaError_t launch_stats_final(bpmf_gpu_ctx *c, int side);     // fixed-order sum of the STATS_BLOCKS partials, cov
+int stats_block_items(int K, int num);                          // items per statistics block (the granularity of ranges)
 cudaError_t launch_predict(bpmf_gpu_ctx *c, int side, int n);
 cudaError_t launch_aggregate(bpmf_gpu_ctx *c, int side);
 cudaError_t launch_debug_randn(bpmf_gpu_ctx *c, uint32_t seed, int n, double *d_out);
@@ -129,7 +139,7 @@ int block_schedule(int K, int kb, int warp, int *out, int cap_quads);
 cudaError_t launch_items_block(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha);
 // stream_kernel.cu
 cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha);
-cudaError_t launch_stats_partial32(bpmf_gpu_ctx *c, int side);
+cudaError_t launch_stats_partial32(bpmf_gpu_ctx *c, int side, int b0, int nb);
 int heavy_chunk_size();
 int heavy_partial_doubles();
 // build_kernels.cu

@@ -479,13 +479,15 @@ cudaError_t launch_items_exact(bpmf_gpu_ctx *c, int side, uint32_t iter, double 
 // Sweep reductions: sum, prod (outer products), norm over ALL items, then cov (sample.cpp:359-362,379-384)
 // =================================================================================================
 template <int NE>
-__global__ void __launch_bounds__(256) stats_partial_kernel(const double *__restrict__ items, int N, int K, double *__restrict__ partials)
+__global__ void __launch_bounds__(256) stats_partial_kernel(const double *__restrict__ items, int N, int K, double *__restrict__ partials, int b0,
+                                                            int npeers, double *const *__restrict__ peers)
 {
     constexpr int TILE = 32;
     extern __shared__ double sm[];  // TILE * K
     const int tid = threadIdx.x, T = blockDim.x, KK = K * K;
-    const int chunk = (N + gridDim.x - 1) / gridDim.x;
-    const int i0 = min(N, (int)blockIdx.x * chunk), i1 = min(N, i0 + chunk);
+    const int blk_id = b0 + (int)blockIdx.x;                 // block of the fixed STATS_BLOCKS decomposition
+    const int chunk = (N + STATS_BLOCKS - 1) / STATS_BLOCKS;
+    const int i0 = (int)min((long long)N, (long long)blk_id * chunk), i1 = min(N, i0 + chunk);
     double acc[NE];
     int ea[NE], eb[NE];
 #pragma unroll
@@ -509,51 +511,85 @@ __global__ void __launch_bounds__(256) stats_partial_kernel(const double *__rest
             if (tid < K) { const double v = x[tid]; s1 += v; s2 += v * v; }
         }
     }
-    double *out = partials + (size_t)blockIdx.x * (KK + K + 1);
+    const size_t base = (size_t)blk_id * (KK + K + 1);
+    auto put = [&](int e, double v) {                        // own copy + every peer's copy of the partials
+        partials[base + e] = v;
+        for (int q = 0; q < npeers; ++q) {
+            double *dst = peers[q];
+            if (dst && dst != partials) dst[base + e] = v;
+        }
+    };
 #pragma unroll
     for (int n = 0; n < NE; ++n)
-        if (ea[n] >= 0) out[tid + n * T] = acc[n];
+        if (ea[n] >= 0) put(tid + n * T, acc[n]);
     __syncthreads();
-    for (int a = tid; a < K; a += T) { out[KK + a] = s1; sm[a] = s2; }  // (K <= 256 = T)
+    for (int a = tid; a < K; a += T) { put(KK + a, s1); sm[a] = s2; }  // (K <= 256 = T)
     __syncthreads();
     if (tid == 0) {
         double nn = 0.0;
         for (int a = 0; a < K; ++a) nn += sm[a];
-        out[KK + K] = nn;
+        put(KK + K, nn);
     }
 }
 
-__global__ void __launch_bounds__(1024) stats_final_kernel(const double *__restrict__ partials, int nblocks, int N, int K, double *sum,
-                                                           double *prod, double *cov, double *norm)
+// Fixed-order sum of the STATS_BLOCKS partials: eight lanes per element, lane j adds blocks j, j + 8, ... in order, then a
+// fixed shuffle tree. The order depends on nothing but STATS_BLOCKS, so the statistics are the same for any GPU count.
+__global__ void __launch_bounds__(256) stats_sum_kernel(const double *__restrict__ partials, int K, double *sum, double *prod, double *norm)
 {
     const int KK = K * K, W = KK + K + 1;
-    for (int e = threadIdx.x; e < W; e += blockDim.x) {
-        double s = 0.0;
-        for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * W + e];
+    const int gt = blockIdx.x * 256 + threadIdx.x, e = gt >> 3, j = gt & 7;
+    double s = 0.0;
+    if (e < W)
+        for (int b = j; b < STATS_BLOCKS; b += 8) s += partials[(size_t)b * W + e];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (e < W && j == 0) {
         if (e < KK) prod[e] = s;
         else if (e < KK + K) sum[e - KK] = s;
         else *norm = s;
     }
-    __syncthreads();
-    for (int e = threadIdx.x; e < KK; e += blockDim.x) {
+}
+// cov = (prod - sum sum^T / N) / (N - 1)  (sample.cpp:383-384)
+__global__ void __launch_bounds__(256) stats_cov_kernel(int N, int K, const double *__restrict__ sum, const double *__restrict__ prod, double *cov)
+{
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e < K * K) {
         const int a = e % K, b = e / K;
         cov[e] = (prod[e] - (sum[a] * sum[b] / N)) / (N - 1);
     }
 }
 
-cudaError_t launch_stats(bpmf_gpu_ctx *c, int side)
+int stats32_block_items(int num);   // stream_kernel.cu
+
+int stats_block_items(int K, int num)
+{
+    if (K == 32) return stats32_block_items(num);
+    const int chunk = (num + STATS_BLOCKS - 1) / STATS_BLOCKS;
+    return chunk > 0 ? chunk : 1;
+}
+
+// Per-block partial sums. With statistics peers set (multi-GPU) only the blocks of this context's item range are
+// reduced and each partial is stored into every rank's buffer; the range must then be aligned to stats_block_items.
+cudaError_t launch_stats_partial(bpmf_gpu_ctx *c, int side)
 {
     SideDev &s = c->side[side];
     const int K = c->K, KK = K * K;
+    int b0 = 0, nb = STATS_BLOCKS;
+    if (s.n_stat_peers > 0) {
+        const int bi = stats_block_items(K, s.num);
+        if (s.from % bi != 0 || (s.to % bi != 0 && s.to != s.num)) return cudaErrorInvalidValue;
+        b0 = s.from / bi;
+        // the range that ends at the last item also owns the (empty) blocks behind it: every block is written by exactly one rank
+        const int b1 = (s.to == s.num) ? STATS_BLOCKS : s.to / bi;
+        nb = (s.from < s.to) ? b1 - b0 : 0;
+    }
+    if (nb < 1) return cudaSuccess;
+    if (K == 32) return launch_stats_partial32(c, side, b0, nb);          // tensor-core version, same partial layout (stream_kernel.cu)
     const int ne = (KK + 255) / 256;
     const size_t smem = sizeof(double) * 32 * K;
-    const int nb = STATS_BLOCKS;
-#define BPMF_STATS_CASE(NE) stats_partial_kernel<NE><<<nb, 256, smem, c->stream>>>(s.items, s.num, K, s.partials)
-    if (K == 32) {   // tensor-core version, same partial layout (stream_kernel.cu)
-        cudaError_t e32 = launch_stats_partial32(c, side);
-        if (e32 != cudaSuccess) return e32;
-        c->launches--;   // counted once below
-    } else if (ne <= 1) BPMF_STATS_CASE(1);
+#define BPMF_STATS_CASE(NE) stats_partial_kernel<NE><<<nb, 256, smem, c->stream>>>(s.items, s.num, K, s.partials, b0, s.n_stat_peers, s.stat_peers_dev)
+    if (ne <= 1) BPMF_STATS_CASE(1);
     else if (ne <= 2) BPMF_STATS_CASE(2);
     else if (ne <= 4) BPMF_STATS_CASE(4);
     else if (ne <= 8) BPMF_STATS_CASE(8);
@@ -563,11 +599,26 @@ cudaError_t launch_stats(bpmf_gpu_ctx *c, int side)
     else return cudaErrorInvalidValue;
 #undef BPMF_STATS_CASE
     c->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stats_final(bpmf_gpu_ctx *c, int side)
+{
+    SideDev &s = c->side[side];
+    const int K = c->K, KK = K * K, W = KK + K + 1;
+    stats_sum_kernel<<<(W * 8 + 255) / 256, 256, 0, c->stream>>>(s.partials, K, s.sum, s.prod, s.norm);
+    c->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    stats_final_kernel<<<1, 1024, 0, c->stream>>>(s.partials, nb, s.num, K, s.sum, s.prod, s.cov, s.norm);
+    stats_cov_kernel<<<(KK + 255) / 256, 256, 0, c->stream>>>(s.num, K, s.sum, s.prod, s.cov);
     c->launches++;
     return cudaGetLastError();
+}
+
+cudaError_t launch_stats(bpmf_gpu_ctx *c, int side)
+{
+    const cudaError_t e = launch_stats_partial(c, side);
+    return e != cudaSuccess ? e : launch_stats_final(c, side);
 }
 
 // =================================================================================================

@@ -25,6 +25,8 @@
 #include "common.cuh"
 #include "rng.cuh"
 
+#include <cuda.h>             // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no libcuda link)
+#include <algorithm>
 #include <cstdlib>
 
 namespace bpmf {
@@ -62,8 +64,11 @@ struct StreamArgs {
     unsigned long long *err;
     const double *zero_row;   // 256 bytes of zeros in global memory (bulk-copy variant: source of the padding rows)
     int bulk_end;             // v3: items of [from, bulk_end) are claimed CLAIM at a time, [bulk_end, to) CLAIM_TAIL at a time
+    int guided;               // > 0: guided self-scheduling (like the reference's schedule(guided), sample.cpp:352): a claim takes
+                              // remaining / guided items, at most CLAIM, at least CLAIM_TAIL; bulk_end is not used
     int heavy_thr;            // SKIP: items with more ratings than this belong to the chunked path and are passed over
     const double *propLambda; // PROP: K*K x num per-item prior precisions (-m / -l, sample.cpp:272-277)
+    int oob_row;              // gather4 variant: a row index outside the other side's latent matrix (zero fill)
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
@@ -185,25 +190,23 @@ __device__ __forceinline__ void chol3_block_column(double (&c)[10][2], double &m
         }
     }
     // trailing update A(I,J) -= A~(I,KB) D^-1 A~(J,KB)^T for KB < J <= I on the tensor cores
+    // The sum over the block's eight columns may run in any order: DMMA number e takes column 2t + e in its k-slot t, so
+    // the accumulator registers of A~(I,KB) and A~(J,KB) ARE the A and B fragments (lane 4g+t holds [g][2t + e]) and no
+    // lane exchange is needed.
     if (KB < 3) {
-        double fr[4][2], rv[2];
+        double nrv[2], bs[4][2];
 #pragma unroll
-        for (int kk = 0; kk < 2; ++kk) rv[kk] = __shfl_sync(FULL, myrinv, 8 * KB + 4 * kk + t);
+        for (int e = 0; e < 2; ++e) nrv[e] = -__shfl_sync(FULL, myrinv, 8 * KB + 2 * t + e);   // -1 / d of column 2t + e
 #pragma unroll
-        for (int I = KB + 1; I < 4; ++I)
+        for (int J = KB + 1; J < 4; ++J)
 #pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-                const int src = (lane & ~3) | (2 * kk + (t >> 1));
-                const double v0 = __shfl_sync(FULL, c[blk(I, KB)][0], src);
-                const double v1 = __shfl_sync(FULL, c[blk(I, KB)][1], src);
-                fr[I][kk] = (t & 1) ? v1 : v0;                              // A~(I,KB)[g][4kk + t]
-            }
+            for (int e = 0; e < 2; ++e) bs[J][e] = c[blk(J, KB)][e] * nrv[e];
 #pragma unroll
         for (int I = KB + 1; I < 4; ++I)
 #pragma unroll
             for (int J = KB + 1; J <= I; ++J)
 #pragma unroll
-                for (int kk = 0; kk < 2; ++kk) dmma884(c[blk(I, J)][0], c[blk(I, J)][1], -fr[I][kk], fr[J][kk] * rv[kk]);
+                for (int e = 0; e < 2; ++e) dmma884(c[blk(I, J)][0], c[blk(I, J)][1], c[blk(I, KB)][e], bs[J][e]);
     }
 }
 
@@ -215,8 +218,9 @@ __device__ __forceinline__ void chol3_block_column(double (&c)[10][2], double &m
 // caller keeps in srr0.
 template <int DBG, bool PROP = false>
 __device__ __forceinline__ void tail32_warp(double (&c)[10][2], double (&rrp)[4], const int idx, unsigned char *stg, const double *sLF,
-                                            const double *srr0, const StreamArgs &p, const int lane)
+                                            const double *srr0, const StreamArgs &p, const int lane, unsigned char *vecs = nullptr)
 {
+    if (!vecs) vecs = stg + V3_ZY_OFF;    // zy | zr | wb, 256 bytes each; by default behind the packed factor
     const double *LF = PROP ? p.propLambda + (size_t)idx * 1024 : sLF;   // LambdaF(i,k) at LF[k * LS + i]
     constexpr int LS = PROP ? 32 : LFS;
     double rr0 = 0.0;
@@ -225,8 +229,8 @@ __device__ __forceinline__ void tail32_warp(double (&c)[10][2], double (&rrp)[4]
         for (int j = 0; j < 32; ++j) rr0 = fma(__ldg(LF + j * 32 + lane), srr0[j], rr0);   // rr = hp_LambdaF * hp.mu (sample.cpp:285)
     }
     const int g = lane >> 2, t = lane & 3;
-    double *zy = reinterpret_cast<double *>(stg + V3_ZY_OFF), *zr = reinterpret_cast<double *>(stg + V3_ZR_OFF);
-    double *wb = reinterpret_cast<double *>(stg + V3_B_OFF), *Lp = reinterpret_cast<double *>(stg);
+    double *zy = reinterpret_cast<double *>(vecs), *zr = reinterpret_cast<double *>(vecs + 256);
+    double *wb = reinterpret_cast<double *>(vecs + 512), *Lp = reinterpret_cast<double *>(stg);
     // the K normals of this item: rng_set_pos((idx+1)*K*(iter+1)) (sample.cpp:266). Accepted polar attempts are numbered
     // by ballot; lane n then finishes normal n (one log / sqrt / divide per lane instead of one per attempt).
     if (!(DBG & 8)) {
@@ -402,10 +406,18 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs
     auto claim = [&]() {
         int base = 0, lim = p.bulk_end;
         if (lane == 0) {
-            base = p.from + (int)atomicAdd(p.work_counter, (unsigned)CLAIM);
-            if (base >= p.bulk_end) {     // guided self-scheduling: small groups at the end of the sweep
-                base = p.bulk_end + (int)atomicAdd(p.work_counter + 1, (unsigned)CLAIM_TAIL);
-                lim = min(p.to, base + CLAIM_TAIL);
+            if (p.guided > 0) {
+                // the size comes from a slightly stale read of the counter; whatever it is, [base, base + sz) is this warp's alone
+                const int seen = (int)*reinterpret_cast<volatile unsigned int *>(p.work_counter);
+                const int sz = max(CLAIM_TAIL, min(CLAIM, (p.to - p.from - seen) / p.guided));
+                base = p.from + (int)atomicAdd(p.work_counter, (unsigned)sz);
+                lim = min(p.to, base + sz);
+            } else {
+                base = p.from + (int)atomicAdd(p.work_counter, (unsigned)CLAIM);
+                if (base >= p.bulk_end) {     // small groups at the end of the sweep
+                    base = p.bulk_end + (int)atomicAdd(p.work_counter + 1, (unsigned)CLAIM_TAIL);
+                    lim = min(p.to, base + CLAIM_TAIL);
+                }
             }
         }
         base = __shfl_sync(FULL, base, 0);
@@ -571,6 +583,486 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs
 }
 
 // =====================================================================================================================
+// The v3 kernel with the gather on the TMA unit in its Blackwell GATHER form: cp.async.bulk.tensor.2d ... tile::gather4
+// (SASS UTMALDG) copies FOUR index-addressed rows of the other side's latent matrix per instruction, through a 2-D tensor
+// map of that matrix (box = 16 doubles x 1 row, SWIZZLE_128B; a latent row is two boxes), completion counted in bytes on
+// the stage's mbarrier. A stage of 16 ratings is 8 such copies, issued by lanes 0..7 in one instruction, instead of
+// 8 x (shuffle + address + cp.async) by the whole warp.
+// Shared-memory layout of a stage: the LEFT halves (latent 0..15) of its 16 rows are 16 lines of 128 bytes (two swizzle
+// atoms of 1024 bytes), the RIGHT halves another 16 lines. TMA cannot pad rows, so bank conflicts of the fragment loads
+// are avoided by WHERE a rating goes instead: rating 4q + t (k-slot t of DMMA group q) sits in line 8 (q >> 1) + 2 t + (q & 1),
+// so the four ratings of a group are in lines of equal parity and the 128-byte swizzle (16-byte chunk index XOR line
+// index) spreads a half-warp's 8 x 32 bytes over all 32 banks. Rating slots past the item's end name row `num_other`,
+// which is outside the tensor: the TMA unit fills them with zeros.
+// =====================================================================================================================
+constexpr int G4_ROWS_BYTES = SR * 256;                      // per stage, 1024-byte aligned
+constexpr int G4_AUX_STAGE = SR * 8 + 32;                    // weights | meta int4 | mbarrier
+constexpr int G4_VECS = 768;                                 // per warp: zy | zr | wb of the tail
+template <int NS> constexpr __host__ __device__ int g4_aux_warp() { return NS * G4_AUX_STAGE + G4_VECS; }
+constexpr int G4_SHARED = ((SHARED_BYTES + 1023) / 1024) * 1024;
+static_assert(LPACK1 * 8 <= G4_ROWS_BYTES, "the packed factor must fit in a stage's rows");
+
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const void *tmap, int col, int r0, int r1, int r2, int r3, uint32_t mbar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n"
+                 ::"r"(dst), "l"(tmap), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(mbar)
+                 : "memory");
+}
+
+// one group of four staged ratings in the gather4 layout: lo = left-half line of this lane's rating, already including
+// the lane's 8-byte slot; sw0 / sw1 = the swizzled 16-byte chunk offsets for fragment pairs (0, 2) and (1, 3)
+__device__ __forceinline__ void gram_group_g4(double (&c)[10][2], double (&rrp)[4], const unsigned char *line, int sw0, int sw1, const double *wq)
+{
+    double f[4];
+    f[0] = *reinterpret_cast<const double *>(line + sw0);
+    f[1] = *reinterpret_cast<const double *>(line + sw1);
+    f[2] = *reinterpret_cast<const double *>(line + 2048 + sw0);
+    f[3] = *reinterpret_cast<const double *>(line + 2048 + sw1);
+    const double w = *wq;
+#pragma unroll
+    for (int I = 0; I < 4; ++I)
+#pragma unroll
+        for (int J = 0; J <= I; ++J) dmma884(c[blk(I, J)][0], c[blk(I, J)][1], f[I], f[J]);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) rrp[a] = fma(f[a], w, rrp[a]);
+}
+
+template <int NS, int NW, bool SKIP>
+__global__ void __launch_bounds__(NW * 32, 1) items_stream32g4_kernel(StreamArgs p, const __grid_constant__ CUtensorMap tmap)
+{
+    extern __shared__ __align__(1024) unsigned char smem_g4[];
+    unsigned char *const smem_raw = smem_g4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    double *sLF = reinterpret_cast<double *>(smem_raw);            // LambdaF(i,k) at sLF[k * LFS + i]
+    double *srr0 = sLF + 32 * LFS;                                 // LambdaF * mu
+    unsigned char *rows = smem_raw + G4_SHARED + (size_t)warp * NS * G4_ROWS_BYTES;
+    unsigned char *aux = smem_raw + G4_SHARED + (size_t)NW * NS * G4_ROWS_BYTES + (size_t)warp * g4_aux_warp<NS>();
+    unsigned char *vecs = aux + NS * G4_AUX_STAGE;
+    const uint32_t rows_s = (uint32_t)__cvta_generic_to_shared(rows), aux_s = (uint32_t)__cvta_generic_to_shared(aux);
+
+    if ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u) {   // the 128-byte swizzle pattern follows the address bits
+        if (tid == 0) atomicMax(p.err, ERR_CHOLESKY | 0xfffffffeull);
+        return;
+    }
+    for (int e = tid; e < 1024; e += NW * 32) sLF[(e >> 5) * LFS + (e & 31)] = p.LambdaF[e];
+    __syncthreads();
+    if (tid < 32) {
+        double s = 0.0;
+        for (int j = 0; j < 32; ++j) s += sLF[j * LFS + tid] * p.mu[j];   // rr = LambdaF * hp.mu (sample.cpp:285)
+        srr0[tid] = s;
+    }
+    if (lane == 0) {
+#pragma unroll 1
+        for (int s = 0; s < NS; ++s) mbar_init(aux_s + s * G4_AUX_STAGE + SR * 8 + 16, 1);
+    }
+    fence_proxy_async();
+    __syncthreads();
+
+    // ---------------- fetch-side state (warp-uniform unless noted)
+    int g_base = 0, g_n = 0, f_it = 0;
+    int cpr = 0;                          // per lane: colptr[g_base + lane] - colptr[g_base]
+    int f_pos = 0, f_end = 0, f_start = 0, g_end = 0;
+    const int32_t *g_idx = p.rowidx;
+    const double *g_val = p.val;
+    int32_t n_idx = 0;                    // per lane: index / value of stream position f_pos + (lane & 15): the NEXT stage's
+    double n_w = 0.0;
+    bool f_done = false;
+    unsigned phases = 0;                  // bit h = parity of the phase of stage h the consumer waits for next
+    // this lane's copy (lanes 0..7): atom A = groups 2A and 2A + 1, lines 4h .. 4h + 3 of the atom, half hf of the latent row;
+    // it gathers ratings 8A + 2h + {0, 4, 1, 5} (see the layout above)
+    const int cA = (lane >> 2) & 1, ch = (lane >> 1) & 1, chf = lane & 1;
+    const int cr0 = 8 * cA + 2 * ch;      // ratings cr0, cr0 + 4, cr0 + 1, cr0 + 5
+    const uint32_t cdst = rows_s + chf * 2048 + (8 * cA + 4 * ch) * 128;
+    const int oob = p.oob_row;            // a row outside the tensor: zero fill
+
+    auto load_next = [&]() {
+        const int q = f_pos + (lane & 15);
+        n_idx = oob; n_w = 0.0;
+        if (q < min(g_end, f_end)) {
+            n_idx = __ldg(g_idx + q);
+            n_w = __ldg(g_val + q);
+        }
+    };
+    auto claim = [&]() {
+        int base = 0, lim = p.bulk_end;
+        if (lane == 0) {
+            if (p.guided > 0) {
+                const int seen = (int)*reinterpret_cast<volatile unsigned int *>(p.work_counter);
+                const int sz = max(CLAIM_TAIL, min(CLAIM, (p.to - p.from - seen) / p.guided));
+                base = p.from + (int)atomicAdd(p.work_counter, (unsigned)sz);
+                lim = min(p.to, base + sz);
+            } else {
+                base = p.from + (int)atomicAdd(p.work_counter, (unsigned)CLAIM);
+                if (base >= p.bulk_end) {
+                    base = p.bulk_end + (int)atomicAdd(p.work_counter + 1, (unsigned)CLAIM_TAIL);
+                    lim = min(p.to, base + CLAIM_TAIL);
+                }
+            }
+        }
+        base = __shfl_sync(FULL, base, 0);
+        lim = __shfl_sync(FULL, lim, 0);
+        if (base >= p.to) { f_done = true; return; }
+        g_base = base;
+        g_n = min(CLAIM, lim - base);
+        const int64_t c0 = __ldg(p.colptr + base);
+        cpr = (lane <= g_n) ? (int)(__ldg(p.colptr + base + lane) - c0) : 0;
+        g_idx = p.rowidx + c0;
+        g_val = p.val + c0;
+        g_end = __shfl_sync(FULL, cpr, g_n);
+        f_it = 0;
+        f_start = 0;
+        f_end = __shfl_sync(FULL, cpr, 1);
+        if (SKIP && f_end - f_start > p.heavy_thr) f_start = f_end;     // heavy: gathered as if it had no ratings
+        f_pos = f_start;
+    };
+    // fill ring slot `slot` with the next (at most SR) ratings of the current item
+    auto issue_stage = [&](int slot) {
+        unsigned char *ax = aux + slot * G4_AUX_STAGE;
+        const uint32_t mbar = aux_s + slot * G4_AUX_STAGE + SR * 8 + 16;
+        if (f_done) {
+            if (lane == 0) {
+                *reinterpret_cast<int4 *>(ax + SR * 8) = make_int4(-1, 0, 0, 0);
+                mbar_arrive_expect_tx(mbar, 0);
+            }
+            return;
+        }
+        const int n = min(SR, f_end - f_pos);
+        // the four rows of this lane's copy; n_idx already holds the out-of-tensor row for slots past the item's end
+        const int r0 = __shfl_sync(FULL, n_idx, cr0), r1 = __shfl_sync(FULL, n_idx, cr0 + 4);
+        const int r2 = __shfl_sync(FULL, n_idx, cr0 + 1), r3 = __shfl_sync(FULL, n_idx, cr0 + 5);
+        const int nops = n > 8 ? 8 : (n > 0 ? 4 : 0);               // ratings 8..15 live in the second atom
+        // the stage was last touched through the generic proxy (fragment loads, tail scratch): order those before the TMA writes
+        fence_proxy_async();
+        if (lane == 0) mbar_arrive_expect_tx(mbar, (unsigned)nops * 512u);
+        __syncwarp();
+        if (lane < nops) tma_gather4(cdst + slot * G4_ROWS_BYTES, &tmap, 16 * chf, r0, r1, r2, r3, mbar);
+        // rr weight (v - mean_rating) * alpha (sample.cpp:255)
+        if (lane < SR) reinterpret_cast<double *>(ax)[lane] = (lane < n) ? (n_w - p.mean_rating) * p.alpha : 0.0;
+        const int last = (f_pos + n == f_end);
+        if (lane == 0) *reinterpret_cast<int4 *>(ax + SR * 8) = make_int4(n, g_base + f_it, f_pos == f_start, last);
+        f_pos += n;
+        if (last) {
+            ++f_it;
+            if (f_it >= g_n) claim();
+            else {
+                f_start = f_end; f_end = __shfl_sync(FULL, cpr, f_it + 1);
+                if (SKIP && f_end - f_start > p.heavy_thr) { f_start = f_end; f_pos = f_start; }
+            }
+        }
+        if (!f_done) load_next();
+    };
+
+    claim();
+    if (!f_done) load_next();
+#pragma unroll 1
+    for (int s = 0; s < NS; ++s) issue_stage(s);
+
+    double c[10][2];
+    double rrp[4];
+#pragma unroll
+    for (int b = 0; b < 10; ++b) { c[b][0] = 0.0; c[b][1] = 0.0; }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) rrp[a] = 0.0;
+
+    // fragment addressing of this lane: group q's rating t is in line 8 (q >> 1) + 2 t + (q & 1); chunk index XOR (line & 7)
+    const int y0 = (g >> 1) ^ (2 * t);                             // groups 0, 2 (even lines)
+    const int e_sw0 = (y0 << 4) + (g & 1) * 8, e_sw1 = ((y0 ^ 4) << 4) + (g & 1) * 8;
+    const int o_sw0 = ((y0 ^ 1) << 4) + (g & 1) * 8, o_sw1 = ((y0 ^ 5) << 4) + (g & 1) * 8;
+    const int l_even = 2 * t * 128, l_odd = (2 * t + 1) * 128;
+
+    int h = 0;
+#pragma unroll 1
+    for (;;) {
+        mbar_wait(aux_s + h * G4_AUX_STAGE + SR * 8 + 16, (phases >> h) & 1u);
+        phases ^= 1u << h;
+        unsigned char *st = rows + h * G4_ROWS_BYTES;
+        unsigned char *ax = aux + h * G4_AUX_STAGE;
+        const int4 meta = *reinterpret_cast<const int4 *>(ax + SR * 8);
+        if (meta.x < 0) break;
+        {
+            const double *wq = reinterpret_cast<const double *>(ax) + t;
+            if (meta.x == SR) {
+                gram_group_g4(c, rrp, st + l_even, e_sw0, e_sw1, wq);
+                gram_group_g4(c, rrp, st + l_odd, o_sw0, o_sw1, wq + 4);
+                gram_group_g4(c, rrp, st + 1024 + l_even, e_sw0, e_sw1, wq + 8);
+                gram_group_g4(c, rrp, st + 1024 + l_odd, o_sw0, o_sw1, wq + 12);
+            } else {
+                if (meta.x > 0) gram_group_g4(c, rrp, st + l_even, e_sw0, e_sw1, wq);
+                if (meta.x > 4) gram_group_g4(c, rrp, st + l_odd, o_sw0, o_sw1, wq + 4);
+                if (meta.x > 8) gram_group_g4(c, rrp, st + 1024 + l_even, e_sw0, e_sw1, wq + 8);
+                if (meta.x > 12) gram_group_g4(c, rrp, st + 1024 + l_odd, o_sw0, o_sw1, wq + 12);
+            }
+        }
+        __syncwarp();                     // every lane is done reading slot h
+        if (!meta.w) {                    // more stages of this item to come: refill the slot and go on
+            issue_stage(h);
+            h = (h + 1 == NS) ? 0 : h + 1;
+            continue;
+        }
+        // ---------------- tail: one item's Gram is complete; slot h's rows are its scratch until the refill at the end
+        tail32_warp<0, false>(c, rrp, meta.y, st, sLF, srr0, p, lane, vecs);
+        __syncwarp();                     // the scratch is free again
+        issue_stage(h);
+        h = (h + 1 == NS) ? 0 : h + 1;
+    }
+}
+
+// =====================================================================================================================
+// Version 5: warp ROLES. DMMA and scalar fp64 share one pipe per scheduler and the arbiter serves warps by instruction:
+// a dependent DFMA of one warp waits ~32 cycles per warp that streams DMMAs on the same scheduler
+// (profiles/r02_fp64_mix_microbench*.txt: 9 cycles alone, 42 / 74 / 106 with one / two / three streaming warps), while
+// the pipe TIME of the two kinds simply adds. In v3 every warp alternates between its Gram and its tail, so a tail (a
+// chain of ~260 dependent fp64 instructions) usually runs against one to three Gram streams. Here the roles are split:
+//   Gram warps  (bit w of cfg.gram_mask) run the fetch ring + the DMMA Gram of v3 and, when an item is complete, hand its
+//               accumulators (24 doubles per lane, the DMMA layout as it is) to a transit slot in shared memory;
+//   tail warps  take a full slot into registers, free it, and run tail32_warp (normals, LDL^T, solves, store).
+// Which warps are which decides what a tail competes with: warp w issues on scheduler w % 4, so e.g. mask 0x0000f is one
+// Gram stream per scheduler with four tail warps each, 0x77777 keeps scheduler 3 free of DMMAs altogether.
+// Slots: state 0 free -> 2 being written -> 1 full -> 3 being read -> 0. Gram warps that run out of items count themselves
+// in `done`; a tail warp leaves when it saw done == number of Gram warps BEFORE a scan that found nothing.
+// =====================================================================================================================
+struct V5Cfg {
+    unsigned gram_mask;   // bit w: warp w is a Gram warp
+    int ns;               // ring stages per Gram warp
+    int nslot;            // transit slots
+};
+constexpr int V5_SLOT_DOUBLES = 24 * 32;
+constexpr int V5_SLOT_BYTES = V5_SLOT_DOUBLES * 8 + 32;      // + item index
+constexpr int V5_CTRL_BYTES = 256;                           // slot states (<= 48) + done counter
+constexpr int V5_TSCRATCH = ((V3_B_OFF + 256 + 15) / 16) * 16;
+inline size_t v5_smem_bytes(const V5Cfg &cfg, int nw)
+{
+    const int ng = __builtin_popcount(cfg.gram_mask & ((nw >= 32) ? 0xffffffffu : ((1u << nw) - 1u)));
+    return (size_t)SHARED_BYTES + (size_t)cfg.nslot * V5_SLOT_BYTES + V5_CTRL_BYTES + (size_t)ng * cfg.ns * STAGE_BYTES + (size_t)(nw - ng) * V5_TSCRATCH;
+}
+
+__device__ __forceinline__ void cp_async_wait_dyn(int pending)
+{
+    switch (pending) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    case 5: cp_async_wait<5>(); break;
+    case 6: cp_async_wait<6>(); break;
+    default: cp_async_wait<7>(); break;
+    }
+}
+
+template <int NW, int DBG>
+__global__ void __launch_bounds__(NW * 32, 1) items_stream32v5_kernel(StreamArgs p, V5Cfg cfg)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    double *sLF = reinterpret_cast<double *>(smem_raw);            // LambdaF(i,k) at sLF[k * LFS + i]
+    double *srr0 = sLF + 32 * LFS;                                 // LambdaF * mu
+    unsigned char *slots = smem_raw + SHARED_BYTES;
+    volatile int *state = reinterpret_cast<volatile int *>(slots + (size_t)cfg.nslot * V5_SLOT_BYTES);
+    int *state_nv = const_cast<int *>(state);
+    volatile int *done = state + 48;
+    unsigned char *regions = slots + (size_t)cfg.nslot * V5_SLOT_BYTES + V5_CTRL_BYTES;
+    const unsigned wmask = (NW >= 32) ? 0xffffffffu : ((1u << NW) - 1u);
+    const unsigned gmask = cfg.gram_mask & wmask;
+    const int n_gram = __popc(gmask);
+    const bool is_gram = (gmask >> warp) & 1u;
+    const int my_rank = __popc(gmask & ((1u << warp) - 1u));       // rank among the Gram warps (for a Gram warp)
+    const int NS = cfg.ns;
+
+    for (int e = tid; e < 1024; e += NW * 32) sLF[(e >> 5) * LFS + (e & 31)] = p.LambdaF[e];
+    if (tid < 64) state_nv[tid] = 0;
+    __syncthreads();
+    if (tid < 32) {
+        double s = 0.0;
+        for (int j = 0; j < 32; ++j) s += sLF[j * LFS + tid] * p.mu[j];   // rr = LambdaF * hp.mu (sample.cpp:285)
+        srr0[tid] = s;
+    }
+    __syncthreads();
+
+    double c[10][2];
+    double rrp[4];
+
+    if (!is_gram) {
+        // ------------------------------------------------------------------------------------------------ tail warp
+        unsigned char *scratch = regions + (size_t)n_gram * NS * STAGE_BYTES + (size_t)(warp - my_rank) * V5_TSCRATCH;
+        int start = warp % cfg.nslot;
+        for (;;) {
+            int s = -1;
+            if (lane == 0) {
+                for (;;) {
+                    const int d = *done;
+                    for (int k = 0; k < cfg.nslot; ++k) {
+                        int q = start + k; if (q >= cfg.nslot) q -= cfg.nslot;
+                        if (state[q] == 1 && atomicCAS(state_nv + q, 1, 3) == 1) { s = q; break; }
+                    }
+                    if (s >= 0) break;
+                    if (d == n_gram) { s = -2; break; }
+                    __nanosleep(100);
+                }
+            }
+            s = __shfl_sync(FULL, s, 0);
+            if (s < 0) break;
+            __threadfence_block();
+            const double *sl = reinterpret_cast<const double *>(slots + (size_t)s * V5_SLOT_BYTES) + lane;
+#pragma unroll
+            for (int b = 0; b < 10; ++b) { c[b][0] = sl[(2 * b) * 32]; c[b][1] = sl[(2 * b + 1) * 32]; }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) rrp[a] = sl[(20 + a) * 32];
+            const int idx = *reinterpret_cast<const int *>(slots + (size_t)s * V5_SLOT_BYTES + V5_SLOT_DOUBLES * 8);
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); state[s] = 0; }
+            start = s + 1; if (start >= cfg.nslot) start = 0;
+            tail32_warp<DBG, false>(c, rrp, idx, scratch, sLF, srr0, p, lane);
+            __syncwarp();
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------------------------------------- Gram warp
+    unsigned char *wbase = regions + (size_t)my_rank * NS * STAGE_BYTES;
+    const uint32_t wbase_s = (uint32_t)__cvta_generic_to_shared(wbase);
+    int g_base = 0, g_n = 0, f_it = 0;
+    int cpr = 0;                          // per lane: colptr[g_base + lane] - colptr[g_base]
+    int f_pos = 0, f_end = 0, f_start = 0, g_end = 0;
+    const int32_t *g_idx = p.rowidx;
+    const double *g_val = p.val;
+    int32_t n_idx = 0;
+    double n_w = 0.0;
+    bool f_done = false;
+    const unsigned char *src_lane = reinterpret_cast<const unsigned char *>(p.other) + (lane & 15) * 16;
+    const uint32_t dst_lane = wbase_s + (lane >> 4) * ROWB + (lane & 15) * 16;
+    const int half = lane >> 4;
+
+    auto load_next = [&]() {
+        const int q = f_pos + (lane & 15);
+        n_idx = 0; n_w = 0.0;
+        if (q < g_end) {
+            n_idx = __ldg(g_idx + q);
+            n_w = __ldg(g_val + q);
+        }
+    };
+    auto claim = [&]() {
+        int base = 0, lim = p.bulk_end;
+        if (lane == 0) {
+            base = p.from + (int)atomicAdd(p.work_counter, (unsigned)CLAIM);
+            if (base >= p.bulk_end) {
+                base = p.bulk_end + (int)atomicAdd(p.work_counter + 1, (unsigned)CLAIM_TAIL);
+                lim = min(p.to, base + CLAIM_TAIL);
+            }
+        }
+        base = __shfl_sync(FULL, base, 0);
+        lim = __shfl_sync(FULL, lim, 0);
+        if (base >= p.to) { f_done = true; return; }
+        g_base = base;
+        g_n = min(CLAIM, lim - base);
+        const int64_t c0 = __ldg(p.colptr + base);
+        cpr = (lane <= g_n) ? (int)(__ldg(p.colptr + base + lane) - c0) : 0;
+        g_idx = p.rowidx + c0;
+        g_val = p.val + c0;
+        g_end = __shfl_sync(FULL, cpr, g_n);
+        f_it = 0;
+        f_start = 0;
+        f_end = __shfl_sync(FULL, cpr, 1);
+        f_pos = f_start;
+    };
+    auto issue_stage = [&](int slot) {
+        const uint32_t st = dst_lane + slot * STAGE_BYTES;
+        unsigned char *stg = wbase + slot * STAGE_BYTES;
+        if (f_done) {
+            if (lane == 0) *reinterpret_cast<int4 *>(stg + META_OFF) = make_int4(-1, 0, 0, 0);
+            cp_async_commit();
+            return;
+        }
+        const int n = min(SR, f_end - f_pos);
+        const int nn = n - half;
+#pragma unroll
+        for (int i = 0; i < SR / 2; ++i) {
+            const unsigned j = (unsigned)__shfl_sync(FULL, n_idx, 2 * i + half);
+            if (!(DBG & 4)) cp_async16(st + 2 * i * ROWB, src_lane + (size_t)j * 256, (2 * i < nn) ? 16 : 0);
+        }
+        if (lane < SR) reinterpret_cast<double *>(stg + W_OFF)[lane] = (lane < n) ? (n_w - p.mean_rating) * p.alpha : 0.0;
+        const int last = (f_pos + n == f_end);
+        if (lane == 0) *reinterpret_cast<int4 *>(stg + META_OFF) = make_int4(n, g_base + f_it, f_pos == f_start, last);
+        cp_async_commit();
+        f_pos += n;
+        if (last) {
+            ++f_it;
+            if (f_it >= g_n) claim();
+            else { f_start = f_end; f_end = __shfl_sync(FULL, cpr, f_it + 1); }
+        }
+        if (!f_done) load_next();
+    };
+
+    claim();
+    if (!f_done) load_next();
+#pragma unroll 1
+    for (int s = 0; s < NS; ++s) issue_stage(s);
+#pragma unroll
+    for (int b = 0; b < 10; ++b) { c[b][0] = 0.0; c[b][1] = 0.0; }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) rrp[a] = 0.0;
+
+    int h = 0, sstart = my_rank % cfg.nslot;
+#pragma unroll 1
+    for (;;) {
+        cp_async_wait_dyn(NS - 1);
+        __syncwarp();
+        unsigned char *stg = wbase + h * STAGE_BYTES;
+        const int4 meta = *reinterpret_cast<const int4 *>(stg + META_OFF);
+        if (meta.x < 0) break;
+        {
+            const unsigned char *row = stg + t * ROWB + g * 8;
+            const double *wq = reinterpret_cast<const double *>(stg + W_OFF) + t;
+            if (!(DBG & 2)) {
+                if (meta.x == SR) {
+                    gram_group(c, rrp, row, wq);
+                    gram_group(c, rrp, row + 4 * ROWB, wq + 4);
+                    gram_group(c, rrp, row + 8 * ROWB, wq + 8);
+                    gram_group(c, rrp, row + 12 * ROWB, wq + 12);
+                } else {
+                    if (meta.x > 0) gram_group(c, rrp, row, wq);
+                    if (meta.x > 4) gram_group(c, rrp, row + 4 * ROWB, wq + 4);
+                    if (meta.x > 8) gram_group(c, rrp, row + 8 * ROWB, wq + 8);
+                    if (meta.x > 12) gram_group(c, rrp, row + 12 * ROWB, wq + 12);
+                }
+            }
+        }
+        __syncwarp();                     // every lane is done reading slot h
+        issue_stage(h);                   // refill first: the hand-off below may have to wait for a free slot
+        h = (h + 1 == NS) ? 0 : h + 1;
+        if (!meta.w) continue;
+        // ---------------- the item's Gram is complete: hand the accumulators to a tail warp
+        int s = 0;
+        if (lane == 0) {
+            for (;;) {
+                s = -1;
+                for (int k = 0; k < cfg.nslot; ++k) {
+                    int q = sstart + k; if (q >= cfg.nslot) q -= cfg.nslot;
+                    if (state[q] == 0 && atomicCAS(state_nv + q, 0, 2) == 0) { s = q; break; }
+                }
+                if (s >= 0) break;
+                __nanosleep(64);
+            }
+        }
+        s = __shfl_sync(FULL, s, 0);
+        sstart = s + 1; if (sstart >= cfg.nslot) sstart = 0;
+        double *sl = reinterpret_cast<double *>(slots + (size_t)s * V5_SLOT_BYTES) + lane;
+#pragma unroll
+        for (int b = 0; b < 10; ++b) { sl[(2 * b) * 32] = c[b][0]; sl[(2 * b + 1) * 32] = c[b][1]; c[b][0] = 0.0; c[b][1] = 0.0; }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { sl[(20 + a) * 32] = rrp[a]; rrp[a] = 0.0; }
+        if (lane == 0) *reinterpret_cast<int *>(slots + (size_t)s * V5_SLOT_BYTES + V5_SLOT_DOUBLES * 8) = meta.y;
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); state[s] = 1; }
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+    if (lane == 0) { __threadfence_block(); atomicAdd(const_cast<int *>(done), 1); }
+}
+
+// =====================================================================================================================
 // Heavy items (skew handling): an item with tens of thousands of ratings (ChEMBL's hottest target has 110 118) would be
 // ONE warp's work in the stream kernel and set the duration of the whole sweep. Such items are cut into chunks of
 // HEAVY_CHUNK ratings: heavy_gram32_kernel computes one partial Gram per chunk (a warp per chunk, DMMA, fragments
@@ -685,11 +1177,14 @@ cudaError_t launch_cfg(bpmf_gpu_ctx *c, const StreamArgs &p, long long n)
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int SW = 8;   // warps per stats block
 
-__global__ void __launch_bounds__(SW * 32) stats_partial32_kernel(const double *__restrict__ items, int N, double *__restrict__ partials)
+// Block b0 + blockIdx.x of the fixed STATS_BLOCKS decomposition; the partial goes to `partials` and to every peer's copy.
+__global__ void __launch_bounds__(SW * 32) stats_partial32_kernel(const double *__restrict__ items, int N, double *__restrict__ partials, int b0,
+                                                                  int npeers, double *const *__restrict__ peers)
 {
     __shared__ double sp[SW][10 * 64 + 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-    const long long nw = (long long)gridDim.x * SW, w = (long long)blockIdx.x * SW + warp;
+    const int blk_id = b0 + (int)blockIdx.x;
+    const long long nw = (long long)STATS_BLOCKS * SW, w = (long long)blk_id * SW + warp;
     long long chunk = (N + nw - 1) / nw;
     chunk = (chunk + 3) & ~3ll;
     const long long i0 = min((long long)N, w * chunk), i1 = min((long long)N, i0 + chunk);
@@ -726,8 +1221,11 @@ __global__ void __launch_bounds__(SW * 32) stats_partial32_kernel(const double *
         for (int a = 0; a < 4; ++a) sp[warp][640 + 8 * a + g] = sx[a];
     }
     __syncthreads();
-    double *out = partials + (size_t)blockIdx.x * (1024 + 32 + 1);
-    for (int e = tid; e < 1024; e += SW * 32) {
+    // the block's partial, first in registers (every sp[][] value is still needed), then in sp itself
+    double acc4[1024 / (SW * 32)], accs = 0.0;
+#pragma unroll
+    for (int q = 0; q < 1024 / (SW * 32); ++q) {
+        const int e = tid + q * SW * 32;
         int i = e & 31, k = e >> 5;                          // prod(i,k), column-major
         if (i < k) { const int x = i; i = k; k = x; }        // mirror of the lower triangle
         const int I = i >> 3, J = k >> 3;
@@ -735,29 +1233,109 @@ __global__ void __launch_bounds__(SW * 32) stats_partial32_kernel(const double *
         double acc = 0.0;
 #pragma unroll
         for (int ww = 0; ww < SW; ++ww) acc += sp[ww][off];
-        out[e] = acc;
+        acc4[q] = acc;
     }
     if (tid < 32) {
-        double acc = 0.0;
 #pragma unroll
-        for (int ww = 0; ww < SW; ++ww) acc += sp[ww][640 + tid];
-        out[1024 + tid] = acc;
+        for (int ww = 0; ww < SW; ++ww) accs += sp[ww][640 + tid];
     }
+    __syncthreads();
+    double *so = &sp[0][0];                                  // 1024 + 32 + 1 doubles
+#pragma unroll
+    for (int q = 0; q < 1024 / (SW * 32); ++q) so[tid + q * SW * 32] = acc4[q];
+    if (tid < 32) so[1024 + tid] = accs;
     __syncthreads();
     if (tid == 0) {   // norm = sum of squared norms = trace of the outer-product sum
         double nn = 0.0;
-        for (int d = 0; d < 32; ++d) nn += out[d * 33];
-        out[1024 + 32] = nn;
+        for (int d = 0; d < 32; ++d) nn += so[d * 33];
+        so[1024 + 32] = nn;
+    }
+    __syncthreads();
+    const size_t base = (size_t)blk_id * (1024 + 32 + 1);
+    for (int e = tid; e < 1024 + 32 + 1; e += SW * 32) {
+        const double v = so[e];
+        partials[base + e] = v;
+        for (int q = 0; q < npeers; ++q) {
+            double *dst = peers[q];
+            if (dst && dst != partials) dst[base + e] = v;
+        }
     }
 }
 
 }  // namespace
 
-cudaError_t launch_stats_partial32(bpmf_gpu_ctx *c, int side)
+cudaError_t launch_stats_partial32(bpmf_gpu_ctx *c, int side, int b0, int nb)
 {
     SideDev &s = c->side[side];
-    stats_partial32_kernel<<<STATS_BLOCKS, SW * 32, 0, c->stream>>>(s.items, s.num, s.partials);
+    if (nb < 1) return cudaSuccess;
+    stats_partial32_kernel<<<nb, SW * 32, 0, c->stream>>>(s.items, s.num, s.partials, b0, s.n_stat_peers, s.stat_peers_dev);
     c->launches++;
+    return cudaGetLastError();
+}
+
+// items per statistics block for K == 32: SW warps x a warp's chunk (a multiple of four)
+int stats32_block_items(int num)
+{
+    const long long nw = (long long)STATS_BLOCKS * SW;
+    long long chunk = (num + nw - 1) / nw;
+    chunk = (chunk + 3) & ~3ll;
+    return (int)(chunk * SW);
+}
+
+template <int NW>
+static cudaError_t launch_v5(bpmf_gpu_ctx *c, const StreamArgs &p, long long n, const V5Cfg &cfg)
+{
+    const size_t smem = v5_smem_bytes(cfg, NW);
+    if (smem > 227 * 1024 || cfg.nslot < 1 || cfg.nslot > 48 || cfg.ns < 1 || cfg.ns > 8) return cudaErrorInvalidConfiguration;
+    const unsigned gm = cfg.gram_mask & ((1u << NW) - 1u);
+    if (gm == 0 || gm == ((1u << NW) - 1u)) return cudaErrorInvalidConfiguration;   // both roles must be present
+    auto kern = items_stream32v5_kernel<NW, 0>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    long long grid = c->sm_count;
+    const long long ng = __builtin_popcount(gm);
+    const long long need = (n + ng * CLAIM_TAIL - 1) / (ng * CLAIM_TAIL);
+    if (grid > need) grid = need;
+    kern<<<(unsigned)grid, NW * 32, smem, c->stream>>>(p, cfg);
+    return cudaGetLastError();
+}
+
+// 2-D tensor map of a latent matrix for the gather4 kernel: [num rows][32 doubles], box = 16 doubles x 1 row, 128-byte swizzle
+static cudaError_t make_gather_map(const double *items, int num, CUtensorMap *out)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = [] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) fn = nullptr;
+        return reinterpret_cast<EncodeFn>(fn);
+    }();
+    if (!encode) return cudaErrorNotSupported;
+    const cuuint64_t dims[2] = {32, (cuuint64_t)(num > 0 ? num : 1)};
+    const cuuint64_t strides[1] = {256};
+    const cuuint32_t box[2] = {16, 1}, estr[2] = {1, 1};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(items), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+template <int NS, int NW, bool SKIP>
+static cudaError_t launch_g4(bpmf_gpu_ctx *c, StreamArgs p, long long n, int num_other)
+{
+    constexpr size_t smem = (size_t)G4_SHARED + (size_t)NW * NS * G4_ROWS_BYTES + (size_t)NW * g4_aux_warp<NS>();
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    CUtensorMap tmap;
+    cudaError_t e = make_gather_map(p.other, num_other, &tmap);
+    if (e != cudaSuccess) return e;
+    p.oob_row = num_other > 0 ? num_other : 1;
+    auto kern = items_stream32g4_kernel<NS, NW, SKIP>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    long long grid = c->sm_count;
+    const long long need = (n + (long long)NW * CLAIM_TAIL - 1) / ((long long)NW * CLAIM_TAIL);
+    if (grid > need) grid = need;
+    kern<<<(unsigned)grid, NW * 32, smem, c->stream>>>(p, tmap);
     return cudaGetLastError();
 }
 
@@ -772,10 +1350,13 @@ static cudaError_t launch_stream_range(bpmf_gpu_ctx *c, int side, uint32_t iter,
     p.npeers = s.npeers; p.peers = s.peers_dev;
     p.mu = s.hp.mu; p.LambdaF = s.hp.LambdaF;
     p.work_counter = s.work_counter; p.err = c->d_err; p.zero_row = c->d_zero_row; p.heavy_thr = s.heavy_thr; p.propLambda = s.propLambda;
+    p.oob_row = o.num;
     cudaError_t e = cudaMemsetAsync(s.work_counter, 0, 2 * sizeof(unsigned int), c->stream);
     if (e != cudaSuccess) return e;
     const long long n = (long long)to - from;
     if (n < 1) return cudaSuccess;
+    p.guided = 0;
+    if (c->stream_guided > 0) p.guided = (int)std::min<long long>(0x7fffffff, (long long)c->stream_guided * c->sm_count * 20 / 4);   // quarters of a warp count
     {   // the last ~4 items per resident warp are handed out CLAIM_TAIL at a time (v3 kernel); bulk region is a multiple of CLAIM
         static const int tail_per_warp = [] { const char *v = getenv("BPMF_STREAM_TAIL"); return v ? atoi(v) : 8; }();
         long long tail_items = (long long)c->sm_count * 16 * tail_per_warp;
@@ -803,7 +1384,18 @@ static cudaError_t launch_stream_range(bpmf_gpu_ctx *c, int side, uint32_t iter,
         c->launches++;
         return e;
     }
+    if (c->v5_gram_mask) {                // warp-role kernel (bpmf_gpu_debug_set_roles)
+        V5Cfg v5{c->v5_gram_mask, c->v5_ns, c->v5_nslot};
+        e = c->v5_nw == 24 ? launch_v5<24>(c, p, n, v5) : c->v5_nw == 16 ? launch_v5<16>(c, p, n, v5) : launch_v5<20>(c, p, n, v5);
+        c->launches++;
+        return e;
+    }
     switch (cfg) {
+    // 14<NS><NW>: TMA gather4 (cp.async.bulk.tensor.2d tile::gather4, UTMALDG) instead of cp.async
+    case 14220: e = launch_g4<2, 20, false>(c, p, n, o.num); break;
+    case 14224: e = launch_g4<2, 24, false>(c, p, n, o.num); break;
+    case 14216: e = launch_g4<2, 16, false>(c, p, n, o.num); break;
+    case 14316: e = launch_g4<3, 16, false>(c, p, n, o.num); break;
     case 3218: e = launch_cfg<2, 18, 3>(c, p, n); break;
     // 11<NS><NW>: v3 "phased" (all Grams of a CTA together, all tails together)
     case 11216: e = launch_cfg<2, 16, 9>(c, p, n); break;
@@ -899,7 +1491,7 @@ cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, doub
     p.other = o.items; p.items = s.items;
     p.npeers = s.npeers; p.peers = s.peers_dev;
     p.mu = s.hp.mu; p.LambdaF = s.hp.LambdaF;
-    p.work_counter = s.work_counter; p.err = c->d_err; p.zero_row = c->d_zero_row; p.bulk_end = s.to; p.heavy_thr = s.heavy_thr;
+    p.work_counter = s.work_counter; p.err = c->d_err; p.zero_row = c->d_zero_row; p.bulk_end = s.to; p.guided = 0; p.heavy_thr = s.heavy_thr;
     p.propLambda = nullptr;
     const int ch0 = s.h_heavy_first[first], ch1 = s.h_heavy_first[last];
     heavy_gram32_kernel<<<(ch1 - ch0 + 3) / 4, 128, 0, c->stream>>>(p, ch1 - ch0, s.hv_p0 + ch0, s.hv_p1 + ch0,

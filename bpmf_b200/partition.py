@@ -17,16 +17,20 @@ def split_range(n, world, rank):
     return lo, min(n, lo + chunk), chunk
 
 
-def balanced_ranges(colptr, world, fixed_cost=12):
+def balanced_ranges(colptr, world, fixed_cost=12, align=1):
     """Contiguous ranges balanced on work = fixed_cost + nnz per item, the reference's heuristic (c++/assign.cpp:111 uses
     10 + nnz; on the GPU the per-item Cholesky / solve / RNG tail costs about 12 ratings' worth of Gram updates at K=32).
-    Returns world+1 boundaries. Used by the push exchange, which does not need equal-sized slices."""
+    Returns world+1 boundaries. Used by the push exchange, which does not need equal-sized slices.
+    align > 1 rounds the inner boundaries to multiples of it (the statistics-block size: every rank then reduces whole
+    blocks of the fixed decomposition, bpmf_gpu_stats_block_items)."""
     colptr = np.asarray(colptr, np.int64)
     n = len(colptr) - 1
     work = colptr[1:] - colptr[:-1] + fixed_cost
     cum = np.concatenate([[0], np.cumsum(work)])
     targets = cum[-1] * np.arange(1, world) / world
     cuts = np.searchsorted(cum, targets, side="left")
+    if align > 1:
+        cuts = ((cuts + align // 2) // align) * align
     b = np.concatenate([[0], cuts, [n]]).astype(np.int64)
     return np.maximum.accumulate(np.minimum(b, n))
 

@@ -41,8 +41,9 @@ class GibbsSampler:
             self.num[side] = n
             self.ctx.load_side(side, n, n_other, ptr, idx, val, ratings.mean_rating)
             if self.exchange == "push":
-                # ragged, work-balanced ranges; the library's own (cudaMalloc) storage is what CUDA IPC can export
-                b = balanced_ranges(ptr, self.world)
+                # ragged, work-balanced ranges on statistics-block boundaries; the library's own (cudaMalloc) storage is what
+                # CUDA IPC can export
+                b = balanced_ranges(ptr, self.world, align=self.ctx.stats_block_items(side))
                 lo, hi, chunk = int(b[self.rank]), int(b[self.rank + 1]), 0
             else:
                 lo, hi, chunk = split_range(n, self.world, self.rank)
@@ -58,6 +59,12 @@ class GibbsSampler:
                 ptrs = [self.ctx.items_device_ptr(side) if r == self.rank else self.ctx.ipc_open(handles[r])
                         for r in range(self.world)]
                 self.ctx.set_peers(side, ptrs)
+                # the sweep statistics: every rank reduces the blocks of its own range and stores them into all ranks' buffers
+                dist.all_gather_object(handles, self.ctx.ipc_export_stats(side))
+                sptrs = [self.ctx.stats_device_ptr(side) if r == self.rank else self.ctx.ipc_open(handles[r])
+                         for r in range(self.world)]
+                self.ctx.set_stats_peers(side, sptrs)
+        self._readers = False     # a host-initiated read of a replica is in flight that the next remote stores must not overtake
         if with_test:
             for side in (MOVIES, USERS):
                 self.ctx.load_test(side, *ratings.test_side(side))
@@ -66,12 +73,26 @@ class GibbsSampler:
     # ---- one Sys::sample(other) (sample.cpp:341-385), multi-GPU aware -------------------------------------------
     def sample(self, side):
         ctx = self.ctx
+        self._fence_readers()
         it = ctx.get_iter(side) + 1
         ctx.set_iter(side, it)
         ctx.sample_hyper(side, it)                       # every rank draws the same (mu, Lambda): cov is replicated
         ctx.sample_items(side, it, self.alpha, self.variant)
-        self._exchange(side)
-        ctx.reduce_stats(side)                           # over ALL items, fixed order: identical on every rank
+        if self.exchange == "push":
+            ctx.reduce_stats_partial(side)               # own blocks only, stored into every rank's buffer over NVLink
+            self._exchange(side)                         # the barrier that orders items AND partials of all ranks
+            ctx.reduce_stats_final(side)                 # fixed-order sum of all blocks: identical on every rank
+        else:
+            self._exchange(side)
+            ctx.reduce_stats(side)                       # over ALL items, fixed order: identical on every rank
+
+    def _fence_readers(self):
+        """Push mode: a peer's next sweep stores into THIS rank's replicas while it runs. Reads that this rank enqueued after
+        its last sweep (predict, items_host, downloads) are ordered before those stores by one more cross-rank barrier, issued
+        only when such a read happened since the last sweep. SPMD: every rank reads at the same points of the program."""
+        if self._readers and self.exchange == "push":
+            self.dist.all_reduce(self._tiny)
+        self._readers = False
 
     def _exchange(self, side):
         if self.world == 1:
@@ -99,15 +120,30 @@ class GibbsSampler:
             self.ctx.push_range(side, lo, hi)
             self.dist.all_reduce(self._tiny)      # every rank's copies are ordered before the next kernel of any rank
 
+    def sample_host(self, side, host_other_ptr, host_items_ptr):
+        """Sys::sample(Sys &other) with HOST-resident latent matrices (pinned): other.items() is read from host memory, this
+        side's fresh items() end up in host memory. One GPU: bpmf_gpu_sample_host. Several: every rank's host memory holds
+        ITS slice of each matrix (host_*_ptr are the bases of full-size matrices of which only the slice is touched)."""
+        if self.world == 1:
+            self.ctx.sample_host(side, host_other_ptr, host_items_ptr, self.alpha, self.variant)
+            return
+        self.upload_slice(1 - side, host_other_ptr)
+        self.sample(side)
+        lo, hi, _ = self.range[side]
+        self.ctx.get_items_range_ptr(side, lo, hi, host_items_ptr)    # synchronises this rank's stream: own slice only, which
+        #                                                               no peer writes (no fence needed)
+
     def step(self):
         """movies.sample(users); users.sample(movies)  (bpmf.cpp:184-185)"""
         self.sample(MOVIES)
         self.sample(USERS)
 
     def predict(self, burnin):
+        self._readers = True
         return self.ctx.predict(MOVIES, burnin), self.ctx.predict(USERS, burnin)
 
     def items_host(self, side):
+        self._readers = True
         return self.ctx.get_items(side)
 
     def items_view(self, side):

@@ -148,6 +148,22 @@ int bpmf_gpu_get_hyper(bpmf_gpu_ctx *ctx, int side, double *mu, double *LambdaU,
 int bpmf_gpu_sample_items(bpmf_gpu_ctx *ctx, int side, uint32_t iter, double alpha, int kernel_variant);
 /* sums.combine()/prods.combine()/norms.combine() + cov (c++/sample.cpp:359-362,379-384) over all items */
 int bpmf_gpu_reduce_stats(bpmf_gpu_ctx *ctx, int side);
+/* The two halves of _reduce_stats. Multi-GPU hosts call _partial right after _sample_items, then their cross-rank barrier,
+ * then _final: with statistics peers set (below) _partial reduces only the blocks of this context's item range and stores
+ * each block's partial sums into EVERY rank's buffer over NVLink, so nobody reduces the whole replica and no all-reduce of
+ * K*K + K + 1 doubles is needed (replaces the three MPI_Allreduce of c++/mpi_common.h:44-50); _final adds the fixed
+ * number of block partials in a fixed order, so the chain is bit-identical for any GPU count. */
+int bpmf_gpu_reduce_stats_partial(bpmf_gpu_ctx *ctx, int side);
+int bpmf_gpu_reduce_stats_final(bpmf_gpu_ctx *ctx, int side);
+/* Items per statistics block of a side: item ranges (bpmf_gpu_set_range) must start and end on multiples of it (or at
+ * num_items) once statistics peers are set. */
+int bpmf_gpu_stats_block_items(bpmf_gpu_ctx *ctx, int side, int *items_per_block);
+/* Every rank's buffer of block partials, like bpmf_gpu_set_peers for the latent matrices: device pointer of this context's
+ * buffer, its CUDA IPC handle (map it with bpmf_gpu_ipc_open), and the list of all ranks' buffers. npeers = 0 = every
+ * context reduces its full replica by itself. */
+int bpmf_gpu_stats_device_ptr(bpmf_gpu_ctx *ctx, int side, double **dev_partials);
+int bpmf_gpu_ipc_export_stats(bpmf_gpu_ctx *ctx, int side, unsigned char handle[BPMF_GPU_IPC_HANDLE_BYTES]);
+int bpmf_gpu_set_stats_peers(bpmf_gpu_ctx *ctx, int side, int npeers, double *const *dev_peer_partials);
 /* any of the out pointers may be NULL. sum[K], prod[K*K], cov[K*K], norm scalar. synchronises. */
 int bpmf_gpu_get_stats(bpmf_gpu_ctx *ctx, int side, double *sum, double *prod, double *cov, double *norm);
 
@@ -181,6 +197,10 @@ int bpmf_gpu_last_items_kernel_ms(bpmf_gpu_ctx *ctx, float *ms);
 int bpmf_gpu_items_kernel_time(bpmf_gpu_ctx *ctx, double *total_ms, int *count);
 /* kernel tuning knob of the K == 32 stream kernel: "<version><stages><warps>", e.g. 3216; 0 = default */
 int bpmf_gpu_debug_set_tuning(bpmf_gpu_ctx *ctx, int stream_cfg);
+/* warp roles of the K == 32 stream kernel (tuning): bit w of gram_mask makes warp w of the CTA (`warps` = 16, 20 or 24 of them)
+ * a Gram warp with a ring of `stages` gather stages, the others tail warps; `slots` transit slots between them.
+ * gram_mask == 0 = the library's default configuration. */
+int bpmf_gpu_debug_set_roles(bpmf_gpu_ctx *ctx, unsigned gram_mask, int stages, int slots, int warps);
 /* device RNG probes for known-answer tests: n normals of the stream rng_set_pos(c) */
 int bpmf_gpu_debug_randn(bpmf_gpu_ctx *ctx, uint32_t c, int n, double *host_out);
 /* Host only, no GPU needed (tests): the trailing-update schedule of the CTA-per-item kernel (K = 16 m, K != 32) — the

@@ -233,6 +233,51 @@ def test_range_and_peer_push(gpu):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("K", [32, 16])
+def test_sliced_statistics_match_the_full_reduction(gpu, K):
+    """Multi-GPU sweep statistics (replaces the three MPI_Allreduce of c++/mpi_common.h:44-50): three "ranks" on one GPU each
+    reduce only the statistics blocks of their own block-aligned item range and store the partials into every rank's
+    buffer; after that every rank's sum / prod / cov / norm are bit-identical to what one context reduces by itself."""
+    train, test = util.synth_ratings(5000, 4100, 60000, 12)
+    orc = util.make_oracle(K, train, test)
+    ctxs = [util.make_gpu_from_oracle(orc, K) for _ in range(4)]
+    single, ranks = ctxs[0], ctxs[1:]
+    rng = np.random.default_rng(1)
+    for side in (MOVIES, USERS):
+        n = orc.num(side)
+        x = rng.normal(0, 0.7, size=(n, K))
+        for c in ctxs:
+            c.set_items(side, x)
+        single.reduce_stats(side)
+        ref = single.get_stats(side)
+        bi = single.stats_block_items(side)
+        assert bi >= 1 and bi * 296 >= n
+        cuts = [0, 5 * bi, min(n, 5 * bi + 40 * bi), n]           # ragged, block-aligned; the last range takes the tail blocks
+        ptrs = [c.stats_device_ptr(side) for c in ranks]
+        for r, c in enumerate(ranks):
+            c.set_range(side, cuts[r], cuts[r + 1])
+            c.set_stats_peers(side, ptrs)
+        for c in ranks:
+            c.reduce_stats_partial(side)
+        for c in ranks:
+            c.sync()
+        for c in ranks:
+            c.reduce_stats_final(side)
+            got = c.get_stats(side)
+            for a, b in zip(got[:3], ref[:3]):
+                assert a.tobytes() == b.tobytes()
+            assert got[3] == ref[3]
+        # a range that does not sit on block boundaries is refused while peers are set
+        ranks[0].set_range(side, 1, cuts[1])
+        with pytest.raises(gpu.BpmfGpuError):
+            ranks[0].reduce_stats_partial(side)
+        ranks[0].set_stats_peers(side, [])
+        ranks[0].reduce_stats(side)                                # without peers: the full replica, any range
+        assert ranks[0].get_stats(side)[2].tobytes() == ref[2].tobytes()
+    for c in ctxs:
+        c.close()
+
+
 def test_cholesky_failure_is_reported(gpu):
     K = 32
     train, test = util.synth_ratings(50, 40, 600, 1)

@@ -109,3 +109,18 @@ def test_split_and_balanced_ranges():
     work = np.diff(colptr) + 12
     loads = [work[b[r]:b[r + 1]].sum() for r in range(8)]
     assert max(loads) <= work[17] + work.sum() / 8              # no rank holds more than the hot item plus a fair share
+
+
+def test_balanced_ranges_on_statistics_block_boundaries():
+    """push exchange: inner range boundaries are multiples of the statistics-block size (bpmf_gpu_stats_block_items), so
+    every rank reduces whole blocks of the fixed decomposition"""
+    rng = np.random.default_rng(3)
+    n = 100003
+    colptr = np.concatenate([[0], np.cumsum(rng.poisson(40, n))])
+    for world in (2, 3, 8):
+        for align in (1, 344, 3392):
+            b = partition.balanced_ranges(colptr, world, align=align)
+            assert len(b) == world + 1 and b[0] == 0 and b[-1] == n and np.all(np.diff(b) >= 0)
+            assert all(int(x) % align == 0 for x in b[1:-1])
+            work = np.diff(colptr[b]) + 12 * np.diff(b)
+            assert work.max() <= work.mean() * (1.0 + 1.5 * world * align * 52.0 / work.sum()) + 1
