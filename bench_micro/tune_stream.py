@@ -44,7 +44,13 @@ def main():
         ctx.set_items(USERS, state[USERS])
         ctx.set_tuning(cfg)
         ctx.sample_items(MOVIES, 7, 2.0, bpmf_b200.KERNEL_STREAM)
-        ctx.sync()
+
+        def sync():          # timing probes compute garbage and may report "Cholesky failed": only their time matters
+            try:
+                ctx.sync()
+            except bpmf_b200.BpmfGpuError as e:
+                print("   (cfg %d: %s)" % (cfg, e), flush=True)
+        sync()
         out = ctx.get_items(MOVIES)
         if ref is None:
             ref = out
@@ -54,7 +60,7 @@ def main():
         for rep in range(4):
             ctx.sample_items(MOVIES, 8 + rep, 2.0, bpmf_b200.KERNEL_STREAM)
             ctx.sample_items(USERS, 8 + rep, 2.0, bpmf_b200.KERNEL_STREAM)
-        ctx.sync()
+        sync()
         ms, cnt = ctx.items_kernel_time()
         per = ms / cnt
         print("cfg %d: %.3f ms/launch  %.1f GB/s  (%.1f%% of 6459 GB/s)  max|diff vs first| %.3e  wall %.2fs"

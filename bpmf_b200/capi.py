@@ -69,6 +69,9 @@ SYMBOLS = {
     "bpmf_gpu_last_items_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "bpmf_gpu_items_kernel_time": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "bpmf_gpu_debug_set_tuning": (C.c_int, [C.c_void_p, C.c_int]),
+    "bpmf_gpu_load_side_slice": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i64p, _i32p, _f64p, C.c_double]),
+    "bpmf_gpu_finalize_aggregates": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "bpmf_gpu_stats_block_items_for": (C.c_int, [C.c_int, C.c_int]),
     "bpmf_gpu_reduce_stats_partial": (C.c_int, [C.c_void_p, C.c_int]),
     "bpmf_gpu_reduce_stats_final": (C.c_int, [C.c_void_p, C.c_int]),
     "bpmf_gpu_stats_block_items": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
@@ -87,6 +90,14 @@ class BpmfGpuError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("bpmf_gpu error %d: %s" % (code, msg))
         self.code = code
+
+
+def stats_block_items_for(num_latent, num_items):
+    """items per statistics block of a side with num_items items (the granularity of multi-GPU item ranges)"""
+    n = load_library().bpmf_gpu_stats_block_items_for(num_latent, num_items)
+    if n < 1:
+        raise ValueError("bad arguments")
+    return n
 
 
 def load_library():
@@ -149,6 +160,18 @@ class Context:
         assert colptr.shape == (num_items + 1,)
         self._ck(self.L.bpmf_gpu_load_side(self.h, side, num_items, num_other, colptr, rowidx, val, mean_rating))
         self.num[side] = num_items
+
+    def load_side_slice(self, side, num_items, num_other, lo, hi, colptr, rowidx, val, mean_rating):
+        """only the ratings of the items [lo, hi) become resident; colptr / rowidx / val are the FULL arrays of the side"""
+        colptr = np.asarray(colptr)
+        p0, p1 = int(colptr[lo]), int(colptr[hi])
+        cs = np.ascontiguousarray(colptr[lo:hi + 1] - p0, np.int64)
+        ri = np.ascontiguousarray(rowidx[p0:p1], np.int32) if p1 > p0 else np.zeros(1, np.int32)
+        va = np.ascontiguousarray(val[p0:p1], np.float64) if p1 > p0 else np.zeros(1, np.float64)
+        self._ck(self.L.bpmf_gpu_load_side_slice(self.h, side, num_items, num_other, lo, hi, cs, ri, va, float(mean_rating)))
+        self.num[side] = num_items
+
+    def finalize_aggregates(self, side, nsamples): self._ck(self.L.bpmf_gpu_finalize_aggregates(self.h, side, nsamples))
 
     def set_heavy_threshold(self, n): self._ck(self.L.bpmf_gpu_set_heavy_threshold(self.h, n))
 
@@ -321,7 +344,7 @@ class Context:
 
     def get_aggregates(self, side):
         K, n = self.K, self.num[side]
-        mu, lam = np.empty((n, K)), np.empty((n, K * K))
+        mu, lam = np.zeros((n, K)), np.zeros((n, K * K))      # only the columns of the aggregation range are written
         self._ck(self.L.bpmf_gpu_get_aggregates(self.h, side, mu.reshape(-1), lam.reshape(-1)))
         return mu, lam
 

@@ -236,6 +236,27 @@ int bpmf_gpu_load_side(bpmf_gpu_ctx *ctx, int side, int num_items, int num_other
     return setup_side(ctx, s, colptr);
 }
 
+int bpmf_gpu_load_side_slice(bpmf_gpu_ctx *ctx, int side, int num_items, int num_other, int from, int to, const int64_t *colptr_slice,
+                             const int32_t *rowidx_slice, const double *val_slice, double mean_rating)
+{
+    if (!ctx || !side_ok(side) || num_items < 0 || num_other < 0 || from < 0 || to < from || to > num_items || !colptr_slice) return BPMF_GPU_EINVAL;
+    const int n = to - from;
+    const int64_t nnz = colptr_slice[n];
+    if (colptr_slice[0] != 0 || nnz < 0 || (nnz > 0 && (!rowidx_slice || !val_slice))) return fail(ctx, BPMF_GPU_EINVAL, "bad CSC arrays");
+    // the kernels index items and ratings globally: a full-length column pointer array in which every item outside the
+    // slice is empty costs 8 bytes per item and keeps them unchanged
+    std::vector<int64_t> colptr((size_t)num_items + 1);
+    for (int i = 0; i <= num_items; ++i) colptr[(size_t)i] = i < from ? 0 : (i > to ? nnz : colptr_slice[i - from]);
+    for (int i = 0; i < n; ++i)
+        if (colptr_slice[i + 1] < colptr_slice[i]) return fail(ctx, BPMF_GPU_EINVAL, "colptr not monotone");
+    const int rc = bpmf_gpu_load_side(ctx, side, num_items, num_other, colptr.data(), rowidx_slice, val_slice, mean_rating);
+    if (rc) return rc;
+    SideDev &s = ctx->side[side];
+    s.slice_from = from; s.slice_to = to;
+    s.from = from; s.to = to;
+    return BPMF_GPU_OK;
+}
+
 // Everything of a side but the compressed matrix itself: s.colptr / rowidx / val are on the device, s.num, num_other, nnz
 // and mean_rating are set; colptr is the host copy of the column pointers.
 static int setup_side(bpmf_gpu_ctx *ctx, SideDev &s, const int64_t *colptr)
@@ -244,6 +265,7 @@ static int setup_side(bpmf_gpu_ctx *ctx, SideDev &s, const int64_t *colptr)
     const int num_items = s.num;
     const int64_t nnz = s.nnz;
     s.from = 0; s.to = num_items; s.iter = -1;
+    s.slice_from = 0; s.slice_to = num_items;
     const size_t nitems = (size_t)K * (size_t)(num_items > 0 ? num_items : 1);
     CU(cudaMalloc(&s.items_own, sizeof(double) * nitems));
     CU(cudaMemset(s.items_own, 0, sizeof(double) * nitems));  // items().setZero() (sample.cpp:185)
@@ -322,7 +344,7 @@ int bpmf_gpu_load_test(bpmf_gpu_ctx *ctx, int side, const int64_t *colptr, const
     SideDev &s = ctx->side[side];
     if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "load_side must come before load_test");
     const int64_t nnz = colptr[s.num];
-    if (colptr[0] != 0 || nnz < 0) return fail(ctx, BPMF_GPU_EINVAL, "bad test CSC arrays");
+    if (colptr[0] != 0 || nnz < 0 || (nnz > 0 && (!rowidx || !val))) return fail(ctx, BPMF_GPU_EINVAL, "bad test CSC arrays");
     std::vector<int32_t> col((size_t)nnz);
     for (int i = 0; i < s.num; ++i) {
         if (colptr[i + 1] < colptr[i]) return fail(ctx, BPMF_GPU_EINVAL, "test colptr not monotone");
@@ -332,7 +354,9 @@ int bpmf_gpu_load_test(bpmf_gpu_ctx *ctx, int side, const int64_t *colptr, const
         }
     }
     CU(cudaSetDevice(ctx->device));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));       // like load_side: nothing in flight may still read the buffers freed below
+    CU(cudaStreamSynchronize(ctx->aux_stream));
+    CU(cudaStreamSynchronize(ctx->copy_stream));
     dfree(s.t_colptr); dfree(s.t_rowidx); dfree(s.t_col); dfree(s.t_val); dfree(s.pavg); dfree(s.pm2); dfree(s.pred_partials);
     s.nnz_test = nnz;
     const size_t n1 = (size_t)(nnz > 0 ? nnz : 1);
@@ -479,6 +503,8 @@ int bpmf_gpu_set_range(bpmf_gpu_ctx *ctx, int side, int from, int to)
     if (!ctx || !side_ok(side)) return BPMF_GPU_EINVAL;
     SideDev &s = ctx->side[side];
     if (!s.loaded || from < 0 || to < from || to > s.num) return fail(ctx, BPMF_GPU_EINVAL, "bad range");
+    if (from < to && (from < s.slice_from || to > s.slice_to))
+        return fail(ctx, BPMF_GPU_EINVAL, "range outside the items whose ratings were loaded (bpmf_gpu_load_side_slice)");
     s.from = from; s.to = to;
     return BPMF_GPU_OK;
 }
@@ -740,6 +766,12 @@ int bpmf_gpu_stats_block_items(bpmf_gpu_ctx *ctx, int side, int *items_per_block
     return BPMF_GPU_OK;
 }
 
+int bpmf_gpu_stats_block_items_for(int num_latent, int num_items)
+{
+    if (num_latent < 1 || num_latent > 128 || num_items < 0) return -1;
+    return stats_block_items(num_latent, num_items);
+}
+
 int bpmf_gpu_stats_device_ptr(bpmf_gpu_ctx *ctx, int side, double **dev_partials)
 {
     if (!ctx || !side_ok(side) || !dev_partials) return BPMF_GPU_EINVAL;
@@ -866,7 +898,9 @@ int bpmf_gpu_enable_aggregation(bpmf_gpu_ctx *ctx, int side, int burnin)
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     dfree(s.aggrMu); dfree(s.aggrLambda);
-    const size_t K = (size_t)ctx->K, n = (size_t)(s.num > 0 ? s.num : 1);
+    // only the items this context samples: with the items split over G GPUs, K*K*num/G doubles each (c++/bpmf.h:161-176)
+    s.aggr_from = s.from; s.aggr_to = s.to;
+    const size_t K = (size_t)ctx->K, n = (size_t)(s.to > s.from ? s.to - s.from : 1);
     CU(cudaMalloc(&s.aggrMu, sizeof(double) * K * n));
     CU(cudaMalloc(&s.aggrLambda, sizeof(double) * K * K * n));
     CU(cudaMemset(s.aggrMu, 0, sizeof(double) * K * n));               // sample.cpp:198-199
@@ -881,7 +915,19 @@ int bpmf_gpu_aggregate(bpmf_gpu_ctx *ctx, int side)
     SideDev &s = ctx->side[side];
     if (!s.loaded || !s.aggrMu) return fail(ctx, BPMF_GPU_EINVAL, "aggregation is not enabled for this side");
     CU(cudaSetDevice(ctx->device));
-    CU(launch_aggregate(ctx, side));
+    const cudaError_t e = launch_aggregate(ctx, side);
+    if (e == cudaErrorInvalidValue) return fail(ctx, BPMF_GPU_EINVAL, "the item range is no longer inside the range aggregation was enabled for");
+    CU(e);
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_finalize_aggregates(bpmf_gpu_ctx *ctx, int side, int nsamples)
+{
+    if (!ctx || !side_ok(side) || nsamples < 2) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded || !s.aggrMu) return fail(ctx, BPMF_GPU_EINVAL, "aggregation is not enabled for this side");
+    CU(cudaSetDevice(ctx->device));
+    CU(launch_finalize_aggregates(ctx, side, nsamples));
     return BPMF_GPU_OK;
 }
 
@@ -891,9 +937,10 @@ int bpmf_gpu_get_aggregates(bpmf_gpu_ctx *ctx, int side, double *aggrMu, double 
     SideDev &s = ctx->side[side];
     if (!s.loaded || !s.aggrMu) return fail(ctx, BPMF_GPU_EINVAL, "aggregation is not enabled for this side");
     CU(cudaSetDevice(ctx->device));
-    const size_t K = (size_t)ctx->K;
-    if (aggrMu) CU(cudaMemcpyAsync(aggrMu, s.aggrMu, sizeof(double) * K * s.num, cudaMemcpyDeviceToHost, ctx->stream));
-    if (aggrLambda) CU(cudaMemcpyAsync(aggrLambda, s.aggrLambda, sizeof(double) * K * K * s.num, cudaMemcpyDeviceToHost, ctx->stream));
+    // the host arrays are full size (K x num, K*K x num); only the columns of [aggr_from, aggr_to) are written
+    const size_t K = (size_t)ctx->K, n = (size_t)(s.aggr_to - s.aggr_from), off = (size_t)s.aggr_from;
+    if (aggrMu && n) CU(cudaMemcpyAsync(aggrMu + K * off, s.aggrMu, sizeof(double) * K * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (aggrLambda && n) CU(cudaMemcpyAsync(aggrLambda + K * K * off, s.aggrLambda, sizeof(double) * K * K * n, cudaMemcpyDeviceToHost, ctx->stream));
     return check_device_error(ctx);
 }
 

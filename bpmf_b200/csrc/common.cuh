@@ -25,6 +25,7 @@ struct SideDev {          // the device mirror of one Sys (c++/bpmf.h:112-239)
     int num = 0, num_other = 0;
     int64_t nnz = 0, nnz_test = 0;
     int from = 0, to = 0;
+    int slice_from = 0, slice_to = 0;     // items whose ratings are resident (bpmf_gpu_load_side_slice); [0, num) after load_side
     int iter = -1;
     double mean_rating = 0.0;
     // train CSC: column = item of this side
@@ -56,7 +57,8 @@ struct SideDev {          // the device mirror of one Sys (c++/bpmf.h:112-239)
     // propagated posterior (-m / -l): per-item prior precision K*K x num, nullptr = none (bpmf_gpu_set_prop_posterior)
     double *propLambda = nullptr;
     // posterior aggregation (-o): K x num and K*K x num, allocated by bpmf_gpu_enable_aggregation
-    double *aggrMu = nullptr, *aggrLambda = nullptr;
+    double *aggrMu = nullptr, *aggrLambda = nullptr;   // items [aggr_from, aggr_to) only: the range at _enable_aggregation time
+    int aggr_from = 0, aggr_to = 0;
     int aggr_burnin = 0;
     // heavy items (K == 32 stream kernel): items with more than the threshold of ratings, cut into chunks (stream_kernel.cu)
     int n_heavy = 0;
@@ -129,6 +131,7 @@ cudaError_t launch_stats_final(bpmf_gpu_ctx *c, int side);     // fixed-order su
 int stats_block_items(int K, int num);                          // items per statistics block (the granularity of ranges)
 cudaError_t launch_predict(bpmf_gpu_ctx *c, int side, int n);
 cudaError_t launch_aggregate(bpmf_gpu_ctx *c, int side);
+cudaError_t launch_finalize_aggregates(bpmf_gpu_ctx *c, int side, int nsamples);   // c++/bpmf.cpp:281-295, batched
 cudaError_t launch_debug_randn(bpmf_gpu_ctx *c, uint32_t seed, int n, double *d_out);
 size_t exact_items_smem_bytes(int K);
 // fast_kernels.cu

@@ -8,6 +8,7 @@
 //   stats kernels       sums/prods/norms + cov (sample.cpp:359-362,379-384)
 //   predict kernels     Sys::predict (sample.cpp:48-96)
 #include "common.cuh"
+#include <algorithm>
 #include "rng.cuh"
 
 namespace bpmf {
@@ -684,7 +685,8 @@ cudaError_t launch_predict(bpmf_gpu_ctx *c, int side, int n)
 // Posterior aggregation of -o (sample.cpp:364-368): aggrMu.col(i) += r; aggrLambda.col(i) += vec(r r^T)
 // One thread per element of the K x K outer product, items of [from, to).
 // =================================================================================================
-__global__ void __launch_bounds__(256) aggregate_kernel(int K, int from, int to, const double *__restrict__ items, double *aggrMu,
+// aggrMu / aggrLambda hold the items of [base, ...) only (the range the context samples).
+__global__ void __launch_bounds__(256) aggregate_kernel(int K, int from, int to, int base, const double *__restrict__ items, double *aggrMu,
                                                         double *aggrLambda)
 {
     const int KK = K * K;
@@ -694,9 +696,112 @@ __global__ void __launch_bounds__(256) aggregate_kernel(int K, int from, int to,
         const int e = (int)(q % KK), a = e % K, b = e / K;
         const double *r = items + (size_t)i * K;
         const double ra = r[a], rb = r[b];
-        aggrLambda[(size_t)i * KK + e] += ra * rb;
-        if (b == 0) aggrMu[(size_t)i * K + a] += ra;
+        aggrLambda[(size_t)(i - base) * KK + e] += ra * rb;
+        if (b == 0) aggrMu[(size_t)(i - base) * K + a] += ra;
     }
+}
+
+// Sys::finalize_mu_lambda (c++/bpmf.cpp:281-295), one warp per item, in place: cov = (prod - sum sum^T / n) / (n - 1),
+// aggrLambda.col(i) = cov^-1, aggrMu.col(i) = sum / n. The inverse is an in-place Gauss-Jordan elimination with partial
+// pivoting (rows swapped as PartialPivLU would, columns un-swapped at the end) on the matrix in shared memory; lane j owns
+// columns j, j + 32, ... (CPL of them).
+template <int CPL>   // columns per lane: ceil(K / 32)
+__global__ void finalize_aggregates_kernel(int K, int nitems, int nsamples, double *aggrMu, double *aggrLambda)
+{
+    extern __shared__ double fsm[];                  // per warp: A (K x K, column-major) | colk (K) | perm (K ints)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5, KK = K * K;
+    double *A = fsm + (size_t)warp * (KK + 2 * K), *colk = A + KK;
+    int *perm = reinterpret_cast<int *>(colk + K);
+    for (int64_t i = (int64_t)blockIdx.x * nwarp + warp; i < nitems; i += (int64_t)gridDim.x * nwarp) {
+        double *mu = aggrMu + (size_t)i * K, *lam = aggrLambda + (size_t)i * KK;
+        for (int e = lane; e < KK; e += 32) {
+            const int r = e % K, c = e / K;
+            A[e] = (lam[e] - (mu[r] * mu[c] / nsamples)) / (nsamples - 1);
+        }
+        __syncwarp();
+        for (int k = 0; k < K; ++k) {
+            // pivot: largest |A(r,k)|, r >= k (the first of equals)
+            double best = -1.0;
+            int prow = k;
+            for (int r = k + lane; r < K; r += 32) {
+                const double v = fabs(A[r + (size_t)k * K]);
+                if (v > best) { best = v; prow = r; }
+            }
+            for (int off = 16; off; off >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+                const int orow = __shfl_xor_sync(0xffffffffu, prow, off);
+                if (ob > best || (ob == best && orow < prow)) { best = ob; prow = orow; }
+            }
+            if (lane == 0) perm[k] = prow;
+            if (prow != k) {
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) {
+                    const int j = lane + 32 * q;
+                    if (j < K) {
+                        double *a = A + (size_t)j * K;
+                        const double ta = a[k];
+                        a[k] = a[prow]; a[prow] = ta;
+                    }
+                }
+            }
+            __syncwarp();
+            const double piv = A[k + (size_t)k * K];
+            for (int r = lane; r < K; r += 32) colk[r] = A[r + (size_t)k * K];
+            __syncwarp();
+            for (int r = lane; r < K; r += 32) A[r + (size_t)k * K] = (r == k) ? 1.0 : 0.0;   // column k becomes e_k, then is eliminated like the rest
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+                const int j = lane + 32 * q;
+                if (j < K) {
+                    double *a = A + (size_t)j * K;
+                    const double ak = a[k] / piv;
+                    for (int r = 0; r < K; ++r)
+                        if (r != k) a[r] -= colk[r] * ak;
+                    a[k] = ak;
+                }
+            }
+            __syncwarp();
+        }
+        for (int k = K - 1; k >= 0; --k) {           // undo the row swaps on the columns of the inverse
+            const int pk = perm[k];
+            if (pk != k)
+                for (int r = lane; r < K; r += 32) {
+                    const double tmp = A[r + (size_t)k * K];
+                    A[r + (size_t)k * K] = A[r + (size_t)pk * K];
+                    A[r + (size_t)pk * K] = tmp;
+                }
+            __syncwarp();
+        }
+        for (int e = lane; e < KK; e += 32) lam[e] = A[e];
+        for (int r = lane; r < K; r += 32) mu[r] = mu[r] / nsamples;
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_finalize_aggregates(bpmf_gpu_ctx *c, int side, int nsamples)
+{
+    SideDev &s = c->side[side];
+    const int K = c->K, n = s.aggr_to - s.aggr_from;
+    if (n <= 0) return cudaSuccess;
+    const size_t per_warp = sizeof(double) * ((size_t)K * K + 2 * (size_t)K);
+    int nwarp = (int)std::min<size_t>(4, (200 * 1024) / per_warp);
+    if (nwarp < 1) return cudaErrorInvalidConfiguration;
+    const size_t smem = per_warp * nwarp;
+    int nb = (n + nwarp - 1) / nwarp;
+    if (nb > c->sm_count * 8) nb = c->sm_count * 8;
+    cudaError_t e;
+#define BPMF_FIN_CASE(CPL)                                                                                              \
+    e = cudaFuncSetAttribute(finalize_aggregates_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return e;                                                                                     \
+    finalize_aggregates_kernel<CPL><<<nb, 32 * nwarp, smem, c->stream>>>(K, n, nsamples, s.aggrMu, s.aggrLambda)
+    if (K <= 32) { BPMF_FIN_CASE(1); }
+    else if (K <= 64) { BPMF_FIN_CASE(2); }
+    else if (K <= 96) { BPMF_FIN_CASE(3); }
+    else { BPMF_FIN_CASE(4); }
+#undef BPMF_FIN_CASE
+    c->launches++;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_aggregate(bpmf_gpu_ctx *c, int side)
@@ -707,7 +812,8 @@ cudaError_t launch_aggregate(bpmf_gpu_ctx *c, int side)
     int64_t nb = (total + 255) / 256;
     const int64_t cap = (int64_t)c->sm_count * 16;
     if (nb > cap) nb = cap;
-    aggregate_kernel<<<(unsigned)nb, 256, 0, c->stream>>>(c->K, s.from, s.to, s.items, s.aggrMu, s.aggrLambda);
+    if (s.from < s.aggr_from || s.to > s.aggr_to) return cudaErrorInvalidValue;   // the range grew after _enable_aggregation
+    aggregate_kernel<<<(unsigned)nb, 256, 0, c->stream>>>(c->K, s.from, s.to, s.aggr_from, s.items, s.aggrMu, s.aggrLambda);
     c->launches++;
     return cudaGetLastError();
 }

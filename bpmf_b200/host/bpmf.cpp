@@ -56,6 +56,8 @@ const OptionRow OPTION_TABLE[] = {
     {'t', true, "  [-t N]: Number of OpenMP threads (accepted, unused: the sweep runs on the GPU)", [](Options &, const char *) {}},
     {'x', false, "  [-x]: use the reference-order (exact) kernel instead of the fastest one",
      [](Options &, const char *) { CUDA_Sys::kernel_variant = BPMF_GPU_KERNEL_EXACT; }},
+    {'H', false, "  [-H]: build the compressed matrices on the host (default: on the GPU, from the files' entry lists)",
+     [](Options &, const char *) { CUDA_Sys::device_build = false; }},
     {'w', true, nullptr, [](Options &, const char *) {}},
     {'u', true, nullptr, [](Options &, const char *) {}},
     {'s', true, nullptr, [](Options &, const char *) {}},
@@ -63,7 +65,7 @@ const OptionRow OPTION_TABLE[] = {
 
 void usage()
 {
-    std::cout << "Usage: bpmf -n <MTX> -p <MTX> [-o DIR/] [-i N] [-b N] [-f N] [-a F] [-d K] [-g N] [-krv] [-t N]\n\nParamaters: \n";
+    std::cout << "Usage: bpmf -n <MTX> -p <MTX> [-o DIR/] [-i N] [-b N] [-f N] [-a F] [-d K] [-g N] [-krvxH] [-t N]\n\nParamaters: \n";
     for (const OptionRow &row : OPTION_TABLE)
         if (row.help) std::cout << row.help << "\n";
     std::cout << "\nMatrix Formats:\n"

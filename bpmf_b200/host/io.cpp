@@ -83,18 +83,21 @@ struct BinCursor {
     explicit BinCursor(const std::string &s) : b(s) {}
     void take(void *dst, size_t n)
     {
-        if (off + n > b.size()) fail("Unexpected end of binary matrix file");
+        if (n > b.size() - off) fail("Unexpected end of binary matrix file");   // (off <= size always; no wrap-around)
         memcpy(dst, b.data() + off, n);
         off += n;
     }
     uint64_t u64() { uint64_t v; take(&v, 8); return v; }
 };
 
-void read_sparse_bin(const std::string &bytes, bool with_values, SparseMatrixD &X)
+template <class Sink>
+void read_sparse_bin(const std::string &bytes, bool with_values, Sink &X)
 {
     BinCursor c(bytes);
     const uint64_t nrow = c.u64(), ncol = c.u64(), nnz = c.u64();
-    if (bytes.size() < 24 + nnz * (with_values ? 16 : 8)) fail("Invalid number of values");
+    // sizes come from the file: bound them by what the file can hold BEFORE multiplying (a crafted header must not wrap)
+    if (nnz > (bytes.size() - 24) / (with_values ? 16 : 8)) fail("Invalid number of values");
+    if (nrow > 0x7fffffffull || ncol > 0x7fffffffull) fail("Matrix dimensions exceed the 32-bit index range");
     std::vector<uint32_t> rows(nnz), cols(nnz);
     c.take(rows.data(), nnz * 4);
     c.take(cols.data(), nnz * 4);
@@ -113,6 +116,8 @@ void read_dense_bin(const std::string &bytes, DenseMatrixD &X)
 {
     BinCursor c(bytes);
     const uint64_t nrow = c.u64(), ncol = c.u64();
+    const uint64_t cap = (bytes.size() - 16) / 8;           // doubles the file holds after its header
+    if ((ncol != 0 && nrow > cap / ncol) || nrow * ncol > cap) fail("Invalid dense matrix size");   // also refuses a wrapping product
     X.resize((int64_t)nrow, (int64_t)ncol);
     c.take(X.data(), (size_t)(nrow * ncol) * 8);
 }
@@ -195,7 +200,8 @@ MMHeader mm_header(TextCursor &c)
     return h;
 }
 
-void read_mm_sparse(const std::string &bytes, SparseMatrixD &X)
+template <class Sink>
+void read_mm_sparse(const std::string &bytes, Sink &X)
 {
     TextCursor c(bytes);
     const MMHeader h = mm_header(c);
@@ -363,6 +369,18 @@ void read_matrix(const std::string &filename, SparseMatrixD &X)
     const std::string bytes = slurp(filename, mt.compressed);
     switch (mt.type) {
     case MatrixType::sdm: read_sparse_bin(bytes, true, X); break;
+    case MatrixType::sbm: read_sparse_bin(bytes, false, X); break;
+    case MatrixType::mtx: read_mm_sparse(bytes, X); break;
+    default: fail("Invalid matrix type: " + filename + " is a dense format, a sparse matrix was asked for");
+    }
+}
+
+void read_matrix(const std::string &filename, TripletList &X)
+{
+    const MatrixType mt = ExtensionToMatrixType(filename);
+    const std::string bytes = slurp(filename, mt.compressed);
+    switch (mt.type) {
+    case MatrixType::sdm: read_sparse_bin(bytes, true, X); X.refuse_duplicates = true; break;   // refused by the caller once they are summed
     case MatrixType::sbm: read_sparse_bin(bytes, false, X); break;
     case MatrixType::mtx: read_mm_sparse(bytes, X); break;
     default: fail("Invalid matrix type: " + filename + " is a dense format, a sparse matrix was asked for");

@@ -21,6 +21,8 @@ MatrixType ExtensionToMatrixType(const std::string &fname);
 
 void read_matrix(const std::string &filename, SparseMatrixD &X);
 void read_matrix(const std::string &filename, DenseMatrixD &X);
+// the entries of a sparse matrix file in file order, without building the compressed form (same formats, same refusals)
+void read_matrix(const std::string &filename, TripletList &X);
 void write_matrix(const std::string &filename, const SparseMatrixD &X);
 void write_matrix(const std::string &filename, const DenseMatrixD &X);
 // a K x N latent matrix that lives in a raw buffer (Sys::items_ptr)

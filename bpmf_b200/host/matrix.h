@@ -34,6 +34,16 @@ struct Triplet {
     double val;
 };
 
+// A matrix file as its readers see it: the (row, col, value) entries in FILE order. What bpmf_gpu_load_coo takes, so that the
+// compressed matrices of both factors can be built on the device instead of on the host.
+struct TripletList {
+    int64_t nrows = 0, ncols = 0;
+    std::vector<Triplet> t;
+    bool refuse_duplicates = false;   // .sdm: the reference fails with "Invalid number of values" when entries coincide (c++/io.cpp:284-287)
+    void from_triplets(int64_t nr, int64_t nc, std::vector<Triplet> &src) { nrows = nr; ncols = nc; t.swap(src); }
+    int64_t nonZeros() const { return (int64_t)t.size(); }
+};
+
 struct SparseMatrixD {
     int64_t nrows = 0, ncols = 0;
     std::vector<int64_t> colptr{0};

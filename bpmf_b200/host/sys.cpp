@@ -50,6 +50,12 @@ Sys::Sys(std::string name_, std::string fname, std::string probename)
     Pm2 = Pavg = Torig = T;
 }
 
+Sys::Sys(std::string name_)
+    : name(std::move(name_)), iter(-1), mean_rating(0.0), assigned(false), dom((size_t)(nprocs > 0 ? nprocs : 1) + 1, 0),
+      items_ptr(nullptr), norm(0.0), rmse(0.0), rmse_avg(0.0), num_predict(0)
+{
+}
+
 // c++/sample.cpp:132-137: the other factor is the transpose of an existing one
 Sys::Sys(std::string name_, const SparseMatrixD &Mt, const SparseMatrixD &Pt)
     : name(std::move(name_)), iter(-1), mean_rating(0.0), assigned(false), dom((size_t)(nprocs > 0 ? nprocs : 1) + 1, 0),

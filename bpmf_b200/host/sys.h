@@ -75,6 +75,13 @@ struct Sys {
     Sys(std::string name, std::string fname, std::string pname);
     Sys(std::string name, const SparseMatrixD &M, const SparseMatrixD &Pavg);
     virtual ~Sys();
+
+  protected:
+    // for a back end that fills M / T itself (cuda_sys.h builds both factors' matrices on the device): members
+    // initialised, nothing loaded
+    explicit Sys(std::string name);
+
+  public:
     void init();
     virtual void alloc_and_init() = 0;
 

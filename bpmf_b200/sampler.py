@@ -39,13 +39,14 @@ class GibbsSampler:
         for side in (MOVIES, USERS):
             n, n_other, ptr, idx, val = ratings.side(side)
             self.num[side] = n
-            self.ctx.load_side(side, n, n_other, ptr, idx, val, ratings.mean_rating)
             if self.exchange == "push":
                 # ragged, work-balanced ranges on statistics-block boundaries; the library's own (cudaMalloc) storage is what
-                # CUDA IPC can export
-                b = balanced_ranges(ptr, self.world, align=self.ctx.stats_block_items(side))
+                # CUDA IPC can export. Only the ratings of the rank's own items become resident (c++/bpmf.h:161-176).
+                b = balanced_ranges(ptr, self.world, align=capi.stats_block_items_for(K, n))
                 lo, hi, chunk = int(b[self.rank]), int(b[self.rank + 1]), 0
+                self.ctx.load_side_slice(side, n, n_other, lo, hi, ptr, idx, val, ratings.mean_rating)
             else:
+                self.ctx.load_side(side, n, n_other, ptr, idx, val, ratings.mean_rating)
                 lo, hi, chunk = split_range(n, self.world, self.rank)
                 buf = torch.zeros(chunk * self.world, K, dtype=torch.float64, device="cuda:%d" % device)
                 self.ctx.bind_items(side, buf.data_ptr())

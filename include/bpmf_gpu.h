@@ -64,6 +64,12 @@ int bpmf_gpu_sync(bpmf_gpu_ctx *ctx);
  * zeroed, iter = -1, cov = 0, norm = 0, range = [0, num_items). */
 int bpmf_gpu_load_side(bpmf_gpu_ctx *ctx, int side, int num_items, int num_other, const int64_t *colptr,
                        const int32_t *rowidx, const double *val, double mean_rating);
+/* The same for a context that samples only the items of [from, to) (one of G GPUs): only the ratings of those items are made
+ * resident (c++/bpmf.h:161-176: a node holds its own slice). colptr_slice has to - from + 1 entries starting at 0,
+ * rowidx_slice / val_slice colptr_slice[to - from] entries. The range is set to [from, to); bpmf_gpu_set_range must stay
+ * inside it. Latent matrices stay full replicas. */
+int bpmf_gpu_load_side_slice(bpmf_gpu_ctx *ctx, int side, int num_items, int num_other, int from, int to, const int64_t *colptr_slice,
+                             const int32_t *rowidx_slice, const double *val_slice, double mean_rating);
 /* Skew handling (K == 32): an item with more than num_ratings ratings (and more than 16x the side's average; the bar
  * is doubled until at most 16384 items per side are above it) is cut into chunks whose partial Gram matrices are computed by separate warps and added in a fixed
  * order, instead of being one warp's work (ChEMBL's hottest target has 110 118 ratings; the reference only has OpenMP's
@@ -158,6 +164,7 @@ int bpmf_gpu_reduce_stats_final(bpmf_gpu_ctx *ctx, int side);
 /* Items per statistics block of a side: item ranges (bpmf_gpu_set_range) must start and end on multiples of it (or at
  * num_items) once statistics peers are set. */
 int bpmf_gpu_stats_block_items(bpmf_gpu_ctx *ctx, int side, int *items_per_block);
+int bpmf_gpu_stats_block_items_for(int num_latent, int num_items);   /* the same before anything is loaded; -1 = bad argument */
 /* Every rank's buffer of block partials, like bpmf_gpu_set_peers for the latent matrices: device pointer of this context's
  * buffer, its CUDA IPC handle (map it with bpmf_gpu_ipc_open), and the list of all ranks' buffers. npeers = 0 = every
  * context reduces its full replica by itself. */
@@ -185,6 +192,11 @@ int bpmf_gpu_set_prop_posterior(bpmf_gpu_ctx *ctx, int side, const double *host_
  * bpmf_gpu_aggregate is that stage on its own, for hosts that drive the stages individually. */
 int bpmf_gpu_enable_aggregation(bpmf_gpu_ctx *ctx, int side, int burnin);
 int bpmf_gpu_aggregate(bpmf_gpu_ctx *ctx, int side);
+/* Sys::finalize_mu_lambda (c++/bpmf.cpp:281-295) on the device, in place, one warp per item: aggrLambda.col(i) becomes the
+ * inverse of (aggrLambda.col(i) - aggrMu.col(i) aggrMu.col(i)^T / nsamples) / (nsamples - 1), aggrMu.col(i) /= nsamples. */
+int bpmf_gpu_finalize_aggregates(bpmf_gpu_ctx *ctx, int side, int nsamples);
+/* The host arrays are full size (K x num_items, K*K x num_items); the columns of the range aggregation was enabled for
+ * (the context's [from, to) at that time — the only ones the device holds) are written. */
 int bpmf_gpu_get_aggregates(bpmf_gpu_ctx *ctx, int side, double *aggrMu, double *aggrLambda); /* synchronises */
 
 /* ---- introspection --------------------------------------------------------------------------- */

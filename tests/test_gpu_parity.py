@@ -278,6 +278,66 @@ def test_sliced_statistics_match_the_full_reduction(gpu, K):
         c.close()
 
 
+@pytest.mark.parametrize("K", [32, 16])
+def test_slice_loading_sharded_aggregates_and_device_finalize(gpu, K):
+    """One of G GPUs holds only the ratings and the posterior aggregates of ITS items (c++/bpmf.h:161-176):
+    bpmf_gpu_load_side_slice must sample its range exactly like a context that loaded everything, the aggregates of -o
+    (c++/sample.cpp:364-368) exist for the range only, and bpmf_gpu_finalize_aggregates (c++/bpmf.cpp:281-295: posterior mean
+    and the inverse of the sample covariance, batched on the device) agrees with numpy."""
+    train, test = util.synth_ratings(300, 260, 9000, 5)
+    orc = util.make_oracle(K, train, test)
+    full = util.make_gpu_from_oracle(orc, K)
+    part = gpu.Context(K)
+    rng_ = {}
+    for side in (MOVIES, USERS):
+        n = orc.num(side)
+        lo, hi = n // 3, (2 * n) // 3 + 1
+        rng_[side] = (lo, hi)
+        colptr, rowidx, val = orc.csc(side, 0)
+        part.load_side_slice(side, n, orc.num(1 - side), lo, hi, colptr, rowidx, val, orc.mean_rating(side))
+        nnz, _, dptr, _, _ = part.get_side(side)
+        assert nnz == colptr[hi] - colptr[lo]                    # only the slice's ratings are resident
+    _prime(orc, full, K, 21)
+    _prime(orc, part, K, 21)
+    nsamples = K + 8
+    acc = {side: None for side in (MOVIES, USERS)}
+    for side in (MOVIES, USERS):
+        part.enable_aggregation(side, 0)
+    for it in range(nsamples):
+        for side in (MOVIES, USERS):
+            lo, hi = rng_[side]
+            full.set_range(side, lo, hi)
+            full.sample_items(side, it, 2.0, gpu.KERNEL_AUTO)
+            part.sample_items(side, it, 2.0, gpu.KERNEL_AUTO)
+            part.aggregate(side)
+            a, b = part.get_items(side), full.get_items(side)
+            assert a[lo:hi].tobytes() == b[lo:hi].tobytes(), (it, side)
+            x = a[lo:hi]
+            mu, lam = x.copy(), np.einsum("ia,ib->iba", x, x).reshape(len(x), K * K)
+            acc[side] = (mu, lam) if acc[side] is None else (acc[side][0] + mu, acc[side][1] + lam)
+            # both contexts continue from the same state: the other items keep their primed values
+            part.set_items(side, b)
+    with pytest.raises(gpu.BpmfGpuError):
+        part.set_range(MOVIES, 0, rng_[MOVIES][1])              # outside the resident slice
+    for side in (MOVIES, USERS):
+        lo, hi = rng_[side]
+        amu, alam = part.get_aggregates(side)
+        assert not amu[:lo].any() and not amu[hi:].any()        # nothing outside the range
+        np.testing.assert_allclose(amu[lo:hi], acc[side][0], rtol=0, atol=1e-11 * np.abs(acc[side][0]).max())
+        np.testing.assert_allclose(alam[lo:hi], acc[side][1], rtol=0, atol=1e-11 * np.abs(acc[side][1]).max())
+        part.finalize_aggregates(side, nsamples)
+        fmu, flam = part.get_aggregates(side)
+        np.testing.assert_allclose(fmu[lo:hi], amu[lo:hi] / nsamples, rtol=1e-14, atol=0)
+        for i in range(lo, hi, max(1, (hi - lo) // 7)):
+            s_, p_ = amu[i], alam[i].reshape(K, K)
+            cov = (p_ - np.outer(s_, s_) / nsamples) / (nsamples - 1)
+            prec = flam[i].reshape(K, K)
+            np.testing.assert_allclose(prec @ cov, np.eye(K), rtol=0, atol=1e-7 * np.linalg.cond(cov))
+            ref = np.linalg.inv(cov)
+            assert np.abs(prec - ref).max() <= 1e-9 * np.linalg.cond(cov) * np.abs(ref).max()
+    full.close(); part.close()
+
+
 def test_cholesky_failure_is_reported(gpu):
     K = 32
     train, test = util.synth_ratings(50, 40, 600, 1)

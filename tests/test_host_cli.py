@@ -38,7 +38,7 @@ def exe():
     return EXE
 
 
-@pytest.mark.parametrize("K,shape,nnz,extra", [(32, (300, 200), 6000, []), (10, (4, 2), None, []), (16, (150, 90), 2500, ["-x"]),
+@pytest.mark.parametrize("K,shape,nnz,extra", [(32, (300, 200), 6000, []), (10, (4, 2), None, []), (16, (150, 90), 2500, ["-x", "-H"]),
                                                (32, (500, 310), 9000, ["-g", "2"])])
 def test_cli_matches_oracle(exe, tmp_path, K, shape, nnz, extra):
     if "-g" in extra:
