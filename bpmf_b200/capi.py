@@ -69,6 +69,9 @@ SYMBOLS = {
     "bpmf_gpu_last_items_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "bpmf_gpu_items_kernel_time": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "bpmf_gpu_debug_set_tuning": (C.c_int, [C.c_void_p, C.c_int]),
+    "bpmf_gpu_upload_push_range": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "bpmf_gpu_sample_host_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p]),
+    "bpmf_gpu_sample_host_end": (C.c_int, [C.c_void_p, C.c_int]),
     "bpmf_gpu_load_side_slice": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i64p, _i32p, _f64p, C.c_double]),
     "bpmf_gpu_finalize_aggregates": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "bpmf_gpu_stats_block_items_for": (C.c_int, [C.c_int, C.c_int]),
@@ -294,6 +297,14 @@ class Context:
         """Sys::sample(other) with host-resident items on both sides; arguments are raw host addresses (or None)."""
         self._ck(self.L.bpmf_gpu_sample_host(self.h, side, alpha, variant, C.c_void_p(host_other_ptr),
                                              C.c_void_p(host_items_ptr)))
+
+    def upload_push_range(self, side, lo, hi, host_ptr):
+        self._ck(self.L.bpmf_gpu_upload_push_range(self.h, side, lo, hi, C.c_void_p(host_ptr)))
+
+    def sample_host_begin(self, side, host_items_ptr, alpha=2.0, variant=KERNEL_AUTO):
+        self._ck(self.L.bpmf_gpu_sample_host_begin(self.h, side, alpha, variant, C.c_void_p(host_items_ptr)))
+
+    def sample_host_end(self, side): self._ck(self.L.bpmf_gpu_sample_host_end(self.h, side))
 
     def sample_hyper(self, side, it, sum_=None, cov=None):
         s = None if sum_ is None else np.ascontiguousarray(sum_, np.float64)

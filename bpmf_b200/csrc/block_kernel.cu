@@ -56,6 +56,11 @@ struct BlockArgs {
     const double *mu, *LambdaF;
     unsigned int *work_counter;
     unsigned long long *err;
+    const double *propLambda;   // per-item prior precisions K*K x num (-m / -l, sample.cpp:272-277) or nullptr
+    // heavy items (more than heavy_thr ratings): their Gram was computed in chunks by block_gram_chunk_kernel
+    int heavy_thr, n_heavy;
+    const int *hv_item, *hv_first;      // item index (ascending), first chunk (n_heavy + 1)
+    const double *hv_partials;          // per chunk: the accumulators of every thread, Cfg::PARTIAL doubles
     int dbg;   // timing probes (BPMF_BLOCK_DBG): 1 = no factorisation / solves, 2 = no Gram DMMAs, 4 = no solves, 8 = block 0 prints
                // the cycles of its phases for a few items; 0 = the product
 };
@@ -96,6 +101,7 @@ struct Cfg {
     static constexpr int W_OFF = BIG, Z_OFF = W_OFF + NS * SR * 8, B_OFF = Z_OFF + K * 8, RR0_OFF = B_OFF + K * 8;
     static constexpr int D_OFF = RR0_OFF + K * 8, RI_OFF = D_OFF + K * 8, INT_OFF = RI_OFF + K * 8, SMEM = INT_OFF + 16;
     __host__ __device__ static constexpr int tile(int I, int J) { return (I * (I + 1) / 2 + J) * 64; }   // doubles
+    static constexpr int PARTIAL = (2 * NB + 4) * T;             // doubles per chunk of a heavy item: acc[NB+1][2], r0, r1 of every thread
 };
 
 // Tile storage: element (r, c) of an 8 x 8 tile sits at 8 r + (c ^ swz(r)). Without the swizzle the fragment loads of a
@@ -132,49 +138,16 @@ __device__ __forceinline__ void gram_groups(double (&acc)[NB + 1][2], double &r0
     }
 }
 
+// gather + Gram of the ratings [ps, pe) of one item (computeMuLambda, sample.cpp:251-257) by the whole CTA; adds to acc / r0 / r1
 template <int NB>
-__global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB == 10 ? 3 : NB >= 6 ? 4 : 8)) items_block_kernel(BlockArgs p)
+__device__ __forceinline__ void gram_phase(const BlockArgs &p, unsigned char *smem, const int64_t ps, const int64_t pe, double (&acc)[NB + 1][2],
+                                           double &r0, double &r1, const int tid, const int warp, const int g, const int t)
 {
     using C = Cfg<NB>;
-    constexpr int K = C::K, T = C::T, NWB = C::NWB;
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double *MMp = reinterpret_cast<double *>(smem);
-    double *z = reinterpret_cast<double *>(smem + C::Z_OFF), *b = reinterpret_cast<double *>(smem + C::B_OFF);
-    double *rr0 = reinterpret_cast<double *>(smem + C::RR0_OFF);
-    double *sd = reinterpret_cast<double *>(smem + C::D_OFF), *srinv = reinterpret_cast<double *>(smem + C::RI_OFF);
-    const int g = lane >> 2, t = lane & 3;
-    const int fpos = 8 * g + (t ^ swz(g));          // A / B fragment element (g, t); (g, t + 4) is at fpos ^ 4
-    const int cpos = 8 * g + ((2 * t) ^ swz(g));    // C fragment pair (g, 2t), (g, 2t + 1)
-    int *sint = reinterpret_cast<int *>(smem + C::INT_OFF);   // [0] item, [1] failed
-
-    for (int a = tid; a < K; a += T) {    // LambdaF * hp.mu, the same for every item
-        double s = 0.0;
-        for (int j = 0; j < K; ++j) s += __ldg(p.LambdaF + a + (size_t)j * K) * __ldg(p.mu + j);
-        rr0[a] = s;
-    }
-#pragma unroll 1
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) { sint[0] = p.from + (int)atomicAdd(p.work_counter, 1u); sint[1] = 0; }
-        __syncthreads();
-        const int idx = sint[0];
-        if (idx >= p.to) break;
-        const bool prof = BLOCK_PROF && (p.dbg & 8) && blockIdx.x == 0 && tid == 0;
-        long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (prof) tk[0] = clock64();
-        for (int a = tid; a < K; a += T) b[a] = rr0[a];
-        // the K normals of this item: rng_set_pos((idx+1) * K * (iter+1)) (sample.cpp:266)
-        if (warp == NWB - 1) warp_randn((uint32_t)(((long long)idx + 1) * (long long)K * ((long long)p.iter + 1)), K, z);
-        __syncthreads();
-        const int64_t ps = __ldg(p.colptr + idx), pe = __ldg(p.colptr + idx + 1);
-        {
+    constexpr int K = C::K, NWB = C::NWB;
             // ---- gather + Gram of the item (computeMuLambda, sample.cpp:251-257)
             const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(smem);
             double *sw = reinterpret_cast<double *>(smem + C::W_OFF);
-            double acc[NB + 1][2], r0 = 0.0, r1 = 0.0;
-#pragma unroll
-            for (int n = 0; n <= NB; ++n) { acc[n][0] = 0.0; acc[n][1] = 0.0; }
             const int nst = (int)((pe - ps + SR - 1) / SR);
             // this thread's 16-byte chunks of a stage: rows rq, rq + 4, rq + 8, ..., chunk cq of the row
             const int rq = tid / (K / 2), cq = tid % (K / 2);
@@ -225,6 +198,72 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB == 10 ? 3 : NB 
                 }
             }
             cp_async_wait<0>();
+            __syncthreads();              // the ring is dead
+}
+
+template <int NB>
+__global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB == 10 ? 3 : NB >= 6 ? 4 : 8)) items_block_kernel(BlockArgs p)
+{
+    using C = Cfg<NB>;
+    constexpr int K = C::K, T = C::T, NWB = C::NWB;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *MMp = reinterpret_cast<double *>(smem);
+    double *z = reinterpret_cast<double *>(smem + C::Z_OFF), *b = reinterpret_cast<double *>(smem + C::B_OFF);
+    double *rr0 = reinterpret_cast<double *>(smem + C::RR0_OFF);
+    double *sd = reinterpret_cast<double *>(smem + C::D_OFF), *srinv = reinterpret_cast<double *>(smem + C::RI_OFF);
+    const int g = lane >> 2, t = lane & 3;
+    const int fpos = 8 * g + (t ^ swz(g));          // A / B fragment element (g, t); (g, t + 4) is at fpos ^ 4
+    const int cpos = 8 * g + ((2 * t) ^ swz(g));    // C fragment pair (g, 2t), (g, 2t + 1)
+    int *sint = reinterpret_cast<int *>(smem + C::INT_OFF);   // [0] item, [1] failed
+
+    for (int a = tid; a < K; a += T) {    // LambdaF * hp.mu, the same for every item
+        double s = 0.0;
+        for (int j = 0; j < K; ++j) s += __ldg(p.LambdaF + a + (size_t)j * K) * __ldg(p.mu + j);
+        rr0[a] = s;
+    }
+#pragma unroll 1
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) { sint[0] = p.from + (int)atomicAdd(p.work_counter, 1u); sint[1] = 0; }
+        __syncthreads();
+        const int idx = sint[0];
+        if (idx >= p.to) break;
+        const bool prof = BLOCK_PROF && (p.dbg & 8) && blockIdx.x == 0 && tid == 0;
+        long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (prof) tk[0] = clock64();
+        const double *LFi = p.propLambda ? p.propLambda + (size_t)idx * K * K : p.LambdaF;   // per-item prior precision (propagated posterior)
+        if (p.propLambda) {               // rr = hp_LambdaF * hp.mu with the GLOBAL hp.mu (sample.cpp:285, quirk Q5)
+            for (int a = tid; a < K; a += T) {
+                double s2 = 0.0;
+                for (int j = 0; j < K; ++j) s2 += __ldg(LFi + a + (size_t)j * K) * __ldg(p.mu + j);
+                b[a] = s2;
+            }
+        } else {
+            for (int a = tid; a < K; a += T) b[a] = rr0[a];
+        }
+        // the K normals of this item: rng_set_pos((idx+1) * K * (iter+1)) (sample.cpp:266)
+        if (warp == NWB - 1) warp_randn((uint32_t)(((long long)idx + 1) * (long long)K * ((long long)p.iter + 1)), K, z);
+        __syncthreads();
+        const int64_t ps = __ldg(p.colptr + idx), pe = __ldg(p.colptr + idx + 1);
+        {
+            double acc[NB + 1][2], r0 = 0.0, r1 = 0.0;
+#pragma unroll
+            for (int n = 0; n <= NB; ++n) { acc[n][0] = 0.0; acc[n][1] = 0.0; }
+            if (pe - ps > p.heavy_thr && p.n_heavy > 0) {
+                // a heavy item: its ratings were cut into chunks whose partial Grams block_gram_chunk_kernel computed; they
+                // are added in chunk order, so the result does not depend on scheduling
+                int lo = 0, hi = p.n_heavy - 1;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(p.hv_item + mid) < idx) lo = mid + 1; else hi = mid; }
+                for (int ch = __ldg(p.hv_first + lo); ch < __ldg(p.hv_first + lo + 1); ++ch) {
+                    const double *in = p.hv_partials + (size_t)ch * C::PARTIAL + tid;
+#pragma unroll
+                    for (int n = 0; n <= NB; ++n) { acc[n][0] += in[(2 * n) * T]; acc[n][1] += in[(2 * n + 1) * T]; }
+                    r0 += in[(2 * NB + 2) * T]; r1 += in[(2 * NB + 3) * T];
+                }
+            } else {
+                gram_phase<NB>(p, smem, ps, pe, acc, r0, r1, tid, warp, g, t);
+            }
             __syncthreads();              // the ring is dead: the tiles may overwrite it
             // MM = LambdaF + alpha * G (sample.cpp:297-298) into the tiles: lane (g, t) owns elements (g, 2t), (g, 2t + 1).
             // acc[n] is block (warp, n) for n <= warp and block (NB-1-warp, n-warp-1) after that.
@@ -233,8 +272,8 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB == 10 ? 3 : NB 
                 const int I = (n <= warp) ? warp : NB - 1 - warp, J = (n <= warp) ? n : n - warp - 1;
                 const int i = 8 * I + g, k = 8 * J + 2 * t;
                 double2 v;
-                v.x = fma(p.alpha, acc[n][0], __ldg(p.LambdaF + i + (size_t)k * K));
-                v.y = fma(p.alpha, acc[n][1], __ldg(p.LambdaF + i + (size_t)(k + 1) * K));
+                v.x = fma(p.alpha, acc[n][0], __ldg(LFi + i + (size_t)k * K));
+                v.y = fma(p.alpha, acc[n][1], __ldg(LFi + i + (size_t)(k + 1) * K));
                 *reinterpret_cast<double2 *>(MMp + C::tile(I, J) + cpos) = v;
             }
             // rhs: sum over the quad's four ratings-of-a-group, on top of LambdaF * mu (sample.cpp:285) already in b
@@ -464,6 +503,27 @@ __global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB == 10 ? 3 : NB 
     }
 }
 
+// One CTA per chunk of a heavy item: the partial Gram and right-hand side of its ratings, in the accumulator layout of
+// items_block_kernel (every thread's acc[NB+1][2], r0, r1), to be added there in chunk order.
+template <int NB>
+__global__ void __launch_bounds__(Cfg<NB>::T, (NB >= 12 ? 2 : NB == 10 ? 3 : NB >= 6 ? 4 : 8))
+    block_gram_chunk_kernel(BlockArgs p, const int64_t *__restrict__ ch_p0, const int64_t *__restrict__ ch_p1, double *__restrict__ partials)
+{
+    using C = Cfg<NB>;
+    constexpr int T = C::T;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int ch = blockIdx.x;
+    double acc[NB + 1][2], r0 = 0.0, r1 = 0.0;
+#pragma unroll
+    for (int n = 0; n <= NB; ++n) { acc[n][0] = 0.0; acc[n][1] = 0.0; }
+    gram_phase<NB>(p, smem, ch_p0[ch], ch_p1[ch], acc, r0, r1, tid, warp, g, t);
+    double *out = partials + (size_t)ch * C::PARTIAL + tid;
+#pragma unroll
+    for (int n = 0; n <= NB; ++n) { out[(2 * n) * T] = acc[n][0]; out[(2 * n + 1) * T] = acc[n][1]; }
+    out[(2 * NB + 2) * T] = r0; out[(2 * NB + 3) * T] = r1;
+}
+
 // The trailing-update schedule of block column kb: the trailing triangle plus block row NB (the right-hand side), minus
 // the next diagonal tile (warp 0's), cut into 2 x 2 QUADS of tiles that share their A / B fragments; the quads go
 // round-robin to warps 1 .. NWB-1 (to the only warp when NWB == 1). It does not depend on the item.
@@ -530,10 +590,18 @@ static cudaError_t build_schedules(int device)
 }
 
 template <int NB>
-cudaError_t launch_nb(bpmf_gpu_ctx *c, const BlockArgs &p, long long n)
+cudaError_t launch_nb(bpmf_gpu_ctx *c, const BlockArgs &p, long long n, int ch0, int ch1, const int64_t *hv_p0, const int64_t *hv_p1, double *hv_partials)
 {
     using C = Cfg<NB>;
     static_assert(C::SMEM <= 227 * 1024, "shared memory budget");
+    if (ch1 > ch0) {                      // the chunks of the heavy items of [from, to) first, on the same stream
+        auto ck = block_gram_chunk_kernel<NB>;
+        cudaError_t ec = cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (ec != cudaSuccess) return ec;
+        ck<<<(unsigned)(ch1 - ch0), C::T, C::SMEM, c->stream>>>(p, hv_p0 + ch0, hv_p1 + ch0, hv_partials + (size_t)ch0 * C::PARTIAL);
+        c->launches++;
+        if ((ec = cudaGetLastError()) != cudaSuccess) return ec;
+    }
     auto kern = items_block_kernel<NB>;
     // BPMF_BLOCK_1CTA (timing probe): pad the shared memory request so that only one CTA fits an SM
     static const bool one_cta = getenv("BPMF_BLOCK_1CTA") != nullptr;
@@ -551,6 +619,14 @@ cudaError_t launch_nb(bpmf_gpu_ctx *c, const BlockArgs &p, long long n)
 }
 
 }  // namespace
+
+// doubles of a heavy item's chunk partial for the CTA-per-item kernel (capi.cu sizes hv_partials with it)
+int block_partial_doubles(int K)
+{
+    const int NB = K / 8;
+    return (2 * NB + 4) * 32 * (NB / 2);
+}
+int block_heavy_chunk_size() { return 4096; }
 
 bool block_kernel_supports(int K) { return K % 16 == 0 && K >= 16 && K <= 128 && K != 32; }
 
@@ -584,6 +660,14 @@ cudaError_t launch_items_block(bpmf_gpu_ctx *c, int side, uint32_t iter, double 
     p.npeers = s.npeers; p.peers = s.peers_dev;
     p.mu = s.hp.mu; p.LambdaF = s.hp.LambdaF;
     p.work_counter = s.work_counter; p.err = c->d_err;
+    p.propLambda = s.propLambda;
+    // heavy items of [from, to): their chunks are reduced by block_gram_chunk_kernel before the item kernel
+    int first = 0, last = 0;
+    while (first < s.n_heavy && s.h_heavy_item[(size_t)first] < s.from) ++first;
+    last = first;
+    while (last < s.n_heavy && s.h_heavy_item[(size_t)last] < s.to) ++last;
+    p.heavy_thr = s.heavy_thr; p.n_heavy = s.n_heavy; p.hv_item = s.hv_item; p.hv_first = s.hv_first; p.hv_partials = s.hv_partials;
+    const int ch0 = s.n_heavy ? s.h_heavy_first[(size_t)first] : 0, ch1 = s.n_heavy ? s.h_heavy_first[(size_t)last] : 0;
     static const int dbg = [] { const char *v = getenv("BPMF_BLOCK_DBG"); return v ? atoi(v) : 0; }();
     p.dbg = dbg;
     cudaError_t e = cudaSuccess;
@@ -593,13 +677,13 @@ cudaError_t launch_items_block(bpmf_gpu_ctx *c, int side, uint32_t iter, double 
     const long long n = (long long)s.to - s.from;
     if (n < 1) return cudaSuccess;
     switch (c->K) {
-    case 16: e = launch_nb<2>(c, p, n); break;
-    case 48: e = launch_nb<6>(c, p, n); break;
-    case 64: e = launch_nb<8>(c, p, n); break;
-    case 80: e = launch_nb<10>(c, p, n); break;
-    case 96: e = launch_nb<12>(c, p, n); break;
-    case 112: e = launch_nb<14>(c, p, n); break;
-    case 128: e = launch_nb<16>(c, p, n); break;
+    case 16: e = launch_nb<2>(c, p, n, ch0, ch1, s.hv_p0, s.hv_p1, s.hv_partials); break;
+    case 48: e = launch_nb<6>(c, p, n, ch0, ch1, s.hv_p0, s.hv_p1, s.hv_partials); break;
+    case 64: e = launch_nb<8>(c, p, n, ch0, ch1, s.hv_p0, s.hv_p1, s.hv_partials); break;
+    case 80: e = launch_nb<10>(c, p, n, ch0, ch1, s.hv_p0, s.hv_p1, s.hv_partials); break;
+    case 96: e = launch_nb<12>(c, p, n, ch0, ch1, s.hv_p0, s.hv_p1, s.hv_partials); break;
+    case 112: e = launch_nb<14>(c, p, n, ch0, ch1, s.hv_p0, s.hv_p1, s.hv_partials); break;
+    case 128: e = launch_nb<16>(c, p, n, ch0, ch1, s.hv_p0, s.hv_p1, s.hv_partials); break;
     default: return cudaErrorInvalidValue;
     }
     c->launches++;

@@ -75,6 +75,8 @@ int check_device_error(bpmf_gpu_ctx *ctx)
     return fail(ctx, BPMF_GPU_ECUDA, b);
 }
 
+// per-item prior precisions (propagated posterior) are read by the PROP instantiation of the K = 32 stream kernel (sides
+// without heavy items), by the CTA-per-item kernel (any side) and by the any-K kernel
 static bool prop_on_stream(const bpmf_gpu_ctx *ctx, int side) { return ctx->K == 32 && ctx->side[side].n_heavy == 0; }
 
 int pick_variant(const bpmf_gpu_ctx *ctx, int side, int v)
@@ -82,7 +84,8 @@ int pick_variant(const bpmf_gpu_ctx *ctx, int side, int v)
     // per-item prior precisions (propagated posterior) are read by the any-K kernel and, for K = 32 on a side without
     // heavy items, by the PROP instantiation of the stream kernel
     if (v == BPMF_GPU_KERNEL_AUTO) {
-        if (ctx->side[side].propLambda) return prop_on_stream(ctx, side) ? BPMF_GPU_KERNEL_STREAM : BPMF_GPU_KERNEL_EXACT;
+        if (ctx->side[side].propLambda)
+            return prop_on_stream(ctx, side) ? BPMF_GPU_KERNEL_STREAM : block_kernel_supports(ctx->K) ? BPMF_GPU_KERNEL_BLOCK : BPMF_GPU_KERNEL_EXACT;
         if (ctx->K == 32) return BPMF_GPU_KERNEL_STREAM;
         return block_kernel_supports(ctx->K) ? BPMF_GPU_KERNEL_BLOCK : BPMF_GPU_KERNEL_EXACT;
     }
@@ -296,12 +299,14 @@ static int setup_side(bpmf_gpu_ctx *ctx, SideDev &s, const int64_t *colptr)
     CU(cudaMalloc(&s.work_counter, 2 * sizeof(unsigned int)));
     CU(cudaMemset(s.work_counter, 0, 2 * sizeof(unsigned int)));
     // skew handling for the K == 32 stream kernel: items far heavier than the rest are sampled by the chunked path
-    if (K == 32 && num_items > 0) {
+    if ((K == 32 || block_kernel_supports(K)) && num_items > 0) {
         // heavy = more ratings than max(threshold, 16 x the mean); the bar is doubled until at most MAX_HEAVY items and
-        // MAX_CHUNKS chunks (6 KB of partial Gram each) are above it
+        // MAX_CHUNKS chunks (6 KB of partial Gram each at K = 32; the CTA-per-item kernel's partials are K^2 / 2 doubles and more,
+        // so it gets larger chunks and fewer of them) are above it
         constexpr int MAX_HEAVY = 16384;
-        constexpr long long MAX_CHUNKS = 131072;
-        const int CH = heavy_chunk_size();
+        const long long MAX_CHUNKS = K == 32 ? 131072 : (long long)(1.5e9 / (8.0 * block_partial_doubles(K)));
+        const int CH = K == 32 ? heavy_chunk_size() : block_heavy_chunk_size();
+        const size_t part_doubles = K == 32 ? (size_t)heavy_partial_doubles() : (size_t)block_partial_doubles(K);
         long long thr = std::max<long long>(ctx->heavy_threshold, 16 * (nnz / num_items + 1));
         for (;; thr *= 2) {
             long long cnt = 0, chunks = 0;
@@ -327,7 +332,7 @@ static int setup_side(bpmf_gpu_ctx *ctx, SideDev &s, const int64_t *colptr)
             CU(cudaMalloc(&s.hv_first, sizeof(int) * first.size()));
             CU(cudaMalloc(&s.hv_p0, sizeof(int64_t) * p0.size()));
             CU(cudaMalloc(&s.hv_p1, sizeof(int64_t) * p1.size()));
-            CU(cudaMalloc(&s.hv_partials, sizeof(double) * p0.size() * heavy_partial_doubles()));
+            CU(cudaMalloc(&s.hv_partials, sizeof(double) * p0.size() * part_doubles));
             CU(cudaMemcpy(s.hv_item, items.data(), sizeof(int) * items.size(), cudaMemcpyHostToDevice));
             CU(cudaMemcpy(s.hv_first, first.data(), sizeof(int) * first.size(), cudaMemcpyHostToDevice));
             CU(cudaMemcpy(s.hv_p0, p0.data(), sizeof(int64_t) * p0.size(), cudaMemcpyHostToDevice));
@@ -738,8 +743,8 @@ int bpmf_gpu_sample_items(bpmf_gpu_ctx *ctx, int side, uint32_t iter, double alp
     if (s.num_other != o.num) return fail(ctx, BPMF_GPU_EINVAL, "sides disagree on dimensions");
     CU(cudaSetDevice(ctx->device));
     const int v = pick_variant(ctx, side, kernel_variant);
-    if (s.propLambda && v != BPMF_GPU_KERNEL_EXACT && !(v == BPMF_GPU_KERNEL_STREAM && prop_on_stream(ctx, side)))
-        return fail(ctx, BPMF_GPU_EINVAL, "a propagated posterior needs the EXACT, AUTO or (K = 32, no heavy items) STREAM kernel variant");
+    if (s.propLambda && v != BPMF_GPU_KERNEL_EXACT && v != BPMF_GPU_KERNEL_BLOCK && !(v == BPMF_GPU_KERNEL_STREAM && prop_on_stream(ctx, side)))
+        return fail(ctx, BPMF_GPU_EINVAL, "a propagated posterior needs the EXACT, AUTO, BLOCK or (K = 32, no heavy items) STREAM kernel variant");
     const int slot = (int)(ctx->ev_count % bpmf_gpu_ctx::EV_RING);
     CU(cudaEventRecord(ctx->ev0[slot], ctx->stream));
     if (v == BPMF_GPU_KERNEL_EXACT) CU(launch_items_exact(ctx, side, iter, alpha));
@@ -923,7 +928,8 @@ int bpmf_gpu_aggregate(bpmf_gpu_ctx *ctx, int side)
 
 int bpmf_gpu_finalize_aggregates(bpmf_gpu_ctx *ctx, int side, int nsamples)
 {
-    if (!ctx || !side_ok(side) || nsamples < 2) return BPMF_GPU_EINVAL;
+    // (nsamples <= 1, i.e. fewer iterations than the burn-in, divides by zero exactly as the reference's host code does: inf / nan out)
+    if (!ctx || !side_ok(side)) return BPMF_GPU_EINVAL;
     SideDev &s = ctx->side[side];
     if (!s.loaded || !s.aggrMu) return fail(ctx, BPMF_GPU_EINVAL, "aggregation is not enabled for this side");
     CU(cudaSetDevice(ctx->device));
@@ -1010,6 +1016,50 @@ int bpmf_gpu_items_kernel_time(bpmf_gpu_ctx *ctx, double *total_ms, int *count)
     return BPMF_GPU_OK;
 }
 
+// how many parts a host-destination sweep of n items is cut into, and the sum of their weights: parts of geometrically
+// decreasing size (ratio 0.6, below the copy : sweep time ratio of a part on PCIe 5), the last one at least MIN_PART items:
+// part p's download hides behind part p + 1's sweep and only the last, smallest part's copy is exposed (6 parts: 3.3 %)
+static int host_parts(int n, double *wsum_out)
+{
+    constexpr int PMAX = bpmf_gpu_ctx::HOST_PARTS, MIN_PART = 8192;
+    constexpr double RATIO = 0.6;
+    int P = 1;
+    double wsum = 1.0;
+    for (double w = 1.0, ws = 1.0; P < PMAX; ++P, wsum = ws) {
+        w *= RATIO; ws += w;
+        if (n * (w / ws) < MIN_PART) break;
+    }
+    *wsum_out = wsum;
+    return P;
+}
+
+// the items of [from, to) in P parts, each downloaded on the copy stream while the next one is being sampled
+static int sample_parts_to_host(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_variant, double *host_items, int P, double wsum)
+{
+    SideDev &s = ctx->side[side];
+    const size_t K = (size_t)ctx->K;
+    const int from = s.from, to = s.to;
+    constexpr double RATIO = 0.6;
+    double wdone = 0.0, w = 1.0;
+    int lo = from, rc = BPMF_GPU_OK;
+    // parts end on statistics-block boundaries when peers are set (so that a part is a valid range for every stage)
+    for (int part = 0; part < P && !rc; ++part, w *= RATIO) {
+        wdone += w;
+        const int hi = part == P - 1 ? to : from + (int)((to - from) * (wdone / wsum));
+        s.from = lo; s.to = hi;
+        rc = bpmf_gpu_sample_items(ctx, side, (uint32_t)s.iter, alpha, kernel_variant);
+        if (rc) break;
+        cudaError_t e = cudaEventRecord(ctx->ev_part[part], ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_part[part], 0);
+        if (e == cudaSuccess && hi > lo)
+            e = cudaMemcpyAsync(host_items + K * lo, s.items + K * lo, sizeof(double) * K * (hi - lo), cudaMemcpyDeviceToHost, ctx->copy_stream);
+        if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = BPMF_GPU_ECUDA; }
+        lo = hi;
+    }
+    s.from = from; s.to = to;
+    return rc;
+}
+
 int bpmf_gpu_sample_host(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_variant, const double *host_other_items,
                          double *host_items)
 {
@@ -1022,17 +1072,8 @@ int bpmf_gpu_sample_host(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_v
     if (host_other_items)   // other.items() lives in host memory in the reference (bpmf.h:193-194)
         CU(cudaMemcpyAsync(o.items, host_other_items, sizeof(double) * K * o.num, cudaMemcpyHostToDevice, ctx->stream));
     const int from = s.from, to = s.to;
-    // Parts of geometrically decreasing size (ratio 0.6, below the copy : sweep time ratio of a part on PCIe 5), the
-    // last one at least MIN_PART items: part p's download hides behind part p + 1's sweep and only the last, smallest
-    // part's copy is exposed (6 parts: 3.3 % of the matrix).
-    constexpr int PMAX = bpmf_gpu_ctx::HOST_PARTS, MIN_PART = 8192;
-    constexpr double RATIO = 0.6;
-    int P = 1;
     double wsum = 1.0;
-    for (double w = 1.0, ws = 1.0; P < PMAX; ++P, wsum = ws) {
-        w *= RATIO; ws += w;
-        if ((to - from) * (w / ws) < MIN_PART) break;
-    }
+    const int P = host_parts(to - from, &wsum);
     if (!host_items || P < 2) {
         const int rc = bpmf_gpu_sample(ctx, side, alpha, kernel_variant);
         if (rc) return rc;
@@ -1049,22 +1090,7 @@ int bpmf_gpu_sample_host(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_v
         CU(cudaMemcpyAsync(host_items, s.items, sizeof(double) * K * from, cudaMemcpyDeviceToHost, ctx->stream));
     if (to < s.num)
         CU(cudaMemcpyAsync(host_items + K * to, s.items + K * to, sizeof(double) * K * (s.num - to), cudaMemcpyDeviceToHost, ctx->stream));
-    double wdone = 0.0, w = 1.0;
-    int lo = from;
-    for (int part = 0; part < P && !rc; ++part, w *= RATIO) {
-        wdone += w;
-        const int hi = part == P - 1 ? to : from + (int)((to - from) * (wdone / wsum));
-        s.from = lo; s.to = hi;
-        rc = bpmf_gpu_sample_items(ctx, side, (uint32_t)s.iter, alpha, kernel_variant);
-        if (rc) break;
-        cudaError_t e = cudaEventRecord(ctx->ev_part[part], ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_part[part], 0);
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(host_items + K * lo, s.items + K * lo, sizeof(double) * K * (hi - lo), cudaMemcpyDeviceToHost, ctx->copy_stream);
-        if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = BPMF_GPU_ECUDA; }
-        lo = hi;
-    }
-    s.from = from; s.to = to;
+    rc = sample_parts_to_host(ctx, side, alpha, kernel_variant, host_items, P, wsum);
     if (rc) return rc;
     if (s.aggrMu && s.iter >= s.aggr_burnin) {
         rc = bpmf_gpu_aggregate(ctx, side);
@@ -1075,6 +1101,65 @@ int bpmf_gpu_sample_host(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_v
     CU(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
     return check_device_error(ctx);   // synchronises the stream
+}
+
+// ---- the same for one rank of a multi-GPU run: host memory holds THIS rank's slice of each latent matrix --------------
+int bpmf_gpu_upload_push_range(bpmf_gpu_ctx *ctx, int side, int from, int to, const double *host_items)
+{
+    if (!ctx || !side_ok(side) || !host_items) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded || from < 0 || to < from || to > s.num) return fail(ctx, BPMF_GPU_EINVAL, "bad range");
+    CU(cudaSetDevice(ctx->device));
+    const size_t K = (size_t)ctx->K;
+    // chunks: the upload of chunk c + 1 (copy stream, PCIe) runs while chunk c goes to the peers (main stream, NVLink)
+    constexpr int NCH = bpmf_gpu_ctx::HOST_PARTS;
+    const int n = to - from, nch = n >= NCH * 4096 ? NCH : 1;
+    CU(cudaEventRecord(ctx->ev_copied, ctx->stream));            // the copy stream starts after what the main stream has enqueued so far
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copied, 0));
+    for (int c = 0; c < nch; ++c) {
+        const int lo = from + (int)((long long)n * c / nch), hi = from + (int)((long long)n * (c + 1) / nch);
+        if (hi <= lo) continue;
+        CU(cudaMemcpyAsync(s.items + K * lo, host_items + K * lo, sizeof(double) * K * (hi - lo), cudaMemcpyHostToDevice, ctx->copy_stream));
+        CU(cudaEventRecord(ctx->ev_part[c], ctx->copy_stream));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_part[c], 0));
+        for (int q = 0; q < s.npeers; ++q) {
+            double *dst = s.peers_host[q];
+            if (!dst || dst == s.items) continue;
+            CU(cudaMemcpyAsync(dst + K * lo, s.items + K * lo, sizeof(double) * K * (hi - lo), cudaMemcpyDefault, ctx->stream));
+        }
+    }
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_sample_host_begin(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_variant, double *host_items)
+{
+    if (!ctx || !side_ok(side) || !host_items) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded || !ctx->side[1 - side].loaded) return fail(ctx, BPMF_GPU_EINVAL, "both sides must be loaded");
+    CU(cudaSetDevice(ctx->device));
+    s.iter++;
+    int rc = bpmf_gpu_sample_hyper(ctx, side, (uint32_t)s.iter, nullptr, nullptr);
+    if (rc) return rc;
+    double wsum = 1.0;
+    const int P = host_parts(s.to - s.from, &wsum);
+    rc = sample_parts_to_host(ctx, side, alpha, kernel_variant, host_items, P, wsum);
+    if (rc) return rc;
+    if (s.aggrMu && s.iter >= s.aggr_burnin) {
+        rc = bpmf_gpu_aggregate(ctx, side);
+        if (rc) return rc;
+    }
+    return bpmf_gpu_reduce_stats_partial(ctx, side);
+}
+
+int bpmf_gpu_sample_host_end(bpmf_gpu_ctx *ctx, int side)
+{
+    if (!ctx || !side_ok(side)) return BPMF_GPU_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    const int rc = bpmf_gpu_reduce_stats_final(ctx, side);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
+    return check_device_error(ctx);   // synchronises the stream: the fresh slice is in host memory
 }
 
 int bpmf_gpu_set_heavy_threshold(bpmf_gpu_ctx *ctx, int64_t num_ratings)

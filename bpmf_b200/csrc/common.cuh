@@ -140,6 +140,8 @@ cudaError_t launch_items_dmma32(bpmf_gpu_ctx *c, int side, uint32_t iter, double
 bool block_kernel_supports(int K);
 int block_schedule(int K, int kb, int warp, int *out, int cap_quads);
 cudaError_t launch_items_block(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha);
+int block_partial_doubles(int K);
+int block_heavy_chunk_size();
 // stream_kernel.cu
 cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha);
 cudaError_t launch_stats_partial32(bpmf_gpu_ctx *c, int side, int b0, int nb);

@@ -128,11 +128,21 @@ class GibbsSampler:
         if self.world == 1:
             self.ctx.sample_host(side, host_other_ptr, host_items_ptr, self.alpha, self.variant)
             return
-        self.upload_slice(1 - side, host_other_ptr)
-        self.sample(side)
-        lo, hi, _ = self.range[side]
-        self.ctx.get_items_range_ptr(side, lo, hi, host_items_ptr)    # synchronises this rank's stream: own slice only, which
-        #                                                               no peer writes (no fence needed)
+        if self.exchange != "push":
+            self.upload_slice(1 - side, host_other_ptr)
+            self.sample(side)
+            lo, hi, _ = self.range[side]
+            self.ctx.get_items_range_ptr(side, lo, hi, host_items_ptr)    # synchronises this rank's stream
+            return
+        # push exchange: chunked upload of the slice of the other side, each chunk forwarded to the peers over NVLink while the
+        # next one is uploaded; then the sweep in parts, each part downloaded while the next is sampled
+        self._fence_readers()
+        lo, hi, _ = self.range[1 - side]
+        self.ctx.upload_push_range(1 - side, lo, hi, host_other_ptr)
+        self.dist.all_reduce(self._tiny)          # every rank's slices are in every replica
+        self.ctx.sample_host_begin(side, host_items_ptr, self.alpha, self.variant)
+        self.dist.all_reduce(self._tiny)          # every rank's fresh columns and statistics blocks are everywhere
+        self.ctx.sample_host_end(side)            # synchronises: this rank's fresh slice is in host memory
 
     def step(self):
         """movies.sample(users); users.sample(movies)  (bpmf.cpp:184-185)"""

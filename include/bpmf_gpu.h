@@ -140,6 +140,19 @@ int bpmf_gpu_sample(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_varian
 int bpmf_gpu_sample_host(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_variant, const double *host_other_items,
                          double *host_items);
 
+/* The same for one rank of a multi-GPU run, whose host memory holds ITS slice of each latent matrix (host pointers are the
+ * bases of full-size matrices; only the slice is touched):
+ *   _upload_push_range   the slice [from, to) of `side` goes host -> device in chunks and each chunk on to every peer replica
+ *                        (bpmf_gpu_set_peers) while the next one is uploaded; asynchronous;
+ *   [the host's cross-rank barrier: every rank's slices have landed everywhere]
+ *   _sample_host_begin   iter++, hyper draw, the context's item range sampled in parts, each part downloaded to host_items
+ *                        while the next is sampled, aggregation, the rank's blocks of the statistics (to all ranks);
+ *   [the host's cross-rank barrier]
+ *   _sample_host_end     statistics summed, the download waited for; synchronises. */
+int bpmf_gpu_upload_push_range(bpmf_gpu_ctx *ctx, int side, int from, int to, const double *host_items);
+int bpmf_gpu_sample_host_begin(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_variant, double *host_items);
+int bpmf_gpu_sample_host_end(bpmf_gpu_ctx *ctx, int side);
+
 /* The stages of bpmf_gpu_sample, individually callable (multi-GPU hosts put the exchange of the
  * fresh columns between _sample_items and _reduce_stats; tests probe each stage). */
 /* rng_set_pos(iter); hp.sample(N, sum, cov)  (c++/sample.cpp:349-350, c++/bpmf.h:98-103,

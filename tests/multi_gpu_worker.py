@@ -42,6 +42,19 @@ def main():
             a, b = multi.items_host(side), single.get_items(side)
             worst = max(worst, float(np.abs(a - b).max()))
             assert a.tobytes() == b.tobytes(), "rank %d iteration %d side %d differs by %g" % (rank, it, side, np.abs(a - b).max())
+    # readers of a replica after a sweep (predict, downloads) against a peer that is already in its next sweep: rank 1 lags
+    # behind before it reads; the sampler's reader fence must keep the peers' next remote stores behind that read
+    import time
+    for it in range(2):
+        multi.step()
+        single.sample(MOVIES); single.sample(USERS)
+        if rank == world - 1:
+            time.sleep(0.3)
+        got = multi.predict(burnin=1)
+        ref = (single.predict(MOVIES, 1), single.predict(USERS, 1))
+        assert got == ref, "rank %d: predict after a lagging read differs: %r vs %r" % (rank, got, ref)
+        for side in (MOVIES, USERS):
+            assert multi.items_host(side).tobytes() == single.get_items(side).tobytes()
     # the end-to-end path of bench.py: every rank keeps ITS slice of each latent matrix in (pinned) host memory
     host = [torch.from_numpy(multi.items_host(s)).pin_memory() for s in (MOVIES, USERS)]
     for it in range(2):
@@ -50,13 +63,13 @@ def main():
             other = host[1 - side].clone()
             other[:lo] = float("nan"); other[hi:] = float("nan")      # only the own slice may be read
             other = other.pin_memory()
-            multi.upload_slice(1 - side, other.data_ptr())
-            multi.sample(side)
+            mine = torch.full_like(host[side], float("nan")).pin_memory()
+            multi.sample_host(side, other.data_ptr(), mine.data_ptr())
             lo, hi, _ = multi.range[side]
-            multi.ctx.get_items_range_ptr(side, lo, hi, host[side].data_ptr())
             single.sample(side)
             ref = single.get_items(side)
-            assert host[side].numpy()[lo:hi].tobytes() == ref[lo:hi].tobytes(), "e2e slice path differs (rank %d)" % rank
+            assert mine.numpy()[lo:hi].tobytes() == ref[lo:hi].tobytes(), "e2e slice path differs (rank %d)" % rank
+            assert np.isnan(mine.numpy()[:lo]).all() and np.isnan(mine.numpy()[hi:]).all()      # only the own slice is written
             assert multi.items_host(side).tobytes() == ref.tobytes()
             host[side] = torch.from_numpy(ref.copy()).pin_memory()
     multi.ctx.sync()

@@ -469,11 +469,12 @@ def test_sample_host_matches_device_resident_sample(gpu):
         ctx.close()
 
 
-@pytest.mark.parametrize("K", [16, 32])
+@pytest.mark.parametrize("K", [16, 32, 64])
 def test_propagated_posterior_priors(gpu, K):
     """-m / -l (c++/sample.cpp:152-174,272-283): per-item prior precisions replace hp.LambdaF, the rhs still uses the
     GLOBAL hp.mu (quirk Q5). Against the oracle: the kernel KERNEL_AUTO picks (K = 32: the PROP instantiation of the
-    stream kernel, otherwise the any-K kernel) and, for K = 32, the any-K kernel asked for explicitly."""
+    stream kernel; K = 16 m: the CTA-per-item kernel, which reads the per-item precision too) and the any-K kernel asked
+    for explicitly."""
     train, test = util.synth_ratings(120, 90, 2500, 5 + K)
     orc = util.make_oracle(K, train, test)
     ctx = util.make_gpu_from_oracle(orc, K)
@@ -489,7 +490,7 @@ def test_propagated_posterior_priors(gpu, K):
         orc.set_iter(side, it)
         orc.sample_range(side, 0, orc.num(side))
         ref = orc.items(side)
-        for variant in ([gpu.KERNEL_AUTO, gpu.KERNEL_EXACT, gpu.KERNEL_STREAM] if K == 32 else [gpu.KERNEL_AUTO]):
+        for variant in ([gpu.KERNEL_AUTO, gpu.KERNEL_EXACT, gpu.KERNEL_STREAM] if K == 32 else [gpu.KERNEL_AUTO, gpu.KERNEL_BLOCK, gpu.KERNEL_EXACT]):
             before = ctx.get_items(side)
             ctx.sample_items(side, it, 2.0, variant)
             got = ctx.get_items(side)
@@ -548,6 +549,54 @@ def test_heavy_items_chunked_path(gpu):
     chunked.sample_items(MOVIES, 3, 2.0, gpu.KERNEL_STREAM)
     orc.set_iter(MOVIES, 3)
     orc.sample_range(MOVIES, 3, 200)
+    got, ref = chunked.get_items(MOVIES), orc.items(MOVIES)
+    assert np.abs(got - ref).max() <= TOL_ITEMS * max(1.0, np.abs(ref).max())
+    for ctx in (chunked, plain):
+        ctx.close()
+
+
+@pytest.mark.parametrize("K", [64, 16])
+def test_heavy_items_in_the_cta_per_item_kernel(gpu, K):
+    """Skew handling outside K = 32 (the reference's schedule(guided), c++/sample.cpp:352-355, covers every K): an item with
+    far more ratings than the rest is cut into chunks of 4096 ratings, one CTA per chunk computes a partial Gram, the item
+    kernel adds them in chunk order. A hot movie of ~9000 ratings (3 chunks) and one of ~4500 (2 chunks) against the oracle
+    and against the unchunked path: every other item bit-identical."""
+    rng = np.random.default_rng(80 + K)
+    nr, nc = 12000, 200
+    rows = rng.integers(0, nr, size=9000); cols = rng.integers(0, nc, size=9000)
+    hot_a = rng.choice(nr, size=9100, replace=False); hot_b = rng.choice(nr, size=4500, replace=False)
+    rows = np.concatenate([rows, hot_a, hot_b]); cols = np.concatenate([cols, np.full(9100, 3), np.full(4500, 199)])
+    key = rows.astype(np.int64) * nc + cols
+    _, first = np.unique(key, return_index=True)
+    rows, cols = rows[first].astype(np.int32), cols[first].astype(np.int32)
+    vals = rng.normal(3.5, 1.0, size=len(rows))
+    train = ((nr, nc), rows, cols, vals)
+    test = ((nr, nc), rows[:50].copy(), cols[:50].copy(), vals[:50].copy())
+    orc = util.make_oracle(K, train, test)
+    chunked = util.make_gpu_from_oracle(orc, K, heavy_threshold=3000)
+    plain = util.make_gpu_from_oracle(orc, K, heavy_threshold=1 << 40)
+    for ctx in (chunked, plain):
+        _prime(orc, ctx, K, 5)
+    for it in (1, 2):
+        orc.set_iter(MOVIES, it)
+        orc.sample_range(MOVIES, 0, nc)
+        ref = orc.items(MOVIES)
+        outs = []
+        for ctx in (chunked, plain):
+            before = ctx.launch_count()
+            ctx.sample_items(MOVIES, it, 2.0, gpu.KERNEL_BLOCK)
+            got = ctx.get_items(MOVIES)
+            assert np.abs(got - ref).max() <= TOL_ITEMS * max(1.0, np.abs(ref).max()), it
+            outs.append((got, ctx.launch_count() - before))
+            ctx.set_items(MOVIES, ref)
+        mask = np.ones(nc, bool); mask[[3, 199]] = False
+        assert outs[0][0][mask].tobytes() == outs[1][0][mask].tobytes()
+        assert outs[0][1] == outs[1][1] + 1                       # + the chunk kernel
+    # a range that holds only the second heavy item (multi-GPU ranges)
+    chunked.set_range(MOVIES, 120, nc)
+    chunked.sample_items(MOVIES, 3, 2.0, gpu.KERNEL_BLOCK)
+    orc.set_iter(MOVIES, 3)
+    orc.sample_range(MOVIES, 120, nc)
     got, ref = chunked.get_items(MOVIES), orc.items(MOVIES)
     assert np.abs(got - ref).max() <= TOL_ITEMS * max(1.0, np.abs(ref).max())
     for ctx in (chunked, plain):
