@@ -27,6 +27,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG", "WARN")     # stdout carries exactly one JSON line: no "NCCL version" banner
 
 METRIC = "latent-vector samples/sec (U+V sweep) at K=32"
 UNIT = "samples/s"
@@ -274,7 +275,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--exchange", default="push", choices=["allgather", "push"])
-    ap.add_argument("--variant", default="auto", choices=["auto", "exact", "dmma", "stream"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "exact", "stream"])
     ap.add_argument("--alpha", type=float, default=2.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -316,8 +317,7 @@ def main():
     config["nnz"] = int(ratings.nnz)
     if rank == 0:
         log("workload %s ready in %.1fs (nnz %d)" % (args.workload, time.time() - t_gen, ratings.nnz))
-    variant = {"auto": bpmf_b200.KERNEL_AUTO, "exact": bpmf_b200.KERNEL_EXACT, "dmma": bpmf_b200.KERNEL_DMMA,
-               "stream": bpmf_b200.KERNEL_STREAM}[args.variant]
+    variant = {"auto": bpmf_b200.KERNEL_AUTO, "exact": bpmf_b200.KERNEL_EXACT, "stream": bpmf_b200.KERNEL_STREAM}[args.variant]
     gs = GibbsSampler(ratings, K, device=local_rank, alpha=args.alpha, variant=variant, exchange=args.exchange, with_test=True)
     parallelism = "1 gpu" if world == 1 else "items of both factors split over %d gpus, %s exchange" % (world, gs.exchange)
     n_samples = nrows + ncols
@@ -372,7 +372,7 @@ def main():
     achieved = bytes_per_launch / (k_avg_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "kernel": ("items_exact_kernel" if args.variant == "exact" or K % 16 else "items_block_kernel<%d>" % (K // 8) if K != 32 else
-                           "items_dmma32_kernel" if args.variant == "dmma" else bpmf_b200.STREAM_KERNEL_NAME),
+                           bpmf_b200.STREAM_KERNEL_NAME),
                 "kernel_ms_avg": k_avg_ms, "kernel_launches_timed": k_n, "kernel_share_of_step": k_ms / ms,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src + " (of measured, burst)"}
     if K != 32:

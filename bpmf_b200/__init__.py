@@ -5,4 +5,4 @@ bpmf_b200/host (the `bpmf` executable: CLI, loaders, Sys / CUDA_Sys). This Pytho
 C ABI for tests and bench.py; nothing here computes on the CPU.
 """
 from .capi import (Context, BpmfGpuError, load_library, SO_PATH, SYMBOLS, MOVIES, USERS,  # noqa: F401
-                   KERNEL_AUTO, KERNEL_EXACT, KERNEL_DMMA, KERNEL_STREAM, KERNEL_BLOCK, STREAM_KERNEL_NAME)
+                   KERNEL_AUTO, KERNEL_EXACT, KERNEL_STREAM, KERNEL_BLOCK, STREAM_KERNEL_NAME)

@@ -19,12 +19,13 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path
 UNITS = [
     ("capi.cu", []),
     ("exact_kernels.cu", ["-fmad=false"]),
-    ("fast_kernels.cu", []),
     ("block_kernel.cu", ["-DBPMF_BLOCK_PROF"] if os.environ.get("BPMF_BLOCK_PROF") else []),
     ("build_kernels.cu", []),
     ("stream_kernel.cu", ["-DBPMF_STREAM_PROBES"] if os.environ.get("BPMF_STREAM_PROBES") else []),
 ]
-HEADERS = ["common.cuh", "rng.cuh", "stream_experiments.cuh", os.path.join(ROOT, "include", "bpmf_gpu.h")]
+HEADERS = ["common.cuh", "rng.cuh", os.path.join(ROOT, "include", "bpmf_gpu.h")]
+if os.environ.get("BPMF_STREAM_PROBES"):     # the experiments of bench_micro/ are compiled into probe builds only
+    HEADERS += [os.path.join(ROOT, "bench_micro", f) for f in ("stream_experiments.cuh", "stream_roles.cuh", "stream_experiment_cases.inc")]
 
 
 def _nvcc():

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libbpmf_b200.so")
 
 MOVIES, USERS = 0, 1
-KERNEL_AUTO, KERNEL_EXACT, KERNEL_DMMA, KERNEL_STREAM, KERNEL_BLOCK = 0, 1, 2, 3, 4
+KERNEL_AUTO, KERNEL_EXACT, KERNEL_STREAM, KERNEL_BLOCK = 0, 1, 3, 4
 STREAM_KERNEL_NAME = "items_stream32v3_kernel<2,20>"   # what KERNEL_AUTO launches at K = 32 (csrc/stream_kernel.cu)
 
 _f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
@@ -75,6 +75,7 @@ SYMBOLS = {
     "bpmf_gpu_load_side_slice": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i64p, _i32p, _f64p, C.c_double]),
     "bpmf_gpu_finalize_aggregates": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "bpmf_gpu_stats_block_items_for": (C.c_int, [C.c_int, C.c_int]),
+    "bpmf_gpu_peer_barrier": (C.c_int, [C.c_void_p, C.c_int]),
     "bpmf_gpu_reduce_stats_partial": (C.c_int, [C.c_void_p, C.c_int]),
     "bpmf_gpu_reduce_stats_final": (C.c_int, [C.c_void_p, C.c_int]),
     "bpmf_gpu_stats_block_items": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
@@ -254,6 +255,7 @@ class Context:
         arr = (C.c_void_p * max(1, len(ptrs)))(*[C.c_void_p(p) for p in ptrs])
         self._ck(self.L.bpmf_gpu_set_stats_peers(self.h, side, len(ptrs), arr))
 
+    def peer_barrier(self, side): self._ck(self.L.bpmf_gpu_peer_barrier(self.h, side))
     def reduce_stats_partial(self, side): self._ck(self.L.bpmf_gpu_reduce_stats_partial(self.h, side))
     def reduce_stats_final(self, side): self._ck(self.L.bpmf_gpu_reduce_stats_final(self.h, side))
 

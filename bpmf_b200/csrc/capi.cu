@@ -71,6 +71,7 @@ int check_device_error(bpmf_gpu_ctx *ctx)
     if (code == 3) { snprintf(b, sizeof b, "Cholesky failed (item %u)", detail); return fail(ctx, BPMF_GPU_ECHOLESKY, b); }
     if (code == 4) return fail(ctx, BPMF_GPU_ERNG, "hyper-parameter draw ran out of pre-generated Philox blocks");
     if (code == 5) { snprintf(b, sizeof b, "hyper-parameter draw: T_c not positive definite (pivot %u)", detail); return fail(ctx, BPMF_GPU_ECHOLESKY, b); }
+    if (code == 6) { snprintf(b, sizeof b, "cross-GPU barrier: rank %u did not arrive", detail); return fail(ctx, BPMF_GPU_ECUDA, b); }
     snprintf(b, sizeof b, "device error word %llx", w);
     return fail(ctx, BPMF_GPU_ECUDA, b);
 }
@@ -292,8 +293,9 @@ static int setup_side(bpmf_gpu_ctx *ctx, SideDev &s, const int64_t *colptr)
     CU(cudaMemset(s.prod, 0, sizeof(double) * KK));
     CU(cudaMemset(s.cov, 0, sizeof(double) * KK));
     CU(cudaMemset(s.norm, 0, sizeof(double)));
-    CU(cudaMalloc(&s.partials, sizeof(double) * (size_t)STATS_BLOCKS * (KK + K + 1)));
-    CU(cudaMemset(s.partials, 0, sizeof(double) * (size_t)STATS_BLOCKS * (KK + K + 1)));
+    // + MAX_PEERS arrival words of the cross-GPU barrier (peer_barrier_kernel) behind the partials
+    CU(cudaMalloc(&s.partials, sizeof(double) * ((size_t)STATS_BLOCKS * (KK + K + 1) + MAX_PEERS)));
+    CU(cudaMemset(s.partials, 0, sizeof(double) * ((size_t)STATS_BLOCKS * (KK + K + 1) + MAX_PEERS)));
     CU(cudaMalloc(&s.stat_peers_dev, sizeof(double *) * MAX_PEERS));
     CU(cudaMemset(s.stat_peers_dev, 0, sizeof(double *) * MAX_PEERS));
     CU(cudaMalloc(&s.work_counter, 2 * sizeof(unsigned int)));
@@ -748,10 +750,7 @@ int bpmf_gpu_sample_items(bpmf_gpu_ctx *ctx, int side, uint32_t iter, double alp
     const int slot = (int)(ctx->ev_count % bpmf_gpu_ctx::EV_RING);
     CU(cudaEventRecord(ctx->ev0[slot], ctx->stream));
     if (v == BPMF_GPU_KERNEL_EXACT) CU(launch_items_exact(ctx, side, iter, alpha));
-    else if (v == BPMF_GPU_KERNEL_DMMA) {
-        if (ctx->K != 32) return fail(ctx, BPMF_GPU_EINVAL, "the DMMA kernel is built for num_latent == 32");
-        CU(launch_items_dmma32(ctx, side, iter, alpha));
-    } else if (v == BPMF_GPU_KERNEL_STREAM) {
+    else if (v == BPMF_GPU_KERNEL_STREAM) {
         if (ctx->K != 32) return fail(ctx, BPMF_GPU_EINVAL, "the stream kernel is built for num_latent == 32");
         CU(launch_items_stream32(ctx, side, iter, alpha));
     } else if (v == BPMF_GPU_KERNEL_BLOCK) {
@@ -807,6 +806,19 @@ int bpmf_gpu_set_stats_peers(bpmf_gpu_ctx *ctx, int side, int npeers, double *co
     CU(cudaMemcpyAsync(s.stat_peers_dev, tmp, sizeof(tmp), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     s.n_stat_peers = npeers;
+    s.stat_rank = -1;
+    for (int i = 0; i < npeers; ++i)
+        if (tmp[i] == s.partials) s.stat_rank = i;
+    if (npeers > 0 && s.stat_rank < 0) { s.n_stat_peers = 0; return fail(ctx, BPMF_GPU_EINVAL, "the list must contain this context's own buffer (bpmf_gpu_stats_device_ptr)"); }
+    return BPMF_GPU_OK;
+}
+
+int bpmf_gpu_peer_barrier(bpmf_gpu_ctx *ctx, int side)
+{
+    if (!ctx || !side_ok(side)) return BPMF_GPU_EINVAL;
+    if (!ctx->side[side].loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
+    CU(cudaSetDevice(ctx->device));
+    CU(launch_peer_barrier(ctx, side));
     return BPMF_GPU_OK;
 }
 
@@ -842,10 +854,14 @@ int bpmf_gpu_reduce_stats_final(bpmf_gpu_ctx *ctx, int side)
     return BPMF_GPU_OK;
 }
 
+// With statistics peers set this is a COLLECTIVE of the ranks: own blocks to every rank, the cross-GPU barrier (which also
+// orders the latent columns the item kernels pushed), the fixed-order sum.
 int bpmf_gpu_reduce_stats(bpmf_gpu_ctx *ctx, int side)
 {
-    const int rc = bpmf_gpu_reduce_stats_partial(ctx, side);
-    return rc ? rc : bpmf_gpu_reduce_stats_final(ctx, side);
+    int rc = bpmf_gpu_reduce_stats_partial(ctx, side);
+    if (rc) return rc;
+    if (ctx->side[side].n_stat_peers > 1 && (rc = bpmf_gpu_peer_barrier(ctx, side))) return rc;
+    return bpmf_gpu_reduce_stats_final(ctx, side);
 }
 
 int bpmf_gpu_get_stats(bpmf_gpu_ctx *ctx, int side, double *sum, double *prod, double *cov, double *norm)
@@ -1069,6 +1085,18 @@ int bpmf_gpu_sample_host(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_v
     if (!s.loaded || !o.loaded) return fail(ctx, BPMF_GPU_EINVAL, "both sides must be loaded");
     CU(cudaSetDevice(ctx->device));
     const size_t K = (size_t)ctx->K;
+    if (s.n_stat_peers > 1) {
+        // One rank of a multi-GPU run: host memory holds THIS rank's slice of each latent matrix. Its slice of the other side
+        // goes up in chunks, each chunk on to the peers while the next is uploaded; barrier; the sweep in parts, each part
+        // downloaded while the next is sampled; own statistics blocks to all ranks; barrier; sum; wait for the download.
+        int rc = BPMF_GPU_OK;
+        if (host_other_items && (rc = bpmf_gpu_upload_push_range(ctx, 1 - side, o.from, o.to, host_other_items))) return rc;
+        if ((rc = bpmf_gpu_peer_barrier(ctx, side))) return rc;
+        if (!host_items) return bpmf_gpu_sample(ctx, side, alpha, kernel_variant);
+        if ((rc = bpmf_gpu_sample_host_begin(ctx, side, alpha, kernel_variant, host_items))) return rc;
+        if ((rc = bpmf_gpu_peer_barrier(ctx, side))) return rc;
+        return bpmf_gpu_sample_host_end(ctx, side);
+    }
     if (host_other_items)   // other.items() lives in host memory in the reference (bpmf.h:193-194)
         CU(cudaMemcpyAsync(o.items, host_other_items, sizeof(double) * K * o.num, cudaMemcpyHostToDevice, ctx->stream));
     const int from = s.from, to = s.to;

@@ -13,6 +13,7 @@ constexpr int STATS_BLOCKS = 296;  // 2 x 148 SMs; fixed so the reduction order 
 // error word written by kernels: 0 = ok. code in the high 32 bits, detail (item index) in the low 32.
 constexpr unsigned long long ERR_CHOLESKY = 3ull << 32;
 constexpr unsigned long long ERR_RNG = 4ull << 32;
+constexpr unsigned long long ERR_BARRIER = 6ull << 32;   // a peer did not arrive at the cross-GPU barrier in time
 
 struct HyperDev {         // HyperParams on the device (c++/bpmf.h:78-104)
     double *mu = nullptr;       // K
@@ -52,6 +53,10 @@ struct SideDev {          // the device mirror of one Sys (c++/bpmf.h:112-239)
     // `partials` (peer-mapped pointers, bpmf_gpu_set_stats_peers); 0 = reduce the full replica locally
     int n_stat_peers = 0;
     double **stat_peers_dev = nullptr;    // device array[MAX_PEERS]
+    // cross-GPU barrier (peer_barrier_kernel): MAX_PEERS arrival words behind the partials of every rank's buffer; this
+    // context is rank `stat_rank` of the peer list; the epoch counts the barriers of this side
+    int stat_rank = -1;
+    unsigned long long barrier_epoch = 0;
     double *pred_partials = nullptr;
     int pred_blocks = 0;
     // propagated posterior (-m / -l): per-item prior precision K*K x num, nullptr = none (bpmf_gpu_set_prop_posterior)
@@ -129,13 +134,12 @@ cudaError_t launch_stats(bpmf_gpu_ctx *c, int side);
 cudaError_t launch_stats_partial(bpmf_gpu_ctx *c, int side);   // per-block partial sums (own blocks only when stat peers are set)
 cudaError_t launch_stats_final(bpmf_gpu_ctx *c, int side);     // fixed-order sum of the STATS_BLOCKS partials, cov
 int stats_block_items(int K, int num);                          // items per statistics block (the granularity of ranges)
+cudaError_t launch_peer_barrier(bpmf_gpu_ctx *c, int side);     // every rank's earlier work on the side has landed everywhere
 cudaError_t launch_predict(bpmf_gpu_ctx *c, int side, int n);
 cudaError_t launch_aggregate(bpmf_gpu_ctx *c, int side);
 cudaError_t launch_finalize_aggregates(bpmf_gpu_ctx *c, int side, int nsamples);   // c++/bpmf.cpp:281-295, batched
 cudaError_t launch_debug_randn(bpmf_gpu_ctx *c, uint32_t seed, int n, double *d_out);
 size_t exact_items_smem_bytes(int K);
-// fast_kernels.cu
-cudaError_t launch_items_dmma32(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha);
 // block_kernel.cu
 bool block_kernel_supports(int K);
 int block_schedule(int K, int kb, int warp, int *out, int cap_quads);

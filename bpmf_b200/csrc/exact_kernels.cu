@@ -561,6 +561,38 @@ __global__ void __launch_bounds__(256) stats_cov_kernel(int N, int K, const doub
     }
 }
 
+// Cross-GPU barrier over peer memory (replaces the MPI_Barrier / MPI_Win_fence of the MPI back ends and the NCCL all-reduce this
+// repository used as one): thread q stores this rank's epoch into rank q's arrival word (NVLink store, after a system-wide
+// fence so that everything earlier kernels of this stream wrote — latent columns, statistics blocks — is visible first),
+// then waits for rank q's epoch in its own buffer. One launch of one warp; no host involvement, so a whole multi-GPU sweep
+// is enqueued by one C call. A peer that does not arrive within ~20 s sets the error word instead of hanging the GPU.
+__global__ void peer_barrier_kernel(double *const *peers, int npeers, int me, size_t flag_off, unsigned long long epoch, unsigned long long *err)
+{
+    const int q = threadIdx.x;
+    if (q >= npeers || !peers[q] || q == me) return;
+    volatile unsigned long long *remote = reinterpret_cast<unsigned long long *>(peers[q] + flag_off) + me;
+    volatile unsigned long long *mine = reinterpret_cast<unsigned long long *>(peers[me] + flag_off) + q;
+    __threadfence_system();
+    *remote = epoch;
+    const long long t0 = clock64();
+    while (*mine < epoch) {
+        if (clock64() - t0 > 40000000000ll) { atomicMax(err, ERR_BARRIER | (unsigned)q); break; }
+        __nanosleep(100);
+    }
+    __threadfence_system();
+}
+
+cudaError_t launch_peer_barrier(bpmf_gpu_ctx *c, int side)
+{
+    SideDev &s = c->side[side];
+    if (s.n_stat_peers < 2 || s.stat_rank < 0) return cudaSuccess;
+    const size_t flag_off = (size_t)STATS_BLOCKS * ((size_t)c->K * c->K + c->K + 1);
+    ++s.barrier_epoch;
+    peer_barrier_kernel<<<1, 32, 0, c->stream>>>(s.stat_peers_dev, s.n_stat_peers, s.stat_rank, flag_off, s.barrier_epoch, c->d_err);
+    c->launches++;
+    return cudaGetLastError();
+}
+
 int stats32_block_items(int num);   // stream_kernel.cu
 
 int stats_block_items(int K, int num)

@@ -260,16 +260,13 @@ void CUDA_Sys::sample(Sys &in)
         check(c, bpmf_gpu_set_iter(c, s, iter - 1), "set_iter");
         check(c, bpmf_gpu_sample(c, s, Sys::alpha, kernel_variant), "sample");
     } else {
-        // every device draws the same hyper-parameters (cov is replicated), samples its range and pushes the columns
+        // every device draws the same hyper-parameters (cov is replicated), samples its range storing each column into every
+        // replica, reduces the statistics blocks of its range into every device's buffer, meets the others at the device-side
+        // barrier and sums: all inside bpmf_gpu_sample, enqueued device by device without a host synchronisation
         for (bpmf_gpu_ctx *c : gpus) {
-            check(c, bpmf_gpu_set_iter(c, s, iter), "set_iter");
-            check(c, bpmf_gpu_sample_hyper(c, s, (uint32_t)iter, nullptr, nullptr), "sample_hyper");
-            check(c, bpmf_gpu_sample_items(c, s, (uint32_t)iter, Sys::alpha, kernel_variant), "sample_items");
-            if (Sys::odirname.size() && iter >= Sys::burnin) check(c, bpmf_gpu_aggregate(c, s), "aggregate");
-            check(c, bpmf_gpu_reduce_stats_partial(c, s), "reduce_stats_partial");   // own blocks, stored into every GPU's buffer
+            check(c, bpmf_gpu_set_iter(c, s, iter - 1), "set_iter");
+            check(c, bpmf_gpu_sample(c, s, Sys::alpha, kernel_variant), "sample");
         }
-        for (bpmf_gpu_ctx *c : gpus) check(c, bpmf_gpu_sync(c), "sync");       // all columns and partials have landed everywhere
-        for (bpmf_gpu_ctx *c : gpus) check(c, bpmf_gpu_reduce_stats_final(c, s), "reduce_stats_final");
     }
     // state the main loop reads after sample(): norm (c++/bpmf.cpp:196), cov + hp for inspection
     bpmf_gpu_ctx *c0 = gpus[0];

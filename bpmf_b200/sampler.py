@@ -75,24 +75,25 @@ class GibbsSampler:
     def sample(self, side):
         ctx = self.ctx
         self._fence_readers()
+        if self.exchange == "push":
+            # one C call: hyper draw (every rank draws the same (mu, Lambda): cov is replicated), the item kernel storing each
+            # fresh column into every replica, own statistics blocks into every rank's buffer, the device-side cross-GPU
+            # barrier (bpmf_gpu_peer_barrier), the fixed-order sum — identical on every rank, no NCCL call in the sweep
+            ctx.sample(side, self.alpha, self.variant)
+            return
         it = ctx.get_iter(side) + 1
         ctx.set_iter(side, it)
-        ctx.sample_hyper(side, it)                       # every rank draws the same (mu, Lambda): cov is replicated
+        ctx.sample_hyper(side, it)
         ctx.sample_items(side, it, self.alpha, self.variant)
-        if self.exchange == "push":
-            ctx.reduce_stats_partial(side)               # own blocks only, stored into every rank's buffer over NVLink
-            self._exchange(side)                         # the barrier that orders items AND partials of all ranks
-            ctx.reduce_stats_final(side)                 # fixed-order sum of all blocks: identical on every rank
-        else:
-            self._exchange(side)
-            ctx.reduce_stats(side)                       # over ALL items, fixed order: identical on every rank
+        self._exchange(side)
+        ctx.reduce_stats(side)                           # over ALL items, fixed order: identical on every rank
 
     def _fence_readers(self):
         """Push mode: a peer's next sweep stores into THIS rank's replicas while it runs. Reads that this rank enqueued after
         its last sweep (predict, items_host, downloads) are ordered before those stores by one more cross-rank barrier, issued
         only when such a read happened since the last sweep. SPMD: every rank reads at the same points of the program."""
         if self._readers and self.exchange == "push":
-            self.dist.all_reduce(self._tiny)
+            self.ctx.peer_barrier(MOVIES)
         self._readers = False
 
     def _exchange(self, side):
@@ -101,10 +102,7 @@ class GibbsSampler:
         if self.exchange == "allgather":
             allgather_slices(self.dist, self.items[side], self.rank, self.world)
         elif self.exchange == "push":
-            # the item kernel already stored every fresh column into all replicas over NVLink; a one-element
-            # all-reduce on the stream orders the next kernel after EVERY rank's item kernel (stores are visible
-            # system-wide once the storing kernel has completed)
-            self.dist.all_reduce(self._tiny)
+            self.ctx.peer_barrier(side)
         else:
             raise ValueError(self.exchange)
 
@@ -119,7 +117,7 @@ class GibbsSampler:
             allgather_slices(self.dist, self.items[side], self.rank, self.world)
         else:
             self.ctx.push_range(side, lo, hi)
-            self.dist.all_reduce(self._tiny)      # every rank's copies are ordered before the next kernel of any rank
+            self.ctx.peer_barrier(side)           # every rank's copies are ordered before the next kernel of any rank
 
     def sample_host(self, side, host_other_ptr, host_items_ptr):
         """Sys::sample(Sys &other) with HOST-resident latent matrices (pinned): other.items() is read from host memory, this
@@ -134,15 +132,11 @@ class GibbsSampler:
             lo, hi, _ = self.range[side]
             self.ctx.get_items_range_ptr(side, lo, hi, host_items_ptr)    # synchronises this rank's stream
             return
-        # push exchange: chunked upload of the slice of the other side, each chunk forwarded to the peers over NVLink while the
-        # next one is uploaded; then the sweep in parts, each part downloaded while the next is sampled
+        # push exchange: one C call per rank (bpmf_gpu_sample_host runs the multi-rank protocol by itself): chunked upload of
+        # the slice of the other side, each chunk forwarded to the peers over NVLink while the next one is uploaded; device-side
+        # barrier; the sweep in parts, each part downloaded while the next is sampled; barrier; statistics; synchronises
         self._fence_readers()
-        lo, hi, _ = self.range[1 - side]
-        self.ctx.upload_push_range(1 - side, lo, hi, host_other_ptr)
-        self.dist.all_reduce(self._tiny)          # every rank's slices are in every replica
-        self.ctx.sample_host_begin(side, host_items_ptr, self.alpha, self.variant)
-        self.dist.all_reduce(self._tiny)          # every rank's fresh columns and statistics blocks are everywhere
-        self.ctx.sample_host_end(side)            # synchronises: this rank's fresh slice is in host memory
+        self.ctx.sample_host(side, host_other_ptr, host_items_ptr, self.alpha, self.variant)
 
     def step(self):
         """movies.sample(users); users.sample(movies)  (bpmf.cpp:184-185)"""

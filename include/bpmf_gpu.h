@@ -41,7 +41,7 @@ extern "C" {
 /* kernel variants of the per-item conditional update */
 #define BPMF_GPU_KERNEL_AUTO 0   /* fastest available for this K                                          */
 #define BPMF_GPU_KERNEL_EXACT 1  /* any K; reference summation order, no FMA contraction (debug / fallback) */
-#define BPMF_GPU_KERNEL_DMMA 2   /* K == 32: warp per item, fp64 tensor-core (DMMA) Gram, registers         */
+/* (2 was round 1's first tensor-core kernel; removed: the STREAM kernel superseded it)                     */
 #define BPMF_GPU_KERNEL_STREAM 3 /* K == 32: persistent, cp.async-staged gather ring, DMMA Gram + blocked LDL^T in registers */
 #define BPMF_GPU_KERNEL_BLOCK 4  /* K = 16 m, K != 32, K <= 128: one CTA per item, DMMA Gram in registers, tail in shared memory */
 
@@ -129,7 +129,11 @@ int bpmf_gpu_set_iter(bpmf_gpu_ctx *ctx, int side, int iter);
 /* ---- the hot path ---------------------------------------------------------------------------
  * bpmf_gpu_sample == Sys::sample(Sys &other) of NO_COMM (c++/sample.cpp:341-385): iter++, seed,
  * hp.sample(num, sum (always 0), cov), every item in [from,to) drawn by the
- * fused kernel, then sum / prod / norm reduced over ALL items and cov updated on the device. */
+ * fused kernel, then sum / prod / norm reduced over ALL items and cov updated on the device.
+ * Multi-GPU (bpmf_gpu_set_peers + bpmf_gpu_set_stats_peers on every rank, ranges on statistics-block boundaries): the same
+ * call on every rank is the whole sweep — the item kernel stores each fresh column into every replica, every rank reduces
+ * the statistics blocks of its range into all ranks' buffers, bpmf_gpu_peer_barrier, fixed-order sum: bit-identical to
+ * one GPU. */
 int bpmf_gpu_sample(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_variant);
 
 /* The same call with HOST-resident latent matrices on both sides, which is literally the reference's
@@ -174,6 +178,13 @@ int bpmf_gpu_reduce_stats(bpmf_gpu_ctx *ctx, int side);
  * number of block partials in a fixed order, so the chain is bit-identical for any GPU count. */
 int bpmf_gpu_reduce_stats_partial(bpmf_gpu_ctx *ctx, int side);
 int bpmf_gpu_reduce_stats_final(bpmf_gpu_ctx *ctx, int side);
+/* The cross-rank barrier itself, ON THE DEVICE: one tiny kernel that stores this rank's epoch into an arrival word of every
+ * peer's statistics buffer over NVLink (after a system-wide fence) and waits for the peers' epochs in its own. Everything
+ * the ranks enqueued on their streams before it (latent columns pushed by the item kernels, statistics blocks, range copies)
+ * is visible to what they enqueue after it. No host synchronisation, no NCCL: with statistics peers set, bpmf_gpu_sample,
+ * bpmf_gpu_reduce_stats and bpmf_gpu_sample_host run the whole multi-GPU protocol by themselves (every rank must make the
+ * same calls). A rank that does not arrive within ~20 s is reported as an error instead of a hang. No-op without peers. */
+int bpmf_gpu_peer_barrier(bpmf_gpu_ctx *ctx, int side);
 /* Items per statistics block of a side: item ranges (bpmf_gpu_set_range) must start and end on multiples of it (or at
  * num_items) once statistics peers are set. */
 int bpmf_gpu_stats_block_items(bpmf_gpu_ctx *ctx, int side, int *items_per_block);

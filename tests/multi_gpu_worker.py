@@ -33,6 +33,8 @@ def main():
     for side in (MOVIES, USERS):
         n, n_other, ptr, idx, val = ratings.side(side)
         single.load_side(side, n, n_other, ptr, idx, val, ratings.mean_rating)
+    for side in (MOVIES, USERS):
+        single.load_test(side, *ratings.test_side(side))
     worst = 0.0
     for it in range(4):
         multi.step()

@@ -99,14 +99,14 @@ CASES = [
 ]
 
 
-VARIANTS = {"exact": 1, "dmma": 2, "stream": 3, "block": 4}
+VARIANTS = {"exact": 1, "stream": 3, "block": 4}
 BLOCK_K = (16, 48, 64, 80, 96, 112, 128)
 
 
 @pytest.mark.parametrize("K,nr,nc,nnz,kw", CASES)
-@pytest.mark.parametrize("variant", ["exact", "dmma", "stream", "block"])
+@pytest.mark.parametrize("variant", ["exact", "stream", "block"])
 def test_item_update_one_sweep(gpu, K, nr, nc, nnz, kw, variant):
-    if variant in ("dmma", "stream") and K != 32:
+    if variant == "stream" and K != 32:
         pytest.skip("the warp-per-item tensor-core kernels are K == 32")
     if variant == "block" and K not in BLOCK_K:
         pytest.skip("the CTA-per-item tensor-core kernel is K = 16 m, K != 32")
@@ -184,7 +184,7 @@ def test_full_run_tiny_k10(gpu):
     _run_both(gpu, 10, util.TINY_TRAIN, util.TINY_TEST, 20, 5, gpu.KERNEL_EXACT)
 
 
-@pytest.mark.parametrize("variant", ["exact", "dmma", "stream"])
+@pytest.mark.parametrize("variant", ["exact", "stream"])
 def test_full_run_movielens_shaped_k32(gpu, variant):
     # ML-100K-shaped synthetic (943 x 1682, ~80k train / 20k test), K=32, 20 iterations, burn-in 5
     v = VARIANTS[variant]
@@ -338,11 +338,58 @@ def test_slice_loading_sharded_aggregates_and_device_finalize(gpu, K):
     full.close(); part.close()
 
 
+def test_two_ranks_on_one_gpu_whole_protocol(gpu):
+    """The multi-GPU sweep as ONE C call per rank (bpmf_gpu_sample with peers set): two "ranks" on one GPU, each on its own
+    stream, each holding only the ratings of its own items; item kernels store into both replicas, every rank reduces its
+    own statistics blocks into both buffers, the device-side barrier (bpmf_gpu_peer_barrier) orders it all. Whole chains,
+    predict included, must be bit-identical to one context that does everything."""
+    torch = pytest.importorskip("torch")
+    K = 32
+    train, test = util.synth_ratings(5000, 4000, 70000, 9)
+    orc = util.make_oracle(K, train, test, burnin=1)
+    single = util.make_gpu_from_oracle(orc, K)
+    ranks, streams = [gpu.Context(K), gpu.Context(K)], [torch.cuda.Stream(), torch.cuda.Stream()]
+    for side in (MOVIES, USERS):
+        n = orc.num(side)
+        bi = gpu.capi.stats_block_items_for(K, n)
+        cut = (n // 2 // bi) * bi
+        colptr, rowidx, val = orc.csc(side, 0)
+        for r, c in enumerate(ranks):
+            lo, hi = (0, cut) if r == 0 else (cut, n)
+            c.load_side_slice(side, n, orc.num(1 - side), lo, hi, colptr, rowidx, val, orc.mean_rating(side))
+    for r, c in enumerate(ranks):
+        c.set_stream(streams[r].cuda_stream)
+        for side in (MOVIES, USERS):
+            c.load_test(side, *orc.csc(side, 1))
+    for side in (MOVIES, USERS):
+        c0, c1 = ranks
+        c0.set_peers(side, [c0.items_device_ptr(side), c1.items_device_ptr(side)])
+        c1.set_peers(side, [c0.items_device_ptr(side), c1.items_device_ptr(side)])
+        for c in ranks:
+            c.set_stats_peers(side, [c0.stats_device_ptr(side), c1.stats_device_ptr(side)])
+    for it in range(4):
+        for side in (MOVIES, USERS):
+            single.sample(side)
+            for c in ranks:
+                c.sample(side)                    # collective: both ranks enqueue, nobody synchronises in between
+        ref = single.predict(MOVIES, 1)
+        for c in ranks:
+            assert c.predict(MOVIES, 1) == ref
+            for side in (MOVIES, USERS):
+                assert c.get_items(side).tobytes() == single.get_items(side).tobytes(), (it, side)
+                a, b = c.get_stats(side), single.get_stats(side)
+                assert a[2].tobytes() == b[2].tobytes() and a[3] == b[3]
+        for c in ranks:
+            c.peer_barrier(MOVIES)                # readers done before the next sweep's remote stores (what the sampler does)
+    for c in ranks + [single]:
+        c.close()
+
+
 def test_cholesky_failure_is_reported(gpu):
     K = 32
     train, test = util.synth_ratings(50, 40, 600, 1)
     orc = util.make_oracle(K, train, test)
-    for v in (gpu.KERNEL_EXACT, gpu.KERNEL_DMMA, gpu.KERNEL_STREAM):
+    for v in (gpu.KERNEL_EXACT, gpu.KERNEL_STREAM):
         ctx = util.make_gpu_from_oracle(orc, K)
         ctx.set_hyper(MOVIES, np.zeros(K), -np.eye(K))   # not positive definite -> "Cholesky failed" (sample.cpp:308)
         ctx.sample_items(MOVIES, 0, 2.0, v)
@@ -498,9 +545,8 @@ def test_propagated_posterior_priors(gpu, K):
             assert np.abs(got - ref).max() <= tol, (side, it, variant)
             ctx.set_items(side, before)
         ctx.set_items(side, ref)
-    if K == 32:   # the first tensor-core kernel reads the shared LambdaF only: asking for it with a prior is an error
-        with pytest.raises(gpu.BpmfGpuError):
-            ctx.sample_items(MOVIES, 4, 2.0, gpu.KERNEL_DMMA)
+    with pytest.raises(gpu.BpmfGpuError):                 # variant 2 (round 1's first tensor-core kernel) no longer exists
+        ctx.sample_items(MOVIES, 4, 2.0, 2)
     ctx.set_prop_posterior(MOVIES, None, None)          # priors removed: back to the shared hyper-parameters
     ctx.sample_items(MOVIES, 4, 2.0, gpu.KERNEL_STREAM if K == 32 else gpu.KERNEL_AUTO)
     ctx.sync()
