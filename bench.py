@@ -27,7 +27,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ.setdefault("NCCL_DEBUG", "WARN")     # stdout carries exactly one JSON line: no "NCCL version" banner
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"           # stdout carries exactly one JSON line: no "NCCL version" banner
 
 METRIC = "latent-vector samples/sec (U+V sweep) at K=32"
 UNIT = "samples/s"

@@ -687,13 +687,19 @@ __global__ void __launch_bounds__(256) predict_kernel(int K, int64_t nnz, int n,
     }
     if (threadIdx.x == 0) { partials[2 * blockIdx.x] = s0[0]; partials[2 * blockIdx.x + 1] = s1[0]; }
 }
-__global__ void predict_final_kernel(const double *partials, int nb, double *out)
+// fixed-order sum of the per-block partials: thread t adds blocks t, t + 256, ...; then a shared-memory tree
+__global__ void __launch_bounds__(256) predict_final_kernel(const double *partials, int nb, double *out)
 {
-    if (threadIdx.x == 0) {
-        double a = 0.0, b = 0.0;
-        for (int i = 0; i < nb; ++i) { a += partials[2 * i]; b += partials[2 * i + 1]; }
-        out[0] = a; out[1] = b;
+    __shared__ double s0[256], s1[256];
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < nb; i += 256) { a += partials[2 * i]; b += partials[2 * i + 1]; }
+    s0[threadIdx.x] = a; s1[threadIdx.x] = b;
+    __syncthreads();
+    for (int off = 128; off; off >>= 1) {
+        if ((int)threadIdx.x < off) { s0[threadIdx.x] += s0[threadIdx.x + off]; s1[threadIdx.x] += s1[threadIdx.x + off]; }
+        __syncthreads();
     }
+    if (threadIdx.x == 0) { out[0] = s0[0]; out[1] = s1[0]; }
 }
 
 cudaError_t launch_predict(bpmf_gpu_ctx *c, int side, int n)
@@ -708,7 +714,7 @@ cudaError_t launch_predict(bpmf_gpu_ctx *c, int side, int n)
     c->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    predict_final_kernel<<<1, 32, 0, c->stream>>>(s.pred_partials, (int)nb, s.pred_partials + 2 * (size_t)s.pred_blocks);
+    predict_final_kernel<<<1, 256, 0, c->stream>>>(s.pred_partials, (int)nb, s.pred_partials + 2 * (size_t)s.pred_blocks);
     c->launches++;
     return cudaGetLastError();
 }
