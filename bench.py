@@ -425,6 +425,11 @@ def main():
         t = torch.tensor([launches], dtype=torch.int64, device="cuda")
         dist.all_reduce(t)
         total_launches = int(t.item())
+        # every rank's average item-kernel time: the spread is the load imbalance the cross-GPU barrier waits for
+        kt = torch.zeros(world, dtype=torch.float64, device="cuda")
+        kt[rank] = k_avg_ms
+        dist.all_reduce(kt)
+        roofline["kernel_ms_avg_per_rank"] = [round(float(x), 4) for x in kt.tolist()]
     witness = latents_witness(gs, (("V", MOVIES), ("U", USERS))) if rank == 0 else None
     gs.close()
     del gs

@@ -162,6 +162,11 @@ __device__ __forceinline__ double fast_rcp(double p)
     return fma(r, t, r);
 }
 
+// (Measured alternative, profiles/r02_tune_rank1_dmma.log: the column step as a RANK-ONE DMMA with one-hot k-slots — lane
+// (g, k2) already holds A~(I,KB)[g][k] and D[g][k], so A fragment (t == k2 ? c[I][e] : 0) and B fragment (t == k2 && g > k ?
+// -c[D][e] / d_k : 0) need no lane exchange at all: per column 1 shuffle + (4 - KB) DMMAs instead of 3 + (4 - KB) shuffles
+// and 2 (4 - KB) DFMAs, 368 fewer fp64 / shuffle instructions per item, bit-identical results — and 7.91 ms instead of 7.70:
+// 80 more DMMAs per item are 864 more cycles of the fp64 pipe, which the kernel cannot spare either.)
 template <int KB, int DBG = 0>
 __device__ __forceinline__ void chol3_block_column(double (&c)[10][2], double &myd, double &myrinv, int lane, int t)
 {

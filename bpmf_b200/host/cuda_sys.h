@@ -6,9 +6,11 @@
 //
 // Everything numerical goes through the C ABI of libbpmf_b200.so (include/bpmf_gpu.h); this header only orders the
 // calls. "movs" is side 0, "users" side 1 (c++/bpmf.cpp:131-132). One host process drives `ngpus` devices (-g N):
-// every device holds a full replica of both latent matrices and the ratings, samples its own contiguous item range
-// [from,to) of each factor, and its item kernel stores each fresh K-vector straight into every replica over NVLink
-// (bpmf_gpu_set_peers) — that store is what replaces send_item() of the MPI / GASPI back ends.
+// every device holds a full replica of both latent matrices but only the ratings (and -o aggregates) of its own contiguous
+// item range [from,to) of each factor (c++/bpmf.h:161-176), samples that range, and its item kernel stores each fresh
+// K-vector straight into every replica over NVLink (bpmf_gpu_set_peers) — that store is what replaces send_item() of the
+// MPI / GASPI back ends; the sweep statistics are reduced range by range into every device's buffer and a device-side
+// barrier replaces the back ends' MPI_Allreduce / MPI_Barrier (bpmf_gpu_set_stats_peers, bpmf_gpu_peer_barrier).
 #pragma once
 #include <algorithm>
 #include <cstdlib>
