@@ -58,14 +58,16 @@ void free_side(SideDev &s)
 
 bool side_ok(int side) { return side == 0 || side == 1; }
 
-// deferred kernel-side errors (the word kernels atomicMax into)
+// deferred kernel-side errors (the word kernels atomicMax into). It is read AND reset by one atomic exchange on the device
+// (launch_fetch_error): a hyper draw running ahead on the auxiliary stream may report into the word at any time, and a
+// read followed by a separate clear could wipe what it wrote in between.
 int check_device_error(bpmf_gpu_ctx *ctx)
 {
-    CU(cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(launch_fetch_error(ctx));
+    CU(cudaMemcpyAsync(ctx->h_err, ctx->d_err + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     const unsigned long long w = *ctx->h_err;
     if (!w) return BPMF_GPU_OK;
-    CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(unsigned long long), ctx->stream));
     const unsigned code = (unsigned)(w >> 32), detail = (unsigned)(w & 0xffffffffu);
     char b[256];
     if (code == 3) { snprintf(b, sizeof b, "Cholesky failed (item %u)", detail); return fail(ctx, BPMF_GPU_ECHOLESKY, b); }
@@ -123,8 +125,8 @@ int bpmf_gpu_create(bpmf_gpu_ctx **out, int device, int num_latent)
     const int K = num_latent, KK = K * K;
     auto bail = [&](cudaError_t ee) { g_create_err = cudaGetErrorString(ee); bpmf_gpu_destroy(ctx); return BPMF_GPU_ECUDA; };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e);
-    if ((e = cudaMalloc(&ctx->d_err, sizeof(unsigned long long))) != cudaSuccess) return bail(e);
-    if ((e = cudaMemset(ctx->d_err, 0, sizeof(unsigned long long))) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&ctx->d_err, 2 * sizeof(unsigned long long))) != cudaSuccess) return bail(e);   // [0] the word, [1] what was fetched
+    if ((e = cudaMemset(ctx->d_err, 0, 2 * sizeof(unsigned long long))) != cudaSuccess) return bail(e);
     if ((e = cudaMallocHost(&ctx->h_err, sizeof(unsigned long long))) != cudaSuccess) return bail(e);
     if ((e = cudaMalloc(&ctx->d_zero_row, sizeof(double) * 128)) != cudaSuccess) return bail(e);
     if ((e = cudaMemset(ctx->d_zero_row, 0, sizeof(double) * 128)) != cudaSuccess) return bail(e);
@@ -149,6 +151,7 @@ int bpmf_gpu_create(bpmf_gpu_ctx **out, int device, int num_latent)
         if ((e = cudaMalloc(&h.host_in, sizeof(double) * (KK + K))) != cudaSuccess) return bail(e);
         if ((e = cudaEventCreateWithFlags(&ctx->ev_stats[sd], cudaEventDisableTiming)) != cudaSuccess) return bail(e);
         if ((e = cudaEventCreateWithFlags(&ctx->ev_hyper[sd], cudaEventDisableTiming)) != cudaSuccess) return bail(e);
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_sdone[sd], cudaEventDisableTiming)) != cudaSuccess) return bail(e);
     }
     if ((e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
     if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
@@ -174,6 +177,7 @@ int bpmf_gpu_destroy(bpmf_gpu_ctx *ctx)
         dfree(h.mats); dfree(h.vecs); dfree(h.piv); dfree(h.host_in);
         if (ctx->ev_stats[sd]) cudaEventDestroy(ctx->ev_stats[sd]);
         if (ctx->ev_hyper[sd]) cudaEventDestroy(ctx->ev_hyper[sd]);
+        if (ctx->ev_sdone[sd]) cudaEventDestroy(ctx->ev_sdone[sd]);
     }
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -828,6 +832,7 @@ int bpmf_gpu_reduce_stats_partial(bpmf_gpu_ctx *ctx, int side)
     SideDev &s = ctx->side[side];
     if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
     CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_sdone[side], 0));   // the previous sums of this side (auxiliary stream) have read the partials
     const cudaError_t e = launch_stats_partial(ctx, side);
     if (e == cudaErrorInvalidValue && s.n_stat_peers > 0)
         return fail(ctx, BPMF_GPU_EINVAL, "with statistics peers the item range must be aligned to bpmf_gpu_stats_block_items");
@@ -841,15 +846,21 @@ int bpmf_gpu_reduce_stats_final(bpmf_gpu_ctx *ctx, int side)
     SideDev &s = ctx->side[side];
     if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
     CU(cudaSetDevice(ctx->device));
-    CU(launch_stats_final(ctx, side));
     if (ctx->overlap_hyper && s.num >= 1) {
-        // hp.sample of the NEXT iteration needs only this cov (c++/sample.cpp:350): start it now on the auxiliary stream
+        // Nothing on the main stream needs sum / prod / cov / norm before the next sweep of THIS side: the fixed-order sum of
+        // the block partials and hp.sample of the next iteration (which needs only this cov, c++/sample.cpp:350) run on the
+        // auxiliary stream, under the other side's sweep. ev_hyper[side] marks their completion (readers wait for it).
         CU(cudaEventRecord(ctx->ev_stats[side], ctx->stream));
         CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_stats[side], 0));
         CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_hyper[side], 0));
+        CU(launch_stats_final(ctx, side, ctx->aux_stream));
+        CU(cudaEventRecord(ctx->ev_sdone[side], ctx->aux_stream));
         CU(launch_hyper(ctx, side, (uint32_t)(s.iter + 1), nullptr, s.cov, true));
         CU(cudaEventRecord(ctx->ev_hyper[side], ctx->aux_stream));
         s.pre_iter = s.iter + 1;
+    } else {
+        CU(launch_stats_final(ctx, side, ctx->stream));
+        CU(cudaEventRecord(ctx->ev_sdone[side], ctx->stream));
     }
     return BPMF_GPU_OK;
 }
@@ -871,6 +882,7 @@ int bpmf_gpu_get_stats(bpmf_gpu_ctx *ctx, int side, double *sum, double *prod, d
     if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
     CU(cudaSetDevice(ctx->device));
     const int K = ctx->K;
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_sdone[side], 0));   // the sums may be in flight on the auxiliary stream
     if (sum) CU(cudaMemcpyAsync(sum, s.sum, sizeof(double) * K, cudaMemcpyDeviceToHost, ctx->stream));
     if (prod) CU(cudaMemcpyAsync(prod, s.prod, sizeof(double) * K * K, cudaMemcpyDeviceToHost, ctx->stream));
     if (cov) CU(cudaMemcpyAsync(cov, s.cov, sizeof(double) * K * K, cudaMemcpyDeviceToHost, ctx->stream));

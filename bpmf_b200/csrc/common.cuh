@@ -101,11 +101,12 @@ struct bpmf_gpu_ctx {
     bpmf::HyperScratch hs[2];             // per side: the two sides' draws may be in flight at the same time
     cudaStream_t aux_stream = nullptr;    // the next iteration's hyper draw runs here, under the other side's sweep
     cudaEvent_t ev_stats[2] = {}, ev_hyper[2] = {};
+    cudaEvent_t ev_sdone[2] = {};         // the statistics of a side (sum / prod / cov / norm) are complete (they may be computed on aux_stream)
     bool overlap_hyper = true;
     cudaStream_t copy_stream = nullptr;   // bpmf_gpu_sample_host: downloads finished item ranges while the rest is sampled
     static constexpr int HOST_PARTS = 6;   // most parts a host-destination sweep is cut into (capi.cu: bpmf_gpu_sample_host)
     cudaEvent_t ev_part[HOST_PARTS] = {}, ev_copied = nullptr;
-    unsigned long long *d_err = nullptr;  // device error word
+    unsigned long long *d_err = nullptr;  // device error word [0]; [1] receives it when the host asks (read-and-reset)
     unsigned long long *h_err = nullptr;  // pinned host copy
     double *h_pinned = nullptr;           // small pinned staging (K*K + K + 8 doubles)
     double *d_zero_row = nullptr;         // 128 doubles of zeros (padding rows of the bulk-copy gather)
@@ -132,12 +133,13 @@ cudaError_t launch_hyper(bpmf_gpu_ctx *c, int side, uint32_t iter, const double 
 cudaError_t launch_items_exact(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha);
 cudaError_t launch_stats(bpmf_gpu_ctx *c, int side);
 cudaError_t launch_stats_partial(bpmf_gpu_ctx *c, int side);   // per-block partial sums (own blocks only when stat peers are set)
-cudaError_t launch_stats_final(bpmf_gpu_ctx *c, int side);     // fixed-order sum of the STATS_BLOCKS partials, cov
+cudaError_t launch_stats_final(bpmf_gpu_ctx *c, int side, cudaStream_t stream);   // fixed-order sum of the STATS_BLOCKS partials, cov
 int stats_block_items(int K, int num);                          // items per statistics block (the granularity of ranges)
 cudaError_t launch_peer_barrier(bpmf_gpu_ctx *c, int side);     // every rank's earlier work on the side has landed everywhere
 cudaError_t launch_predict(bpmf_gpu_ctx *c, int side, int n);
 cudaError_t launch_aggregate(bpmf_gpu_ctx *c, int side);
 cudaError_t launch_finalize_aggregates(bpmf_gpu_ctx *c, int side, int nsamples);   // c++/bpmf.cpp:281-295, batched
+cudaError_t launch_fetch_error(bpmf_gpu_ctx *c);     // d_err[1] = atomicExch(d_err[0], 0)
 cudaError_t launch_debug_randn(bpmf_gpu_ctx *c, uint32_t seed, int n, double *d_out);
 size_t exact_items_smem_bytes(int K);
 // block_kernel.cu

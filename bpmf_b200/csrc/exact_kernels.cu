@@ -586,6 +586,13 @@ cudaError_t launch_peer_barrier(bpmf_gpu_ctx *c, int side)
 {
     SideDev &s = c->side[side];
     if (s.n_stat_peers < 2 || s.stat_rank < 0) return cudaSuccess;
+    // Once this rank has passed the barrier its peers may overwrite its statistics blocks (their next sweep of either side):
+    // the sums of the previous sweeps, which run on the auxiliary stream (bpmf_gpu_reduce_stats_final), must have read them.
+    // They were enqueued at least one item kernel ago, so this wait does not stall.
+    for (int sd = 0; sd < 2; ++sd) {
+        const cudaError_t ew = cudaStreamWaitEvent(c->stream, c->ev_sdone[sd], 0);
+        if (ew != cudaSuccess) return ew;
+    }
     const size_t flag_off = (size_t)STATS_BLOCKS * ((size_t)c->K * c->K + c->K + 1);
     ++s.barrier_epoch;
     peer_barrier_kernel<<<1, 32, 0, c->stream>>>(s.stat_peers_dev, s.n_stat_peers, s.stat_rank, flag_off, s.barrier_epoch, c->d_err);
@@ -635,15 +642,15 @@ cudaError_t launch_stats_partial(bpmf_gpu_ctx *c, int side)
     return cudaGetLastError();
 }
 
-cudaError_t launch_stats_final(bpmf_gpu_ctx *c, int side)
+cudaError_t launch_stats_final(bpmf_gpu_ctx *c, int side, cudaStream_t stream)
 {
     SideDev &s = c->side[side];
     const int K = c->K, KK = K * K, W = KK + K + 1;
-    stats_sum_kernel<<<(W * 8 + 255) / 256, 256, 0, c->stream>>>(s.partials, K, s.sum, s.prod, s.norm);
+    stats_sum_kernel<<<(W * 8 + 255) / 256, 256, 0, stream>>>(s.partials, K, s.sum, s.prod, s.norm);
     c->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    stats_cov_kernel<<<(KK + 255) / 256, 256, 0, c->stream>>>(s.num, K, s.sum, s.prod, s.cov);
+    stats_cov_kernel<<<(KK + 255) / 256, 256, 0, stream>>>(s.num, K, s.sum, s.prod, s.cov);
     c->launches++;
     return cudaGetLastError();
 }
@@ -651,7 +658,7 @@ cudaError_t launch_stats_final(bpmf_gpu_ctx *c, int side)
 cudaError_t launch_stats(bpmf_gpu_ctx *c, int side)
 {
     const cudaError_t e = launch_stats_partial(c, side);
-    return e != cudaSuccess ? e : launch_stats_final(c, side);
+    return e != cudaSuccess ? e : launch_stats_final(c, side, c->stream);
 }
 
 // =================================================================================================
@@ -853,6 +860,14 @@ cudaError_t launch_aggregate(bpmf_gpu_ctx *c, int side)
     if (s.from < s.aggr_from || s.to > s.aggr_to) return cudaErrorInvalidValue;   // the range grew after _enable_aggregation
     aggregate_kernel<<<(unsigned)nb, 256, 0, c->stream>>>(c->K, s.from, s.to, s.aggr_from, s.items, s.aggrMu, s.aggrLambda);
     c->launches++;
+    return cudaGetLastError();
+}
+
+// read-and-reset of the error word in one atomic
+__global__ void fetch_error_kernel(unsigned long long *err) { err[1] = atomicExch(err, 0ull); }
+cudaError_t launch_fetch_error(bpmf_gpu_ctx *c)
+{
+    fetch_error_kernel<<<1, 1, 0, c->stream>>>(c->d_err);
     return cudaGetLastError();
 }
 

@@ -162,16 +162,36 @@ __device__ __forceinline__ double fast_rcp(double p)
     return fma(r, t, r);
 }
 
-// (Measured alternative, profiles/r02_tune_rank1_dmma.log: the column step as a RANK-ONE DMMA with one-hot k-slots — lane
-// (g, k2) already holds A~(I,KB)[g][k] and D[g][k], so A fragment (t == k2 ? c[I][e] : 0) and B fragment (t == k2 && g > k ?
-// -c[D][e] / d_k : 0) need no lane exchange at all: per column 1 shuffle + (4 - KB) DMMAs instead of 3 + (4 - KB) shuffles
-// and 2 (4 - KB) DFMAs, 368 fewer fp64 / shuffle instructions per item, bit-identical results — and 7.91 ms instead of 7.70:
-// 80 more DMMAs per item are 864 more cycles of the fp64 pipe, which the kernel cannot spare either.)
-template <int KB, int DBG = 0>
+// R1 (config 15220, a measured alternative): the column step as a RANK-ONE DMMA with one-hot k-slots. Lane (g, k2) already
+// holds A~(I,KB)[g][k] and D[g][k] (k = 2 k2 + e), so A fragment (t == k2 ? c[I][e] : 0) and B fragment (t == k2 && g > k ?
+// -c[D][e] / d_k : 0) need no lane exchange at all: per column 1 shuffle + (4 - KB) DMMAs instead of 3 + (4 - KB) shuffles and
+// 2 (4 - KB) DFMAs — 368 fewer fp64 / shuffle instructions per item, bit-identical results (the three zero products add
+// exactly), but 80 more DMMAs = 864 more cycles of the fp64 pipe per item.
+template <int KB, int DBG = 0, bool R1 = false>
 __device__ __forceinline__ void chol3_block_column(double (&c)[10][2], double &myd, double &myrinv, int lane, int t)
 {
     constexpr int D = blk(KB, KB);
     const double p_probe = c[D][0] + 3.0;    // DBG & 64 (timing probe, wrong results): reciprocals that do not depend on the chain
+    if (R1) {
+        const int g = lane >> 2;
+#pragma unroll 1
+        for (int k2 = 0; k2 < 4; ++k2) {
+            const bool mine = (t == k2);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int k = 2 * k2 + e;
+                const double p = __shfl_sync(FULL, c[D][e], 4 * k + k2);       // pivot d_k: lane (g = k, t = k2), register e
+                const double rinv = fast_rcp((DBG & 64) ? p_probe + k : p);
+                if (lane == 8 * KB + k) { myd = p; myrinv = rinv; }
+                const double bf = (mine && g > k) ? -(c[D][e] * rinv) : 0.0;   // B[k2][n = g] = -D[n][k] / d_k below the pivot
+#pragma unroll
+                for (int I = KB; I < 4; ++I) {
+                    const double af = mine ? c[blk(I, KB)][e] : 0.0;           // A[m = g][k2] = A~(I,KB)[m][k]
+                    dmma884(c[blk(I, KB)][0], c[blk(I, KB)][1], af, bf);
+                }
+            }
+        }
+    } else {
 #pragma unroll 1
     for (int k2 = 0; k2 < 4; ++k2) {
         const int qsrc = (lane & ~3) | k2;
@@ -195,6 +215,7 @@ __device__ __forceinline__ void chol3_block_column(double (&c)[10][2], double &m
                 c[blk(I, KB)][1] = fma(a[I], bl1, c[blk(I, KB)][1]);
             }
         }
+    }
     }
     // trailing update A(I,J) -= A~(I,KB) D^-1 A~(J,KB)^T for KB < J <= I on the tensor cores
     // The sum over the block's eight columns may run in any order: DMMA number e takes column 2t + e in its k-slot t, so
@@ -223,7 +244,7 @@ __device__ __forceinline__ void chol3_block_column(double (&c)[10][2], double &m
 // PROP: the item has its own prior precision (propagated posterior, sample.cpp:272-283): LambdaF is read from
 // p.propLambda instead of shared memory, and rr starts from LambdaF_i * hp.mu with the GLOBAL hp.mu (quirk Q5), which the
 // caller keeps in srr0.
-template <int DBG, bool PROP = false>
+template <int DBG, bool PROP = false, bool R1 = false>
 __device__ __forceinline__ void tail32_warp(double (&c)[10][2], double (&rrp)[4], const int idx, unsigned char *stg, const double *sLF,
                                             const double *srr0, const StreamArgs &p, const int lane, unsigned char *vecs = nullptr)
 {
@@ -278,10 +299,10 @@ __device__ __forceinline__ void tail32_warp(double (&c)[10][2], double (&rrp)[4]
     double myd = 1.0, myrinv = 1.0;
     bool ok = true;
     if (!(DBG & 16)) {
-        chol3_block_column<0, DBG>(c, myd, myrinv, lane, t);
-        chol3_block_column<1, DBG>(c, myd, myrinv, lane, t);
-        chol3_block_column<2, DBG>(c, myd, myrinv, lane, t);
-        chol3_block_column<3, DBG>(c, myd, myrinv, lane, t);
+        chol3_block_column<0, DBG, R1>(c, myd, myrinv, lane, t);
+        chol3_block_column<1, DBG, R1>(c, myd, myrinv, lane, t);
+        chol3_block_column<2, DBG, R1>(c, myd, myrinv, lane, t);
+        chol3_block_column<3, DBG, R1>(c, myd, myrinv, lane, t);
     } else {
         myd = c[0][0] + 2.0; myrinv = fast_rcp(myd);
     }
@@ -355,7 +376,7 @@ __device__ __forceinline__ void tail32_warp(double (&c)[10][2], double (&rrp)[4]
 // SKIP: the range holds heavy items (more than p.heavy_thr ratings). They are sampled by heavy_gram32_kernel /
 // heavy_tail32_kernel, which run AFTER this kernel on the same stream; here they are gathered as if they had no ratings
 // (a prior-only draw that the heavy path overwrites), which keeps the fetch state machine contiguous.
-template <int NS, int NW, int DBG, bool BULK, int TOK, bool SKIP = false, bool PROP = false>
+template <int NS, int NW, int DBG, bool BULK, int TOK, bool SKIP = false, bool PROP = false, bool R1 = false>
 __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs p)
 {
     constexpr int WARP_BYTES = warp_bytes<NS>();
@@ -580,7 +601,7 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs
             h = (h + 1 == NS) ? 0 : h + 1;
             continue;
         }
-        tail32_warp<DBG, PROP>(c, rrp, idx, stg, sLF, srr0, p, lane);
+        tail32_warp<DBG, PROP, R1>(c, rrp, idx, stg, sLF, srr0, p, lane);
         __syncwarp();                     // the scratch is free again
         issue_stage(h);
         h = (h + 1 == NS) ? 0 : h + 1;
@@ -907,10 +928,10 @@ cudaError_t launch_cfg(bpmf_gpu_ctx *c, const StreamArgs &p, long long n)
     constexpr size_t smem = (size_t)NW * warp_bytes<NS>() + SHARED_BYTES;
     static_assert(smem <= 227 * 1024, "shared memory budget");
 #ifdef BPMF_STREAM_PROBES
-    auto kern = VER >= 3 ? items_stream32v3_kernel<NS, NW, DBG, VER == 6, (VER == 7 ? 1 : VER == 8 ? 2 : VER == 9 ? 3 : 0), VER == 12, VER == 13> : items_stream32_kernel<NS, NW>;
+    auto kern = VER >= 3 ? items_stream32v3_kernel<NS, NW, DBG, VER == 6, (VER == 7 ? 1 : VER == 8 ? 2 : VER == 9 ? 3 : 0), VER == 12, VER == 13, VER == 15> : items_stream32_kernel<NS, NW>;
 #else
     static_assert(VER >= 3, "the v2 kernel is an experiment (stream_experiments.cuh)");
-    auto kern = items_stream32v3_kernel<NS, NW, DBG, VER == 6, (VER == 7 ? 1 : VER == 8 ? 2 : VER == 9 ? 3 : 0), VER == 12, VER == 13>;
+    auto kern = items_stream32v3_kernel<NS, NW, DBG, VER == 6, (VER == 7 ? 1 : VER == 8 ? 2 : VER == 9 ? 3 : 0), VER == 12, VER == 13, VER == 15>;
 #endif
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -1138,6 +1159,7 @@ static cudaError_t launch_stream_range(bpmf_gpu_ctx *c, int side, uint32_t iter,
 #endif
     switch (cfg) {
     // 14<NS><NW>: TMA gather4 (cp.async.bulk.tensor.2d tile::gather4, UTMALDG) instead of cp.async
+    case 15220: e = launch_cfg<2, 20, 15>(c, p, n); break;       // rank-one DMMA column steps in the LDL^T (see chol3_block_column)
     case 14220: e = launch_g4<2, 20, false>(c, p, n, o.num); break;
     case 14216: e = launch_g4<2, 16, false>(c, p, n, o.num); break;
     case 14316: e = launch_g4<3, 16, false>(c, p, n, o.num); break;
