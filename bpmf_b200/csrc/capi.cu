@@ -846,21 +846,22 @@ int bpmf_gpu_reduce_stats_final(bpmf_gpu_ctx *ctx, int side)
     SideDev &s = ctx->side[side];
     if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
     CU(cudaSetDevice(ctx->device));
+    // The sums stay on the main stream (two launches of ~5 us). Running them on the auxiliary stream with the hyper draw was
+    // measured SLOWER (2 GPUs: 8.16 vs 7.99 ms per step): the persistent item kernel of the other side, enqueued right behind,
+    // fills every SM (640 threads x 96 registers leave no room for a second block), so a chain of three small kernels on the
+    // auxiliary stream does not get through before that kernel ends and the next sweep of this side waits for the draw. A
+    // single hyper kernel launched BEFORE the item kernel does get its SM first; the item kernel's CTA on that SM starts
+    // 0.17 ms late and the dynamic claims level it out.
+    CU(launch_stats_final(ctx, side, ctx->stream));
+    CU(cudaEventRecord(ctx->ev_sdone[side], ctx->stream));
     if (ctx->overlap_hyper && s.num >= 1) {
-        // Nothing on the main stream needs sum / prod / cov / norm before the next sweep of THIS side: the fixed-order sum of
-        // the block partials and hp.sample of the next iteration (which needs only this cov, c++/sample.cpp:350) run on the
-        // auxiliary stream, under the other side's sweep. ev_hyper[side] marks their completion (readers wait for it).
+        // hp.sample of the NEXT iteration needs only this cov (c++/sample.cpp:350): start it now on the auxiliary stream
         CU(cudaEventRecord(ctx->ev_stats[side], ctx->stream));
         CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_stats[side], 0));
         CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_hyper[side], 0));
-        CU(launch_stats_final(ctx, side, ctx->aux_stream));
-        CU(cudaEventRecord(ctx->ev_sdone[side], ctx->aux_stream));
         CU(launch_hyper(ctx, side, (uint32_t)(s.iter + 1), nullptr, s.cov, true));
         CU(cudaEventRecord(ctx->ev_hyper[side], ctx->aux_stream));
         s.pre_iter = s.iter + 1;
-    } else {
-        CU(launch_stats_final(ctx, side, ctx->stream));
-        CU(cudaEventRecord(ctx->ev_sdone[side], ctx->stream));
     }
     return BPMF_GPU_OK;
 }

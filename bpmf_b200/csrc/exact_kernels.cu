@@ -587,8 +587,8 @@ cudaError_t launch_peer_barrier(bpmf_gpu_ctx *c, int side)
     SideDev &s = c->side[side];
     if (s.n_stat_peers < 2 || s.stat_rank < 0) return cudaSuccess;
     // Once this rank has passed the barrier its peers may overwrite its statistics blocks (their next sweep of either side):
-    // the sums of the previous sweeps, which run on the auxiliary stream (bpmf_gpu_reduce_stats_final), must have read them.
-    // They were enqueued at least one item kernel ago, so this wait does not stall.
+    // the sums of the previous sweeps must have read them (they run on this stream today, so the wait is a formality that
+    // keeps the protocol correct wherever bpmf_gpu_reduce_stats_final puts them).
     for (int sd = 0; sd < 2; ++sd) {
         const cudaError_t ew = cudaStreamWaitEvent(c->stream, c->ev_sdone[sd], 0);
         if (ew != cudaSuccess) return ew;
