@@ -78,9 +78,9 @@ int check_device_error(bpmf_gpu_ctx *ctx)
     return fail(ctx, BPMF_GPU_ECUDA, b);
 }
 
-// per-item prior precisions (propagated posterior) are read by the PROP instantiation of the K = 32 stream kernel (sides
-// without heavy items), by the CTA-per-item kernel (any side) and by the any-K kernel
-static bool prop_on_stream(const bpmf_gpu_ctx *ctx, int side) { return ctx->K == 32 && ctx->side[side].n_heavy == 0; }
+// per-item prior precisions (propagated posterior) are read by the PROP instantiations of the K = 32 stream kernel and of
+// its heavy-item tail, by the CTA-per-item kernel and by the any-K kernel
+static bool prop_on_stream(const bpmf_gpu_ctx *ctx, int side) { (void)side; return ctx->K == 32; }
 
 int pick_variant(const bpmf_gpu_ctx *ctx, int side, int v)
 {
@@ -750,7 +750,7 @@ int bpmf_gpu_sample_items(bpmf_gpu_ctx *ctx, int side, uint32_t iter, double alp
     CU(cudaSetDevice(ctx->device));
     const int v = pick_variant(ctx, side, kernel_variant);
     if (s.propLambda && v != BPMF_GPU_KERNEL_EXACT && v != BPMF_GPU_KERNEL_BLOCK && !(v == BPMF_GPU_KERNEL_STREAM && prop_on_stream(ctx, side)))
-        return fail(ctx, BPMF_GPU_EINVAL, "a propagated posterior needs the EXACT, AUTO, BLOCK or (K = 32, no heavy items) STREAM kernel variant");
+        return fail(ctx, BPMF_GPU_EINVAL, "a propagated posterior needs the EXACT, AUTO, BLOCK (K = 16 m) or STREAM (K = 32) kernel variant");
     const int slot = (int)(ctx->ev_count % bpmf_gpu_ctx::EV_RING);
     CU(cudaEventRecord(ctx->ev0[slot], ctx->stream));
     if (v == BPMF_GPU_KERNEL_EXACT) CU(launch_items_exact(ctx, side, iter, alpha));

@@ -885,7 +885,8 @@ __global__ void __launch_bounds__(128) heavy_gram32_kernel(StreamArgs p, int nch
     for (int a = 0; a < 4; ++a) out[(20 + a) * 32] = rrp[a];
 }
 
-// one warp (one CTA) per heavy item
+// one warp (one CTA) per heavy item; PROP: per-item prior precision (the tail reads it from p.propLambda, srr0 holds hp.mu)
+template <bool PROP>
 __global__ void __launch_bounds__(32) heavy_tail32_kernel(StreamArgs p, const int *__restrict__ hv_item, const int *__restrict__ hv_first,
                                                           const double *__restrict__ partials)
 {
@@ -898,7 +899,7 @@ __global__ void __launch_bounds__(32) heavy_tail32_kernel(StreamArgs p, const in
     {
         double s = 0.0;
         for (int j = 0; j < 32; ++j) s += sLF[j * LFS + lane] * p.mu[j];
-        srr0[lane] = s;
+        srr0[lane] = PROP ? p.mu[lane] : s;
     }
     __syncwarp();
     const int h = blockIdx.x;
@@ -914,7 +915,7 @@ __global__ void __launch_bounds__(32) heavy_tail32_kernel(StreamArgs p, const in
 #pragma unroll
         for (int a = 0; a < 4; ++a) rrp[a] += in[(20 + a) * 32];
     }
-    tail32_warp<0>(c, rrp, hv_item[h], scratch, sLF, srr0, p, lane);
+    tail32_warp<0, PROP>(c, rrp, hv_item[h], scratch, sLF, srr0, p, lane);
 }
 
 #ifdef BPMF_STREAM_PROBES               // experiments that were measured slower: not part of the product build
@@ -928,10 +929,10 @@ cudaError_t launch_cfg(bpmf_gpu_ctx *c, const StreamArgs &p, long long n)
     constexpr size_t smem = (size_t)NW * warp_bytes<NS>() + SHARED_BYTES;
     static_assert(smem <= 227 * 1024, "shared memory budget");
 #ifdef BPMF_STREAM_PROBES
-    auto kern = VER >= 3 ? items_stream32v3_kernel<NS, NW, DBG, VER == 6, (VER == 7 ? 1 : VER == 8 ? 2 : VER == 9 ? 3 : 0), VER == 12, VER == 13, VER == 15> : items_stream32_kernel<NS, NW>;
+    auto kern = VER >= 3 ? items_stream32v3_kernel<NS, NW, DBG, VER == 6, (VER == 7 ? 1 : VER == 8 ? 2 : VER == 9 ? 3 : 0), VER == 12 || VER == 16, VER == 13 || VER == 16, VER == 15> : items_stream32_kernel<NS, NW>;
 #else
     static_assert(VER >= 3, "the v2 kernel is an experiment (stream_experiments.cuh)");
-    auto kern = items_stream32v3_kernel<NS, NW, DBG, VER == 6, (VER == 7 ? 1 : VER == 8 ? 2 : VER == 9 ? 3 : 0), VER == 12, VER == 13, VER == 15>;
+    auto kern = items_stream32v3_kernel<NS, NW, DBG, VER == 6, (VER == 7 ? 1 : VER == 8 ? 2 : VER == 9 ? 3 : 0), VER == 12 || VER == 16, VER == 13 || VER == 16, VER == 15>;
 #endif
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -1138,7 +1139,7 @@ static cudaError_t launch_stream_range(bpmf_gpu_ctx *c, int side, uint32_t iter,
     static const int env_cfg = [] { const char *v = getenv("BPMF_STREAM_CFG"); return v ? atoi(v) : 0; }();
     const int cfg = c->stream_cfg ? c->stream_cfg : env_cfg;
     if (s.propLambda) {                   // per-item prior precisions (propagated posterior): v3, 2 stages x 16 warps
-        e = launch_cfg<2, 16, 13>(c, p, n);
+        e = skip_heavy ? launch_cfg<2, 16, 16>(c, p, n) : launch_cfg<2, 16, 13>(c, p, n);
         c->launches++;
         return e;
     }
@@ -1197,14 +1198,15 @@ cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, doub
     p.npeers = s.npeers; p.peers = s.peers_dev;
     p.mu = s.hp.mu; p.LambdaF = s.hp.LambdaF;
     p.work_counter = s.work_counter; p.err = c->d_err; p.zero_row = c->d_zero_row; p.bulk_end = s.to; p.guided = 0; p.heavy_thr = s.heavy_thr;
-    p.propLambda = nullptr;
+    p.propLambda = s.propLambda;
     const int ch0 = s.h_heavy_first[first], ch1 = s.h_heavy_first[last];
     heavy_gram32_kernel<<<(ch1 - ch0 + 3) / 4, 128, 0, c->stream>>>(p, ch1 - ch0, s.hv_p0 + ch0, s.hv_p1 + ch0,
                                                                      s.hv_partials + (size_t)ch0 * HEAVY_PART);
     c->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    heavy_tail32_kernel<<<last - first, 32, 0, c->stream>>>(p, s.hv_item + first, s.hv_first + first, s.hv_partials);
+    if (s.propLambda) heavy_tail32_kernel<true><<<last - first, 32, 0, c->stream>>>(p, s.hv_item + first, s.hv_first + first, s.hv_partials);
+    else heavy_tail32_kernel<false><<<last - first, 32, 0, c->stream>>>(p, s.hv_item + first, s.hv_first + first, s.hv_partials);
     c->launches++;
     return cudaGetLastError();
 }

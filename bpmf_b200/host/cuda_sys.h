@@ -201,16 +201,16 @@ void CUDA_Sys::alloc_and_init()
     items_ptr = static_cast<double *>(p);
     init();
 
-    // contiguous ranges balanced on 12 + nnz per item, cut on statistics-block boundaries (every GPU reduces whole blocks
+    // contiguous ranges balanced on 64 + nnz per item (c++/assign.cpp:111 uses 10 + nnz), cut on statistics-block boundaries (every GPU reduces whole blocks
     // of the fixed decomposition, bpmf_gpu_reduce_stats_partial)
     gpu_dom.assign((size_t)ngpus + 1, 0);
     {
         const int bi = ngpus > 1 ? bpmf_gpu_stats_block_items_for(num_latent, num()) : 1;
-        const double total = 12.0 * num() + (double)nnz();
+        const double total = 64.0 * num() + (double)nnz();   // an item's tail costs ~64 ratings' worth of gather + Gram (K = 32)
         double acc = 0.0;
         int g = 1;
         for (int i = 0; i < num() && g < ngpus; ++i) {
-            acc += 12.0 + nnz(i);
+            acc += 64.0 + nnz(i);
             while (g < ngpus && acc >= total * g / ngpus) {
                 const int cut = std::min(num(), ((i + 1 + bi / 2) / bi) * bi);
                 gpu_dom[(size_t)g] = std::max(cut, gpu_dom[(size_t)g - 1]);

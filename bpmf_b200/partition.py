@@ -17,9 +17,10 @@ def split_range(n, world, rank):
     return lo, min(n, lo + chunk), chunk
 
 
-def balanced_ranges(colptr, world, fixed_cost=12, align=1):
+def balanced_ranges(colptr, world, fixed_cost=64, align=1):
     """Contiguous ranges balanced on work = fixed_cost + nnz per item, the reference's heuristic (c++/assign.cpp:111 uses
-    10 + nnz; on the GPU the per-item Cholesky / solve / RNG tail costs about 12 ratings' worth of Gram updates at K=32).
+    10 + nnz; on the B200 the per-item tail — normals, LDL^T, solves: 3.0 ms per million items — costs as much as the gather
+    and Gram of ~65 ratings, 4.7 ms per 100 M, at K=32: profiles/r01_probes.log, r02_tune_chain_probes.log).
     Returns world+1 boundaries. Used by the push exchange, which does not need equal-sized slices.
     align > 1 rounds the inner boundaries to multiples of it (the statistics-block size: every rank then reduces whole
     blocks of the fixed decomposition, bpmf_gpu_stats_block_items)."""

@@ -206,8 +206,8 @@ int bpmf_gpu_get_predictions(bpmf_gpu_ctx *ctx, int side, double *pavg, double *
  * Per-item prior precisions: Lambda is K*K x num_items (item i's K x K matrix, column-major, at Lambda + i*K*K), what
  * Sys::add_prop_posterior reads into propLambda. mu (K x num_items) is accepted for symmetry with the reference, which
  * reads and checks propMu but draws with the global hp.mu (c++/sample.cpp:285). host_Lambda == NULL removes the prior.
- * Items are then sampled by the PROP instantiation of the K = 32 stream kernel (no heavy items on the side) or by the
- * any-K kernel; KERNEL_AUTO picks. */
+ * Items are then sampled by the PROP instantiations of the K = 32 stream kernel (heavy items included), by the CTA-per-item
+ * kernel (K = 16 m) or by the any-K kernel; KERNEL_AUTO picks. */
 int bpmf_gpu_set_prop_posterior(bpmf_gpu_ctx *ctx, int side, const double *host_mu, const double *host_Lambda);
 
 /* ---- posterior aggregation of -o (c++/sample.cpp:195-199,364-368; read back for c++/bpmf.cpp:229-239) ----

@@ -649,6 +649,42 @@ def test_heavy_items_in_the_cta_per_item_kernel(gpu, K):
         ctx.close()
 
 
+def test_propagated_posterior_with_heavy_items_k32(gpu):
+    """-m / -l priors on a side WITH heavy items (K = 32): the stream kernel passes over the heavy items with the per-item
+    precisions of the others, the chunked path finishes the heavy ones with theirs (c++/sample.cpp:272-283); against the
+    oracle and against the any-K kernel."""
+    K = 32
+    rng = np.random.default_rng(28)
+    nr, nc = 6000, 300
+    rows = rng.integers(0, nr, size=20000); cols = rng.integers(0, nc, size=20000)
+    hot = rng.choice(nr, size=5000, replace=False)
+    rows = np.concatenate([rows, hot]); cols = np.concatenate([cols, np.full(5000, 11)])
+    key = rows.astype(np.int64) * nc + cols
+    _, first = np.unique(key, return_index=True)
+    rows, cols = rows[first].astype(np.int32), cols[first].astype(np.int32)
+    vals = rng.normal(3.5, 1.0, size=len(rows))
+    train = ((nr, nc), rows, cols, vals)
+    test = ((nr, nc), rows[:50].copy(), cols[:50].copy(), vals[:50].copy())
+    orc = util.make_oracle(K, train, test)
+    ctx = util.make_gpu_from_oracle(orc, K, heavy_threshold=2100)
+    _prime(orc, ctx, K, 7)
+    lam = np.stack([util.random_spd(K, 3000 + i, scale=2.0).T.reshape(-1) for i in range(nc)])
+    mu = rng.normal(size=(nc, K))
+    orc.set_prop(MOVIES, mu, lam)
+    ctx.set_prop_posterior(MOVIES, mu, lam)
+    for it in (2, 3):
+        orc.set_iter(MOVIES, it)
+        orc.sample_range(MOVIES, 0, nc)
+        ref = orc.items(MOVIES)
+        before = ctx.launch_count()
+        ctx.sample_items(MOVIES, it, 2.0, gpu.KERNEL_AUTO)
+        assert ctx.launch_count() - before == 3                  # stream kernel (SKIP + PROP), partial Grams, heavy tails
+        got = ctx.get_items(MOVIES)
+        assert np.abs(got - ref).max() <= TOL_ITEMS * max(1.0, np.abs(ref).max()), it
+        ctx.set_items(MOVIES, ref)
+    ctx.close()
+
+
 def test_many_heavy_items_skipped_in_claim_groups(gpu):
     """Zipf-like skew: ~150 heavy movies among 40 000 (a sweep large enough for 16-item claim groups), placed so that a
     whole claim group is heavy (items 32..47), the first and the last item are heavy, and the rest are scattered. Against
