@@ -231,7 +231,9 @@ int bpmf_gpu_last_items_kernel_ms(bpmf_gpu_ctx *ctx, float *ms);
 /* sum of the CUDA-event durations (ms) of the bpmf_gpu_sample_items kernels launched since the previous call
  * of this function, and how many there were (at most the last 128 are kept). Synchronises on them. */
 int bpmf_gpu_items_kernel_time(bpmf_gpu_ctx *ctx, double *total_ms, int *count);
-/* kernel tuning knob of the K == 32 stream kernel: "<version><stages><warps>", e.g. 3216; 0 = default */
+/* kernel tuning knob of the K == 32 stream kernel: "<version><stages><warps>", e.g. 3216 (16 warps), 6220 (TMA 1-D bulk-copy
+ * gather), 14220 (TMA tile::gather4 gather), 15220 (rank-one DMMA column steps); + 100000000 x q: guided claims of
+ * remaining / (q/4 x resident warps) items (q = 9: the fixed bulk / tail split); 0 = default. All bit-identical. */
 int bpmf_gpu_debug_set_tuning(bpmf_gpu_ctx *ctx, int stream_cfg);
 /* warp roles of the K == 32 stream kernel (tuning): bit w of gram_mask makes warp w of the CTA (`warps` = 16, 20 or 24 of them)
  * a Gram warp with a ring of `stages` gather stages, the others tail warps; `slots` transit slots between them.

@@ -385,6 +385,32 @@ def test_two_ranks_on_one_gpu_whole_protocol(gpu):
         c.close()
 
 
+@pytest.mark.parametrize("cfg,what", [(3216, "16 warps"), (6220, "TMA 1-D bulk copies (UBLKCP)"), (14220, "TMA tile::gather4 (UTMALDG.2D.GATHER4)"),
+                                      (14316, "gather4, 3 stages x 16 warps"), (15220, "rank-one DMMA column steps"),
+                                      (900003220, "fixed bulk / tail claims instead of guided")])
+def test_stream_kernel_variants_are_bit_identical(gpu, cfg, what):
+    """The measured alternatives of the K = 32 kernel that stay selectable in the product build: other
+    gather engines, claim schedules and the tensor-core column step compute the same bits as the default configuration —
+    ragged items, empty items, a claim group's worth of items and more, two sweeps."""
+    K = 32
+    train, test = util.synth_ratings(9000, 2500, 160000, 19, skew=0.8, empty_rows=300)
+    orc = util.make_oracle(K, train, test)
+    ctx = util.make_gpu_from_oracle(orc, K)
+    _prime(orc, ctx, K, 3)
+    state = [ctx.get_items(MOVIES), ctx.get_items(USERS)]
+    outs = []
+    for c in (0, cfg):
+        ctx.set_tuning(c)
+        ctx.set_items(MOVIES, state[MOVIES]); ctx.set_items(USERS, state[USERS])
+        for side, it in ((USERS, 2), (MOVIES, 2)):
+            ctx.sample_items(side, it, 2.0, gpu.KERNEL_STREAM)
+        outs.append((ctx.get_items(MOVIES), ctx.get_items(USERS)))
+    assert outs[0][0].tobytes() == outs[1][0].tobytes() and outs[0][1].tobytes() == outs[1][1].tobytes(), what
+    orc.set_iter(USERS, 2); orc.sample_range(USERS, 0, orc.num(USERS))
+    assert np.abs(outs[1][1] - orc.items(USERS)).max() <= TOL_ITEMS * max(1.0, np.abs(orc.items(USERS)).max())
+    ctx.close()
+
+
 def test_cholesky_failure_is_reported(gpu):
     K = 32
     train, test = util.synth_ratings(50, 40, 600, 1)
