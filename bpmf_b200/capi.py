@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libbpmf_b200.so")
+SO_PATH = os.environ.get("BPMF_B200_LIB") or os.path.join(_HERE, "libbpmf_b200.so")   # (the override: probe builds of bench_micro/)
 
 MOVIES, USERS = 0, 1
 KERNEL_AUTO, KERNEL_EXACT, KERNEL_STREAM, KERNEL_BLOCK = 0, 1, 3, 4

@@ -37,11 +37,68 @@ __device__ __forceinline__ double normal_at(const uint32_t *words, int q)
     return p.y * polar_mult(p.r2);
 }
 
-__global__ void __launch_bounds__(1024) hyper_kernel(HyperArgs a)
+// Where the kernel's work arrays live. The chain is one block's work and every step waits for the previous one, so its
+// duration is the LATENCY of its memory round trips: from global scratch (L2) the K = 32 draw takes 0.17 ms, which is the
+// critical path of a small problem's sweep (ML-100K: 0.25 ms per sweep). When they fit, the matrices (5 K^2 doubles) and the
+// random-stream arrays are placed in shared memory instead; the arithmetic and its order are untouched.
+struct HyperLayout {
+    size_t mats_off, vecs_off, piv_off, rows_off, rng_off, bytes;   // offsets into dynamic shared memory
+    bool mats, rng;
+};
+__host__ __device__ inline HyperLayout hyper_layout(int K, int nblk, size_t cap)
 {
+    HyperLayout l{};
+    const size_t KK = (size_t)K * K;
+    size_t off = 0;
+    l.mats = 5 * KK * 8 + 4 * (size_t)K * 8 + 3 * (size_t)(K + 1) * 4 + 64 <= cap;
+    if (l.mats) {
+        l.mats_off = off; off += 5 * KK * 8;
+        l.vecs_off = off; off += 4 * (size_t)K * 8;
+        l.piv_off = off; off += (((size_t)K * 4 + 15) / 16) * 16;
+        l.rows_off = off; off += ((2 * (size_t)(K + 1) * 4 + 15) / 16) * 16;
+    }
+    const size_t rng_bytes = (size_t)nblk * 16 + (((size_t)nblk * 2 + 15) / 16) * 16 + 2 * (size_t)nblk * 2 * 4;
+    l.rng = l.mats && off + rng_bytes <= cap;
+    if (l.rng) { l.rng_off = off; off += rng_bytes; }
+    l.bytes = off;
+    return l;
+}
+
+static int hyper_threads(int K) { return K <= 32 ? 256 : K <= 64 ? 512 : 1024; }   // measured: bench_micro/hyper_timing.py
+
+#ifdef BPMF_HYPER_PROF     // phase probes: clock64 of thread 0 at the phase boundaries, printed by the kernel (bench_micro/hyper_timing.py)
+#define HSTAMP(i) do { if (threadIdx.x == 0) hprof[i] = clock64(); } while (0)
+#else
+#define HSTAMP(i) do { } while (0)
+#endif
+
+__global__ void __launch_bounds__(1024) hyper_kernel(HyperArgs a, const size_t smem_cap)
+{
+#ifdef BPMF_HYPER_PROF
+    __shared__ long long hprof[16];
+#endif
+    HSTAMP(0);
     const int tid = threadIdx.x, T = blockDim.x;
     const int K = a.K, N = a.N, nblk = a.nblk;
     const int KK = K * K;
+    extern __shared__ __align__(16) unsigned char hyper_smem[];
+    const HyperLayout lay = hyper_layout(K, nblk, smem_cap);
+    double *Uout = a.LambdaU;                 // where U = LambdaU is kept while the kernel works on it
+    if (lay.mats) {
+        a.mats = reinterpret_cast<double *>(hyper_smem + lay.mats_off);
+        Uout = a.mats + 4 * (size_t)KK;
+        a.vecs = reinterpret_cast<double *>(hyper_smem + lay.vecs_off);
+        a.piv = reinterpret_cast<int *>(hyper_smem + lay.piv_off);
+        a.row_start = reinterpret_cast<int *>(hyper_smem + lay.rows_off);
+        a.row_cls = a.row_start + (K + 1);
+    }
+    if (lay.rng) {
+        unsigned char *q = hyper_smem + lay.rng_off;
+        a.words = reinterpret_cast<uint32_t *>(q); q += (size_t)nblk * 16;
+        a.acc = q; q += (((size_t)nblk * 2 + 15) / 16) * 16;
+        a.rank = reinterpret_cast<int *>(q); q += (size_t)nblk * 2 * 4;
+        a.pos_of_rank = reinterpret_cast<int *>(q);
+    }
     __shared__ int s_scan[1024];
     __shared__ int s_total[2];
     __shared__ int s_piv;
@@ -57,6 +114,7 @@ __global__ void __launch_bounds__(1024) hyper_kernel(HyperArgs a)
         a.words[4 * b + 3] = w.v[0];
     }
     __syncthreads();
+    HSTAMP(1);
     // ---- 2. acceptance of a polar attempt starting at every even word offset 2q ---------------------
     // (all consumers take words in pairs, so attempts start at even offsets; q odd = straddles two blocks,
     //  which happens after std::gamma_distribution has drawn its single uniform = half a block)
@@ -64,6 +122,7 @@ __global__ void __launch_bounds__(1024) hyper_kernel(HyperArgs a)
     for (int q = tid; q < nq; q += T)
         a.acc[q] = polar_attempt(a.words[2 * q], a.words[2 * q + 1], a.words[2 * q + 2], a.words[2 * q + 3]).ok ? 1 : 0;
     __syncthreads();
+    HSTAMP(2);
     // ---- 3. per class (q & 1): rank[q] = #accepted attempts before q, pos_of_rank[class][r] = t ------
     for (int c = 0; c < 2; ++c) {
         const int nc = (nq - c + 1) / 2;            // attempts q = 2t + c, t in [0, nc)
@@ -87,6 +146,7 @@ __global__ void __launch_bounds__(1024) hyper_kernel(HyperArgs a)
         }
         __syncthreads();
     }
+    HSTAMP(3);
     // ---- 4. sequential walk: K gamma draws with the junk / kept normal runs between them ------------
     // (WishartUnitChol, mvnormal.cpp:64-73; std::gamma_distribution = Marsaglia-Tsang,
     //  /usr/include/c++/13/bits/random.tcc:2353-2394). Only the stream POSITIONS of the kept normals are
@@ -162,6 +222,7 @@ __global__ void __launch_bounds__(1024) hyper_kernel(HyperArgs a)
     }
     __syncthreads();
     if (s_fail) return;
+    HSTAMP(4);
     // ---- 5. values of the kept normals ---------------------------------------------------------------
     double *zv = a.vecs;              // K
     for (int e = tid; e < KK; e += T) {
@@ -175,6 +236,7 @@ __global__ void __launch_bounds__(1024) hyper_kernel(HyperArgs a)
         const int c = a.row_cls[K];
         zv[t] = normal_at(a.words, 2 * a.pos_of_rank[c * nblk + a.row_start[K] + t] + c);
     }
+    HSTAMP(5);
     // ---- 6. CondNormalWishart (mvnormal.cpp:116-125) --------------------------------------------------
     const double kappa = 2.0;
     double *mu_c = a.vecs + K, *mu_m = a.vecs + 2 * K;
@@ -194,6 +256,7 @@ __global__ void __launch_bounds__(1024) hyper_kernel(HyperArgs a)
         lu[e] = ((i == j ? 1.0 : 0.0) + N * a.cov[e]) + kappa_m * (mu_m[i] * mu_m[j]);
     }
     __syncthreads();
+    HSTAMP(6);
     // LU with partial pivoting (first maximum wins, like a sequential strict-> scan)
     for (int k = 0; k < K; ++k) {
         if (tid < 32) {
@@ -228,6 +291,7 @@ __global__ void __launch_bounds__(1024) hyper_kernel(HyperArgs a)
         }
         __syncthreads();
     }
+    HSTAMP(7);
     // T_c = X^-1: thread c solves column c (not symmetrised, mvnormal.cpp:124)
     for (int c = tid; c < K; c += T) {
         for (int i = 0; i < K; ++i) bt[i * K + c] = (i == c) ? 1.0 : 0.0;
@@ -248,6 +312,7 @@ __global__ void __launch_bounds__(1024) hyper_kernel(HyperArgs a)
         for (int i = 0; i < K; ++i) L[i + c * K] = bt[i * K + c];
     }
     __syncthreads();
+    HSTAMP(8);
     // chol = T_c.llt(): lower factor from the lower triangle (mvnormal.cpp:78)
     for (int k = 0; k < K; ++k) {
         const double x = L[k + k * K];
@@ -263,8 +328,9 @@ __global__ void __launch_bounds__(1024) hyper_kernel(HyperArgs a)
         }
         __syncthreads();
     }
+    HSTAMP(9);
     // U = au * chol.matrixU()  (mvnormal.cpp:83)
-    double *U = a.LambdaU;
+    double *U = Uout;
     for (int e = tid; e < KK; e += T) {
         const int i = e % K, j = e / K;
         double s = 0.0;
@@ -273,6 +339,7 @@ __global__ void __launch_bounds__(1024) hyper_kernel(HyperArgs a)
         U[e] = s;
     }
     __syncthreads();
+    HSTAMP(10);
     // mu = U \ z / sqrt(kappa_c) + mu_c  (mvnormal.cpp:58-60), column-oriented back substitution
     for (int j = K - 1; j >= 0; --j) {
         if (tid == 0) zv[j] = zv[j] / U[j + j * K];
@@ -281,6 +348,7 @@ __global__ void __launch_bounds__(1024) hyper_kernel(HyperArgs a)
         for (int i = tid; i < j; i += T) zv[i] = zv[i] - U[i + j * K] * bj;
         __syncthreads();
     }
+    HSTAMP(11);
     const double sk = sqrt(kappa_c);
     for (int i = tid; i < K; i += T) a.mu[i] = (zv[i] / sk) + mu_c[i];
     // LambdaF = U^T U  (bpmf.h:101)
@@ -290,7 +358,17 @@ __global__ void __launch_bounds__(1024) hyper_kernel(HyperArgs a)
         double s = 0.0;
         for (int k = 0; k <= kmax; ++k) s += U[k + i * K] * U[k + j * K];
         a.LambdaF[e] = s;
+        if (U != a.LambdaU) a.LambdaU[e] = U[e];
     }
+#ifdef BPMF_HYPER_PROF
+    __syncthreads();
+    if (tid == 0) {
+        const long long e = clock64();
+        printf("hyper K=%d T=%d cycles: words %lld accept %lld scan %lld gamma-walk %lld normals %lld setup %lld LU %lld inverse %lld chol %lld U %lld backsub %lld mu+LambdaF %lld total %lld\n",
+               K, T, hprof[1] - hprof[0], hprof[2] - hprof[1], hprof[3] - hprof[2], hprof[4] - hprof[3], hprof[5] - hprof[4], hprof[6] - hprof[5],
+               hprof[7] - hprof[6], hprof[8] - hprof[7], hprof[9] - hprof[8], hprof[10] - hprof[9], hprof[11] - hprof[10], e - hprof[11], e - hprof[0]);
+    }
+#endif
 }
 
 // ahead = false: draw into hp on the context's stream. ahead = true: the draw for the NEXT iteration, on the auxiliary
@@ -308,7 +386,25 @@ cudaError_t launch_hyper(bpmf_gpu_ctx *c, int side, uint32_t iter, const double 
     a.mats = hs.mats; a.vecs = hs.vecs;
     a.mu = out.mu; a.LambdaU = out.LambdaU; a.LambdaF = out.LambdaF;
     a.err = c->d_err;
-    hyper_kernel<<<1, 1024, 0, ahead ? c->aux_stream : c->stream>>>(a);
+    static size_t cap[64];                     // per device: opt-in dynamic shared memory the kernel may use (0 = not asked yet)
+    size_t &dcap = cap[c->device & 63];
+    if (!dcap) {
+        int optin = 0;
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
+        dcap = optin > 16384 ? (size_t)optin - 10240 : 1;      // s_scan and the other static arrays of the kernel take ~4.2 KB
+        if (getenv("BPMF_HYPER_GLOBAL_SCRATCH")) dcap = 1;       // A/B: everything in global scratch, as before
+        if (dcap > 1 && cudaFuncSetAttribute(hyper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dcap) != cudaSuccess) {
+            cudaGetLastError();
+            dcap = 1;
+        }
+    }
+    const HyperLayout lay = hyper_layout(c->K, hs.nblk, dcap);
+    // threads: every step of the chain ends in a block-wide barrier, whose cost grows with the warps that take part, and at
+    // small K there is little to share out ((K - k - 1)^2 elements per elimination step)
+    static int threads_env = -1;
+    if (threads_env < 0) { const char *t = getenv("BPMF_HYPER_THREADS"); threads_env = t ? atoi(t) : 0; }
+    int threads = threads_env >= 32 && threads_env <= 1024 ? (threads_env / 32) * 32 : hyper_threads(c->K);
+    hyper_kernel<<<1, threads, lay.bytes, ahead ? c->aux_stream : c->stream>>>(a, dcap);
     c->launches++;
     return cudaGetLastError();
 }

@@ -43,6 +43,7 @@ constexpr int MBAR_OFF = META_OFF + 16;      // one mbarrier per stage (bulk-cop
 constexpr int STAGE_BYTES = META_OFF + 32;
 constexpr int LFS = 34;                     // row stride (doubles) of LambdaF in shared memory
 constexpr int SHARED_BYTES = 32 * LFS * 8 + 32 * 8;
+constexpr int TV_DEFAULT = 4 | 16;           // tail / fetch variant of the product kernels (see chol3_block_column, tail_variant)
 constexpr int CLAIM = 16;                   // consecutive items claimed per atomic
 constexpr int CLAIM_TAIL = 2;               // ... for the last ~1 % of the items, so that all warps finish together
 // NS = stages per warp, NW = warps per CTA (one CTA per SM)
@@ -162,18 +163,29 @@ __device__ __forceinline__ double fast_rcp(double p)
     return fma(r, t, r);
 }
 
-// R1 (config 15220, a measured alternative): the column step as a RANK-ONE DMMA with one-hot k-slots. Lane (g, k2) already
-// holds A~(I,KB)[g][k] and D[g][k] (k = 2 k2 + e), so A fragment (t == k2 ? c[I][e] : 0) and B fragment (t == k2 && g > k ?
-// -c[D][e] / d_k : 0) need no lane exchange at all: per column 1 shuffle + (4 - KB) DMMAs instead of 3 + (4 - KB) shuffles and
-// 2 (4 - KB) DFMAs — 368 fewer fp64 / shuffle instructions per item, bit-identical results (the three zero products add
-// exactly), but 80 more DMMAs = 864 more cycles of the fp64 pipe per item.
-template <int KB, int DBG = 0, bool R1 = false>
-__device__ __forceinline__ void chol3_block_column(double (&c)[10][2], double &myd, double &myrinv, int lane, int t)
+// The column steps of one block column of the LDL^T. The last two columns of a block are peeled off the loop: column 7 has
+// nothing to its right inside the block (only its pivot is recorded) and column 6 only column 7, so their zero-multiplier
+// shuffles / multiplies / FMAs are not issued at all (7.55 -> 7.34 ms, profiles/r02b_tune_tail_variants.log).
+// TV (tail variant) is a bit mask of measured alternatives, all bit-identical to TV == 0:
+//   1  R1: every column step as a RANK-ONE DMMA with one-hot k-slots (config 15220). Lane (g, k2) already holds A~(I,KB)[g][k]
+//      and D[g][k] (k = 2 k2 + e), so A fragment (t == k2 ? c[I][e] : 0) and B fragment (t == k2 && g > k ? -c[D][e] / d_k : 0)
+//      need no lane exchange at all: per column 1 shuffle + (4 - KB) DMMAs instead of 3 + (4 - KB) shuffles and 2 (4 - KB)
+//      DFMAs — 368 fewer fp64 / shuffle instructions per item (the three zero products add exactly), but 80 more DMMAs =
+//      864 more cycles of the fp64 pipe per item: measured equal (profiles/r02_tune_rank1_dmma.log).
+//   8  R1 for the block columns KB >= 2 only (config 19220): equal again (7.355 vs 7.338 ms)
+//   2  pivots and their reciprocals go to shared memory (one 16-byte store per column by lane 0) instead of being picked up by
+//      the lane that owns them with a compare + four selects per column; the lanes read them back when they need them
+//   4  the panel blocks of the unit-lower factor are stored right after the trailing update's B fragments are formed: those
+//      ARE -Lu (12 multiplies fewer per item); the factor is kept NEGATED in shared memory
+template <int KB, int DBG = 0, int TV = 0>
+__device__ __forceinline__ void chol3_block_column(double (&c)[10][2], double &myd, double &myrinv, int lane, int t, double2 *pr, double *Lp)
 {
     constexpr int D = blk(KB, KB);
+    constexpr bool R1 = (TV & 1) || ((TV & 8) && KB >= 2);
+    constexpr bool PEEL = true, PR = (TV & 2) != 0;
+    const int g = lane >> 2;
     const double p_probe = c[D][0] + 3.0;    // DBG & 64 (timing probe, wrong results): reciprocals that do not depend on the chain
     if (R1) {
-        const int g = lane >> 2;
 #pragma unroll 1
         for (int k2 = 0; k2 < 4; ++k2) {
             const bool mine = (t == k2);
@@ -182,7 +194,9 @@ __device__ __forceinline__ void chol3_block_column(double (&c)[10][2], double &m
                 const int k = 2 * k2 + e;
                 const double p = __shfl_sync(FULL, c[D][e], 4 * k + k2);       // pivot d_k: lane (g = k, t = k2), register e
                 const double rinv = fast_rcp((DBG & 64) ? p_probe + k : p);
-                if (lane == 8 * KB + k) { myd = p; myrinv = rinv; }
+                if (PR) { if (lane == 0) pr[8 * KB + k] = make_double2(p, rinv); }
+                else if (lane == 8 * KB + k) { myd = p; myrinv = rinv; }
+                if ((TV & 8) && k == 7) break;                                 // nothing right of column 7 (k2 == 3, e == 1: the last step)
                 const double bf = (mine && g > k) ? -(c[D][e] * rinv) : 0.0;   // B[k2][n = g] = -D[n][k] / d_k below the pivot
 #pragma unroll
                 for (int I = KB; I < 4; ++I) {
@@ -193,7 +207,7 @@ __device__ __forceinline__ void chol3_block_column(double (&c)[10][2], double &m
         }
     } else {
 #pragma unroll 1
-    for (int k2 = 0; k2 < 4; ++k2) {
+    for (int k2 = 0; k2 < (PEEL ? 3 : 4); ++k2) {
         const int qsrc = (lane & ~3) | k2;
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
@@ -206,7 +220,8 @@ __device__ __forceinline__ void chol3_block_column(double (&c)[10][2], double &m
 #pragma unroll
             for (int I = KB; I < 4; ++I) a[I] = __shfl_sync(FULL, c[blk(I, KB)][e], qsrc);   // a[8I+g][k]
             const double rinv = fast_rcp((DBG & 64) ? p_probe + k : p);
-            if (lane == 8 * KB + k) { myd = p; myrinv = rinv; }
+            if (PR) { if (lane == 0) pr[8 * KB + k] = make_double2(p, rinv); }
+            else if (lane == 8 * KB + k) { myd = p; myrinv = rinv; }
             bl0 = (2 * t > k) ? -(bl0 * rinv) : 0.0;                        // zero where this lane's column is not right of k
             bl1 = (2 * t + 1 > k) ? -(bl1 * rinv) : 0.0;
 #pragma unroll
@@ -216,19 +231,53 @@ __device__ __forceinline__ void chol3_block_column(double (&c)[10][2], double &m
             }
         }
     }
+    if (PEEL) {
+        // column 6 (k2 = 3, e = 0) updates column 7 only: lanes t == 3, register 1
+        {
+            const double p = __shfl_sync(FULL, c[D][0], 4 * 6 + 3);
+            double bl1 = __shfl_sync(FULL, c[D][0], 4 * 7 + 3);              // D[7][6]
+            double a[4];
+#pragma unroll
+            for (int I = KB; I < 4; ++I) a[I] = __shfl_sync(FULL, c[blk(I, KB)][0], lane | 3);   // a[8I+g][6]
+            const double rinv = fast_rcp((DBG & 64) ? p_probe + 6 : p);
+            if (PR) { if (lane == 0) pr[8 * KB + 6] = make_double2(p, rinv); }
+            else if (lane == 8 * KB + 6) { myd = p; myrinv = rinv; }
+            bl1 = (t == 3) ? -(bl1 * rinv) : 0.0;
+#pragma unroll
+            for (int I = KB; I < 4; ++I) c[blk(I, KB)][1] = fma(a[I], bl1, c[blk(I, KB)][1]);
+        }
+        // column 7: only its pivot
+        {
+            const double p = __shfl_sync(FULL, c[D][1], 4 * 7 + 3);
+            const double rinv = fast_rcp((DBG & 64) ? p_probe + 7 : p);
+            if (PR) { if (lane == 0) pr[8 * KB + 7] = make_double2(p, rinv); }
+            else if (lane == 8 * KB + 7) { myd = p; myrinv = rinv; }
+        }
+    }
     }
     // trailing update A(I,J) -= A~(I,KB) D^-1 A~(J,KB)^T for KB < J <= I on the tensor cores
     // The sum over the block's eight columns may run in any order: DMMA number e takes column 2t + e in its k-slot t, so
     // the accumulator registers of A~(I,KB) and A~(J,KB) ARE the A and B fragments (lane 4g+t holds [g][2t + e]) and no
     // lane exchange is needed.
+    if (PR) __syncwarp();                  // the block column's eight (pivot, reciprocal) pairs are in shared memory
     if (KB < 3) {
         double nrv[2], bs[4][2];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) nrv[e] = -__shfl_sync(FULL, myrinv, 8 * KB + 2 * t + e);   // -1 / d of column 2t + e
+        for (int e = 0; e < 2; ++e) nrv[e] = PR ? -pr[8 * KB + 2 * t + e].y : -__shfl_sync(FULL, myrinv, 8 * KB + 2 * t + e);   // -1 / d of column 2t + e
 #pragma unroll
         for (int J = KB + 1; J < 4; ++J)
 #pragma unroll
             for (int e = 0; e < 2; ++e) bs[J][e] = c[blk(J, KB)][e] * nrv[e];
+        if (TV & 4) {
+            // bs[J][e] = -Lu(8J + g, k) for column k = 8 KB + 2t + e: the factor's panel blocks, stored negated
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int k = 8 * KB + 2 * t + e;
+                double *lq = Lp + (31 * k - ((k * (k - 1)) >> 1)) + g - k - 1;
+#pragma unroll
+                for (int J = KB + 1; J < 4; ++J) lq[8 * J] = bs[J][e];
+            }
+        }
 #pragma unroll
         for (int I = KB + 1; I < 4; ++I)
 #pragma unroll
@@ -244,7 +293,7 @@ __device__ __forceinline__ void chol3_block_column(double (&c)[10][2], double &m
 // PROP: the item has its own prior precision (propagated posterior, sample.cpp:272-283): LambdaF is read from
 // p.propLambda instead of shared memory, and rr starts from LambdaF_i * hp.mu with the GLOBAL hp.mu (quirk Q5), which the
 // caller keeps in srr0.
-template <int DBG, bool PROP = false, bool R1 = false>
+template <int DBG, bool PROP = false, int TV = 0>
 __device__ __forceinline__ void tail32_warp(double (&c)[10][2], double (&rrp)[4], const int idx, unsigned char *stg, const double *sLF,
                                             const double *srr0, const StreamArgs &p, const int lane, unsigned char *vecs = nullptr)
 {
@@ -259,6 +308,8 @@ __device__ __forceinline__ void tail32_warp(double (&c)[10][2], double (&rrp)[4]
     const int g = lane >> 2, t = lane & 3;
     double *zy = reinterpret_cast<double *>(vecs), *zr = reinterpret_cast<double *>(vecs + 256);
     double *wb = reinterpret_cast<double *>(vecs + 512), *Lp = reinterpret_cast<double *>(stg);
+    double2 *prv = reinterpret_cast<double2 *>(vecs);     // TV & 2: (d_k, 1 / d_k) pairs, over zy | zr once z has been formed
+    constexpr bool PR = (TV & 2) != 0, NEGL = (TV & 4) != 0;
     // the K normals of this item: rng_set_pos((idx+1)*K*(iter+1)) (sample.cpp:266). Accepted polar attempts are numbered
     // by ballot; lane n then finishes normal n (one log / sqrt / divide per lane instead of one per attempt).
     if (!(DBG & 8)) {
@@ -287,6 +338,7 @@ __device__ __forceinline__ void tail32_warp(double (&c)[10][2], double (&rrp)[4]
     const double z = (DBG & 8) ? 0.25 * lane : __dmul_rn(zy[lane], polar_mult(zr[lane]));
     double bb = wb[lane];
     if (PROP) bb += rr0;
+    if (PR) __syncwarp();                 // zy | zr are free: the pivots go there
     // MM = LambdaF + alpha * G (sample.cpp:297-298), in place in the accumulator layout
 #pragma unroll
     for (int I = 0; I < 4; ++I)
@@ -299,12 +351,14 @@ __device__ __forceinline__ void tail32_warp(double (&c)[10][2], double (&rrp)[4]
     double myd = 1.0, myrinv = 1.0;
     bool ok = true;
     if (!(DBG & 16)) {
-        chol3_block_column<0, DBG, R1>(c, myd, myrinv, lane, t);
-        chol3_block_column<1, DBG, R1>(c, myd, myrinv, lane, t);
-        chol3_block_column<2, DBG, R1>(c, myd, myrinv, lane, t);
-        chol3_block_column<3, DBG, R1>(c, myd, myrinv, lane, t);
+        chol3_block_column<0, DBG, TV>(c, myd, myrinv, lane, t, prv, Lp);
+        chol3_block_column<1, DBG, TV>(c, myd, myrinv, lane, t, prv, Lp);
+        chol3_block_column<2, DBG, TV>(c, myd, myrinv, lane, t, prv, Lp);
+        chol3_block_column<3, DBG, TV>(c, myd, myrinv, lane, t, prv, Lp);
+        if (PR) { const double2 m = prv[lane]; myd = m.x; myrinv = m.y; }
     } else {
         myd = c[0][0] + 2.0; myrinv = fast_rcp(myd);
+        if (PR) { prv[lane] = make_double2(myd, myrinv); __syncwarp(); }
     }
     // Eigen LLT: a pivot <= 0 -> "Cholesky failed". Lane k holds d_k; a bad pivot poisons what follows (NaN also fails)
     ok = __all_sync(FULL, myd > 0.0) || (DBG & 64);   // (the probe's factorization is garbage: keep the solves in the timing)
@@ -316,11 +370,15 @@ __device__ __forceinline__ void tail32_warp(double (&c)[10][2], double (&rrp)[4]
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int k = 8 * J + 2 * t + e;
-                const double rk = __shfl_sync(FULL, myrinv, k);
+                const double rk = PR ? prv[k].y : __shfl_sync(FULL, myrinv, k);
                 double *lq = Lp + (31 * k - ((k * (k - 1)) >> 1)) + g - k - 1;
+                if (NEGL) {               // the panel blocks are in place already (chol3_block_column), negated like these
+                    if (g > 2 * t + e) lq[8 * J] = c[blk(J, J)][e] * -rk;
+                } else {
 #pragma unroll
                 for (int I = J; I < 4; ++I)
                     if (I > J || g > 2 * t + e) lq[8 * I] = c[blk(I, J)][e] * rk;
+                }
             }
     }
     // reset the accumulators for the next item
@@ -337,7 +395,7 @@ __device__ __forceinline__ void tail32_warp(double (&c)[10][2], double (&rrp)[4]
 #pragma unroll
             for (int k = 0; k < 31; ++k) {
                 const double yk = __shfl_sync(FULL, bb, k);
-                if (lane > k) bb = fma(-lf[col_off1(k) - k], yk, bb);
+                if (lane > k) bb = NEGL ? fma(lf[col_off1(k) - k], yk, bb) : fma(-lf[col_off1(k) - k], yk, bb);
             }
         }
         double yv = fma(bb, myrinv, myrs * z);             // D^-1 Lu^-1 b + D^(-1/2) z
@@ -346,13 +404,13 @@ __device__ __forceinline__ void tail32_warp(double (&c)[10][2], double (&rrp)[4]
 #pragma unroll
             for (int i = 31; i >= 1; --i) {
                 const double xi = __shfl_sync(FULL, yv, i);
-                if (lane < i) yv = fma(-lb[i], xi, yv);
+                if (lane < i) yv = NEGL ? fma(lb[i], xi, yv) : fma(-lb[i], xi, yv);
             }
         }
         // items().col(idx) = rr (sample.cpp:324); push to the peer replicas (replaces send_item, :370)
         p.items[(size_t)idx * 32 + lane] = yv;
-        for (int pr = 0; pr < p.npeers; ++pr) {
-            double *dst = p.peers[pr];
+        for (int q = 0; q < p.npeers; ++q) {
+            double *dst = p.peers[q];
             if (dst && dst != p.items) dst[(size_t)idx * 32 + lane] = yv;
         }
     } else if (lane == 0) {           // THROWERROR("Cholesky failed") (sample.cpp:308): reported through the error word
@@ -376,7 +434,7 @@ __device__ __forceinline__ void tail32_warp(double (&c)[10][2], double (&rrp)[4]
 // SKIP: the range holds heavy items (more than p.heavy_thr ratings). They are sampled by heavy_gram32_kernel /
 // heavy_tail32_kernel, which run AFTER this kernel on the same stream; here they are gathered as if they had no ratings
 // (a prior-only draw that the heavy path overwrites), which keeps the fetch state machine contiguous.
-template <int NS, int NW, int DBG, bool BULK, int TOK, bool SKIP = false, bool PROP = false, bool R1 = false>
+template <int NS, int NW, int DBG, bool BULK, int TOK, bool SKIP = false, bool PROP = false, int TV = 0>
 __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs p)
 {
     constexpr int WARP_BYTES = warp_bytes<NS>();
@@ -423,8 +481,12 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs
         __syncwarp();
     }
 
+    // TV & 16: lane 16 h + i (i < 8) holds the index / value of the stage's row 2 i + h, the row its half-warp copies in step i,
+    // so that the shuffle of step i names its source lane by an immediate (width 16) instead of a per-lane register
+    constexpr bool FPERM = (TV & 16) != 0 && !BULK;
+    const int rowl = FPERM ? 2 * (lane & 7) + (lane >> 4) : (lane & 15);
     auto load_next = [&]() {
-        const int q = f_pos + (lane & 15);
+        const int q = f_pos + rowl;
         n_idx = 0; n_w = 0.0;
         if (q < g_end) {                  // entries past the item's end but inside the group are loaded and never used
             n_idx = __ldg(g_idx + q);
@@ -494,15 +556,28 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs
                 bulk_g2s(st, p.zero_row, 256u, mbar);
             }
         } else {
+            if (FPERM && n == SR) {       // a full stage: no predicates
+#pragma unroll
+                for (int i = 0; i < SR / 2; ++i) {
+                    const unsigned j = (unsigned)__shfl_sync(FULL, n_idx, i, 16);
+                    unsigned long long src;
+                    asm("mad.wide.u32 %0, %1, 256, %2;" : "=l"(src) : "r"(j), "l"(src_lane));
+                    if (!(DBG & 4)) cp_async16(st + 2 * i * ROWB, reinterpret_cast<const void *>(src), 16);
+                }
+            } else
 #pragma unroll
             for (int i = 0; i < SR / 2; ++i) {
-                const unsigned j = (unsigned)__shfl_sync(FULL, n_idx, 2 * i + half);
+                const unsigned j = (unsigned)(FPERM ? __shfl_sync(FULL, n_idx, i, 16) : __shfl_sync(FULL, n_idx, 2 * i + half));
                 // rows past the item's end are zero-filled (src-size 0 reads nothing; j is still a valid row)
-                if (!(DBG & 4)) cp_async16(st + 2 * i * ROWB, src_lane + (size_t)j * 256, (2 * i < nn) ? 16 : 0);
+                // one 64-bit multiply-add per source address (IMAD.WIDE.U32 with the lane's base as the addend; written out,
+                // the compiler makes it four instructions: 7.69 -> 7.55 ms)
+                unsigned long long src;
+                asm("mad.wide.u32 %0, %1, 256, %2;" : "=l"(src) : "r"(j), "l"(src_lane));
+                if (!(DBG & 4)) cp_async16(st + 2 * i * ROWB, reinterpret_cast<const void *>(src), (2 * i < nn) ? 16 : 0);
             }
         }
         // rr weight (v - mean_rating) * alpha (sample.cpp:255)
-        if (lane < SR) reinterpret_cast<double *>(stg + W_OFF)[lane] = (lane < n) ? (n_w - p.mean_rating) * p.alpha : 0.0;
+        if (FPERM ? (lane & 8) == 0 : lane < SR) reinterpret_cast<double *>(stg + W_OFF)[rowl] = (rowl < n) ? (n_w - p.mean_rating) * p.alpha : 0.0;
         const int last = (f_pos + n == f_end);
         if (lane == 0) *reinterpret_cast<int4 *>(stg + META_OFF) = make_int4(n, g_base + f_it, f_pos == f_start, last);
         if (!BULK) cp_async_commit();
@@ -601,7 +676,7 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs
             h = (h + 1 == NS) ? 0 : h + 1;
             continue;
         }
-        tail32_warp<DBG, PROP, R1>(c, rrp, idx, stg, sLF, srr0, p, lane);
+        tail32_warp<DBG, PROP, TV>(c, rrp, idx, stg, sLF, srr0, p, lane);
         __syncwarp();                     // the scratch is free again
         issue_stage(h);
         h = (h + 1 == NS) ? 0 : h + 1;
@@ -915,7 +990,7 @@ __global__ void __launch_bounds__(32) heavy_tail32_kernel(StreamArgs p, const in
 #pragma unroll
         for (int a = 0; a < 4; ++a) rrp[a] += in[(20 + a) * 32];
     }
-    tail32_warp<0, PROP>(c, rrp, hv_item[h], scratch, sLF, srr0, p, lane);
+    tail32_warp<0, PROP, TV_DEFAULT & 4>(c, rrp, hv_item[h], scratch, sLF, srr0, p, lane);
 }
 
 #ifdef BPMF_STREAM_PROBES               // experiments that were measured slower: not part of the product build
@@ -923,16 +998,24 @@ __global__ void __launch_bounds__(32) heavy_tail32_kernel(StreamArgs p, const in
 #include "../../bench_micro/stream_roles.cuh"
 #endif
 
+// The TV mask (chol3_block_column, issue_stage) of a kernel version. The product kernels (3, 12, 13, 16) run TV = 4 | 16:
+// panel blocks of the factor from the trailing update's B fragments, stage indices held by the lanes that copy their rows
+// (7.33 -> 7.19 ms, profiles/r02b_tune_tail_variants2.log). 24 = neither, the others are the measured alternatives.
+constexpr int tail_variant(int VER)
+{
+    return VER == 15 ? (TV_DEFAULT | 1) : VER == 17 ? (TV_DEFAULT | 2) : VER == 19 ? (TV_DEFAULT | 8) : VER == 18 ? 16 : VER == 21 ? 4 : VER == 24 ? 0 : TV_DEFAULT;
+}
+
 template <int NS, int NW, int VER, int DBG = 0>
 cudaError_t launch_cfg(bpmf_gpu_ctx *c, const StreamArgs &p, long long n)
 {
     constexpr size_t smem = (size_t)NW * warp_bytes<NS>() + SHARED_BYTES;
     static_assert(smem <= 227 * 1024, "shared memory budget");
 #ifdef BPMF_STREAM_PROBES
-    auto kern = VER >= 3 ? items_stream32v3_kernel<NS, NW, DBG, VER == 6, (VER == 7 ? 1 : VER == 8 ? 2 : VER == 9 ? 3 : 0), VER == 12 || VER == 16, VER == 13 || VER == 16, VER == 15> : items_stream32_kernel<NS, NW>;
+    auto kern = VER >= 3 ? items_stream32v3_kernel<NS, NW, DBG, VER == 6, (VER == 7 ? 1 : VER == 8 ? 2 : VER == 9 ? 3 : 0), VER == 12 || VER == 16, VER == 13 || VER == 16, tail_variant(VER)> : items_stream32_kernel<NS, NW>;
 #else
     static_assert(VER >= 3, "the v2 kernel is an experiment (stream_experiments.cuh)");
-    auto kern = items_stream32v3_kernel<NS, NW, DBG, VER == 6, (VER == 7 ? 1 : VER == 8 ? 2 : VER == 9 ? 3 : 0), VER == 12 || VER == 16, VER == 13 || VER == 16, VER == 15>;
+    auto kern = items_stream32v3_kernel<NS, NW, DBG, VER == 6, (VER == 7 ? 1 : VER == 8 ? 2 : VER == 9 ? 3 : 0), VER == 12 || VER == 16, VER == 13 || VER == 16, tail_variant(VER)>;
 #endif
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -1161,6 +1244,11 @@ static cudaError_t launch_stream_range(bpmf_gpu_ctx *c, int side, uint32_t iter,
     switch (cfg) {
     // 14<NS><NW>: TMA gather4 (cp.async.bulk.tensor.2d tile::gather4, UTMALDG) instead of cp.async
     case 15220: e = launch_cfg<2, 20, 15>(c, p, n); break;       // rank-one DMMA column steps in the LDL^T (see chol3_block_column)
+    case 17220: e = launch_cfg<2, 20, 17>(c, p, n); break;       // + pivots and reciprocals through shared memory (7.38 vs 7.33 ms)
+    case 19220: e = launch_cfg<2, 20, 19>(c, p, n); break;       // + rank-one DMMA column steps for the block columns 2 and 3 (7.355 vs 7.338 ms)
+    case 18220: e = launch_cfg<2, 20, 18>(c, p, n); break;       // without the factor's panel blocks from the trailing update's B fragments
+    case 21220: e = launch_cfg<2, 20, 21>(c, p, n); break;       // without the permuted ownership of the stage's indices
+    case 24220: e = launch_cfg<2, 20, 24>(c, p, n); break;       // without either (7.33 ms)
     case 14220: e = launch_g4<2, 20, false>(c, p, n, o.num); break;
     case 14216: e = launch_g4<2, 16, false>(c, p, n, o.num); break;
     case 14316: e = launch_g4<3, 16, false>(c, p, n, o.num); break;
