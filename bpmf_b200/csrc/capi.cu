@@ -152,6 +152,7 @@ int bpmf_gpu_create(bpmf_gpu_ctx **out, int device, int num_latent)
         if ((e = cudaEventCreateWithFlags(&ctx->ev_stats[sd], cudaEventDisableTiming)) != cudaSuccess) return bail(e);
         if ((e = cudaEventCreateWithFlags(&ctx->ev_hyper[sd], cudaEventDisableTiming)) != cudaSuccess) return bail(e);
         if ((e = cudaEventCreateWithFlags(&ctx->ev_sdone[sd], cudaEventDisableTiming)) != cudaSuccess) return bail(e);
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_items[sd], cudaEventDisableTiming)) != cudaSuccess) return bail(e);
     }
     if ((e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
     if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
@@ -159,6 +160,10 @@ int bpmf_gpu_create(bpmf_gpu_ctx **out, int device, int num_latent)
         if ((e = cudaEventCreateWithFlags(&ctx->ev_part[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming)) != cudaSuccess) return bail(e);
     ctx->overlap_hyper = getenv("BPMF_NO_HYPER_OVERLAP") == nullptr;
+    // BPMF_STATS_MAIN: the reductions of a sweep on the main stream behind its item kernel (rounds 1 - 2a), all SMs to the item kernels
+    // (K == 32 only: the any-K partial kernel is a wide grid that would take the SMs of the next item kernel in the gap between two)
+    ctx->stats_aux = ctx->overlap_hyper && num_latent == 32 && getenv("BPMF_STATS_MAIN") == nullptr;
+    if (const char *r = getenv("BPMF_RESERVE_SMS")) ctx->reserve_sms = atoi(r) < 0 ? 0 : atoi(r);
     *out = ctx;
     return BPMF_GPU_OK;
 }
@@ -178,6 +183,7 @@ int bpmf_gpu_destroy(bpmf_gpu_ctx *ctx)
         if (ctx->ev_stats[sd]) cudaEventDestroy(ctx->ev_stats[sd]);
         if (ctx->ev_hyper[sd]) cudaEventDestroy(ctx->ev_hyper[sd]);
         if (ctx->ev_sdone[sd]) cudaEventDestroy(ctx->ev_sdone[sd]);
+        if (ctx->ev_items[sd]) cudaEventDestroy(ctx->ev_items[sd]);
     }
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -208,7 +214,17 @@ int bpmf_gpu_sync(bpmf_gpu_ctx *ctx)
 {
     if (!ctx) return BPMF_GPU_EINVAL;
     CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->aux_stream));   // the reductions / next hyper draw of the last sweeps
     return check_device_error(ctx);
+}
+
+// Host-driven changes of a context's device state (latent matrices, ranges, peers, ...) wait for the reductions that may
+// still be reading it on the auxiliary stream.
+static int quiesce_aux(bpmf_gpu_ctx *ctx)
+{
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->aux_stream));
+    return BPMF_GPU_OK;
 }
 
 static int setup_side(bpmf_gpu_ctx *ctx, SideDev &s, const int64_t *colptr);
@@ -297,9 +313,9 @@ static int setup_side(bpmf_gpu_ctx *ctx, SideDev &s, const int64_t *colptr)
     CU(cudaMemset(s.prod, 0, sizeof(double) * KK));
     CU(cudaMemset(s.cov, 0, sizeof(double) * KK));
     CU(cudaMemset(s.norm, 0, sizeof(double)));
-    // + MAX_PEERS arrival words of the cross-GPU barrier (peer_barrier_kernel) behind the partials
-    CU(cudaMalloc(&s.partials, sizeof(double) * ((size_t)STATS_BLOCKS * (KK + K + 1) + MAX_PEERS)));
-    CU(cudaMemset(s.partials, 0, sizeof(double) * ((size_t)STATS_BLOCKS * (KK + K + 1) + MAX_PEERS)));
+    // + 2 x MAX_PEERS arrival words of the cross-GPU barriers (peer_barrier_kernel, one set per kind) behind the partials
+    CU(cudaMalloc(&s.partials, sizeof(double) * ((size_t)STATS_BLOCKS * (KK + K + 1) + 2 * MAX_PEERS)));
+    CU(cudaMemset(s.partials, 0, sizeof(double) * ((size_t)STATS_BLOCKS * (KK + K + 1) + 2 * MAX_PEERS)));
     CU(cudaMalloc(&s.stat_peers_dev, sizeof(double *) * MAX_PEERS));
     CU(cudaMemset(s.stat_peers_dev, 0, sizeof(double *) * MAX_PEERS));
     CU(cudaMalloc(&s.work_counter, 2 * sizeof(unsigned int)));
@@ -427,6 +443,7 @@ int bpmf_gpu_load_coo(bpmf_gpu_ctx *ctx, int num_rows, int num_cols, int64_t nnz
     if (!ctx || num_rows < 1 || num_cols < 1 || nnz < 1 || !row || !col || !val) return BPMF_GPU_EINVAL;
     if (nnz > 0x7fffffffll) return fail(ctx, BPMF_GPU_EINVAL, "more than 2^31 - 1 entries");   // int storage indices, like Eigen's
     CU(cudaSetDevice(ctx->device));
+    { const int qrc = quiesce_aux(ctx); if (qrc) return qrc; }
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaStreamSynchronize(ctx->aux_stream));
     DevCoo d;
@@ -526,6 +543,7 @@ int bpmf_gpu_bind_items(bpmf_gpu_ctx *ctx, int side, double *dev_items)
     SideDev &s = ctx->side[side];
     if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
     CU(cudaSetDevice(ctx->device));
+    { const int qrc = quiesce_aux(ctx); if (qrc) return qrc; }
     double *target = dev_items ? dev_items : s.items_own;
     if (target != s.items) {
         CU(cudaMemcpyAsync(target, s.items, sizeof(double) * (size_t)ctx->K * s.num, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -541,6 +559,7 @@ int bpmf_gpu_set_peers(bpmf_gpu_ctx *ctx, int side, int npeers, double *const *d
     SideDev &s = ctx->side[side];
     if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
     CU(cudaSetDevice(ctx->device));
+    { const int qrc = quiesce_aux(ctx); if (qrc) return qrc; }
     double *tmp[MAX_PEERS] = {nullptr};
     for (int i = 0; i < npeers; ++i) tmp[i] = dev_peer_items[i];
     CU(cudaMemcpyAsync(s.peers_dev, tmp, sizeof(tmp), cudaMemcpyHostToDevice, ctx->stream));
@@ -611,6 +630,7 @@ int bpmf_gpu_set_items(bpmf_gpu_ctx *ctx, int side, const double *host_items)
     SideDev &s = ctx->side[side];
     if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
     CU(cudaSetDevice(ctx->device));
+    { const int qrc = quiesce_aux(ctx); if (qrc) return qrc; }
     CU(cudaMemcpyAsync(s.items, host_items, sizeof(double) * (size_t)ctx->K * s.num, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return BPMF_GPU_OK;
@@ -632,6 +652,7 @@ int bpmf_gpu_set_items_range(bpmf_gpu_ctx *ctx, int side, int from, int to, cons
     SideDev &s = ctx->side[side];
     if (!s.loaded || from < 0 || to < from || to > s.num) return fail(ctx, BPMF_GPU_EINVAL, "bad range");
     CU(cudaSetDevice(ctx->device));
+    { const int qrc = quiesce_aux(ctx); if (qrc) return qrc; }
     const size_t K = (size_t)ctx->K;
     CU(cudaMemcpyAsync(s.items + K * from, host_items + K * from, sizeof(double) * K * (to - from), cudaMemcpyHostToDevice, ctx->stream));
     return BPMF_GPU_OK;
@@ -654,6 +675,7 @@ int bpmf_gpu_push_range(bpmf_gpu_ctx *ctx, int side, int from, int to)
     SideDev &s = ctx->side[side];
     if (!s.loaded || from < 0 || to < from || to > s.num) return fail(ctx, BPMF_GPU_EINVAL, "bad range");
     CU(cudaSetDevice(ctx->device));
+    { const int qrc = quiesce_aux(ctx); if (qrc) return qrc; }
     const size_t K = (size_t)ctx->K;
     for (int q = 0; q < s.npeers; ++q) {
         double *dst = s.peers_host[q];
@@ -805,6 +827,7 @@ int bpmf_gpu_set_stats_peers(bpmf_gpu_ctx *ctx, int side, int npeers, double *co
     SideDev &s = ctx->side[side];
     if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
     CU(cudaSetDevice(ctx->device));
+    { const int qrc = quiesce_aux(ctx); if (qrc) return qrc; }
     double *tmp[MAX_PEERS] = {nullptr};
     for (int i = 0; i < npeers; ++i) tmp[i] = dev_peer_partials[i];
     CU(cudaMemcpyAsync(s.stat_peers_dev, tmp, sizeof(tmp), cudaMemcpyHostToDevice, ctx->stream));
@@ -822,7 +845,9 @@ int bpmf_gpu_peer_barrier(bpmf_gpu_ctx *ctx, int side)
     if (!ctx || !side_ok(side)) return BPMF_GPU_EINVAL;
     if (!ctx->side[side].loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
     CU(cudaSetDevice(ctx->device));
-    CU(launch_peer_barrier(ctx, side));
+    // once this rank has passed, its peers may overwrite its statistics blocks: the sums that read them must be done
+    for (int sd = 0; sd < 2; ++sd) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_sdone[sd], 0));
+    CU(launch_peer_barrier(ctx, side, BARRIER_LATENTS, ctx->stream));
     return BPMF_GPU_OK;
 }
 
@@ -833,7 +858,7 @@ int bpmf_gpu_reduce_stats_partial(bpmf_gpu_ctx *ctx, int side)
     if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_sdone[side], 0));   // the previous sums of this side (auxiliary stream) have read the partials
-    const cudaError_t e = launch_stats_partial(ctx, side);
+    const cudaError_t e = launch_stats_partial(ctx, side, ctx->stream);
     if (e == cudaErrorInvalidValue && s.n_stat_peers > 0)
         return fail(ctx, BPMF_GPU_EINVAL, "with statistics peers the item range must be aligned to bpmf_gpu_stats_block_items");
     CU(e);
@@ -866,14 +891,55 @@ int bpmf_gpu_reduce_stats_final(bpmf_gpu_ctx *ctx, int side)
     return BPMF_GPU_OK;
 }
 
+// The reductions of a sweep on the MAIN stream, behind its item kernel (the host-destination paths, BPMF_STATS_MAIN).
 // With statistics peers set this is a COLLECTIVE of the ranks: own blocks to every rank, the cross-GPU barrier (which also
 // orders the latent columns the item kernels pushed), the fixed-order sum.
-int bpmf_gpu_reduce_stats(bpmf_gpu_ctx *ctx, int side)
+static int reduce_stats_main(bpmf_gpu_ctx *ctx, int side)
 {
     int rc = bpmf_gpu_reduce_stats_partial(ctx, side);
     if (rc) return rc;
     if (ctx->side[side].n_stat_peers > 1 && (rc = bpmf_gpu_peer_barrier(ctx, side))) return rc;
     return bpmf_gpu_reduce_stats_final(ctx, side);
+}
+
+// The reductions of a sweep (c++/sample.cpp:359-362,379-384, and across GPUs c++/mpi_common.h:44-50). Nothing on the main
+// stream needs them before the NEXT sweep of this side, so the whole chain — block partials of the own items (stored into
+// every rank's buffer), the cross-GPU barrier of the statistics, the fixed-order sums, cov, and hp.sample of the next
+// iteration — runs on the auxiliary stream, under the other side's sweep, on the SMs the item kernels leave free
+// (item_sms). The main stream only gets the barrier that orders the pushed latent columns (multi-GPU).
+//   Hazards against the peers' stores into this rank's buffers: (1) a peer's next sweep of this side stores statistics
+// blocks into `partials` that the sums of THIS sweep read: the peer gets there only after a later latents barrier of the
+// OTHER side, and this rank does not arrive at that barrier before the sums are done (ev_sdone of the other side is waited
+// for below); (2) the sums wait for every rank's blocks at the statistics barrier. The two kinds of barrier use separate
+// arrival words and epochs.
+int bpmf_gpu_reduce_stats(bpmf_gpu_ctx *ctx, int side)
+{
+    if (!ctx || !side_ok(side)) return BPMF_GPU_EINVAL;
+    SideDev &s = ctx->side[side];
+    if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
+    if (!stats_on_aux(ctx, side) || s.num < 1) return reduce_stats_main(ctx, side);
+    CU(cudaSetDevice(ctx->device));
+    const bool multi = true;              // (stats_on_aux)
+    cudaStream_t aux = ctx->aux_stream;
+    CU(cudaEventRecord(ctx->ev_items[side], ctx->stream));
+    CU(cudaStreamWaitEvent(aux, ctx->ev_items[side], 0));
+    CU(cudaStreamWaitEvent(aux, ctx->ev_hyper[side], 0));        // a draw of this side launched on the main stream (same scratch)
+    const cudaError_t e = launch_stats_partial(ctx, side, aux);
+    if (e == cudaErrorInvalidValue && s.n_stat_peers > 0)
+        return fail(ctx, BPMF_GPU_EINVAL, "with statistics peers the item range must be aligned to bpmf_gpu_stats_block_items");
+    CU(e);
+    if (multi) CU(launch_peer_barrier(ctx, side, BARRIER_STATS, aux));
+    CU(launch_stats_final(ctx, side, aux));
+    CU(cudaEventRecord(ctx->ev_sdone[side], aux));
+    // hp.sample of the NEXT iteration needs only this cov (c++/sample.cpp:350)
+    CU(launch_hyper(ctx, side, (uint32_t)(s.iter + 1), nullptr, s.cov, true));
+    CU(cudaEventRecord(ctx->ev_hyper[side], aux));
+    s.pre_iter = s.iter + 1;
+    if (multi) {
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_sdone[1 - side], 0));   // hazard (1)
+        CU(launch_peer_barrier(ctx, side, BARRIER_LATENTS, ctx->stream));
+    }
+    return BPMF_GPU_OK;
 }
 
 int bpmf_gpu_get_stats(bpmf_gpu_ctx *ctx, int side, double *sum, double *prod, double *cov, double *norm)
@@ -915,6 +981,7 @@ int bpmf_gpu_set_prop_posterior(bpmf_gpu_ctx *ctx, int side, const double *host_
     SideDev &s = ctx->side[side];
     if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
     CU(cudaSetDevice(ctx->device));
+    { const int qrc = quiesce_aux(ctx); if (qrc) return qrc; }
     CU(cudaStreamSynchronize(ctx->stream));
     dfree(s.propLambda);
     if (!host_Lambda) return BPMF_GPU_OK;
@@ -930,6 +997,7 @@ int bpmf_gpu_enable_aggregation(bpmf_gpu_ctx *ctx, int side, int burnin)
     SideDev &s = ctx->side[side];
     if (!s.loaded) return fail(ctx, BPMF_GPU_EINVAL, "side not loaded");
     CU(cudaSetDevice(ctx->device));
+    { const int qrc = quiesce_aux(ctx); if (qrc) return qrc; }
     CU(cudaStreamSynchronize(ctx->stream));
     dfree(s.aggrMu); dfree(s.aggrLambda);
     // only the items this context samples: with the items split over G GPUs, K*K*num/G doubles each (c++/bpmf.h:161-176)
@@ -1097,6 +1165,7 @@ int bpmf_gpu_sample_host(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_v
     SideDev &o = ctx->side[1 - side];
     if (!s.loaded || !o.loaded) return fail(ctx, BPMF_GPU_EINVAL, "both sides must be loaded");
     CU(cudaSetDevice(ctx->device));
+    { const int qrc = quiesce_aux(ctx); if (qrc) return qrc; }
     const size_t K = (size_t)ctx->K;
     if (s.n_stat_peers > 1) {
         // One rank of a multi-GPU run: host memory holds THIS rank's slice of each latent matrix. Its slice of the other side
@@ -1137,7 +1206,7 @@ int bpmf_gpu_sample_host(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_v
         rc = bpmf_gpu_aggregate(ctx, side);
         if (rc) return rc;
     }
-    rc = bpmf_gpu_reduce_stats(ctx, side);
+    rc = reduce_stats_main(ctx, side);      // (host-destination path: the other side is uploaded next, keep everything on one stream)
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
@@ -1151,6 +1220,7 @@ int bpmf_gpu_upload_push_range(bpmf_gpu_ctx *ctx, int side, int from, int to, co
     SideDev &s = ctx->side[side];
     if (!s.loaded || from < 0 || to < from || to > s.num) return fail(ctx, BPMF_GPU_EINVAL, "bad range");
     CU(cudaSetDevice(ctx->device));
+    { const int qrc = quiesce_aux(ctx); if (qrc) return qrc; }
     const size_t K = (size_t)ctx->K;
     // chunks: the upload of chunk c + 1 (copy stream, PCIe) runs while chunk c goes to the peers (main stream, NVLink)
     constexpr int NCH = bpmf_gpu_ctx::HOST_PARTS;

@@ -8,6 +8,7 @@
 namespace bpmf {
 
 constexpr int MAX_PEERS = 16;
+constexpr int BARRIER_LATENTS = 0, BARRIER_STATS = 1;
 constexpr int STATS_BLOCKS = 296;  // 2 x 148 SMs; fixed so the reduction order never depends on the GPU count
 
 // error word written by kernels: 0 = ok. code in the high 32 bits, detail (item index) in the low 32.
@@ -53,10 +54,12 @@ struct SideDev {          // the device mirror of one Sys (c++/bpmf.h:112-239)
     // `partials` (peer-mapped pointers, bpmf_gpu_set_stats_peers); 0 = reduce the full replica locally
     int n_stat_peers = 0;
     double **stat_peers_dev = nullptr;    // device array[MAX_PEERS]
-    // cross-GPU barrier (peer_barrier_kernel): MAX_PEERS arrival words behind the partials of every rank's buffer; this
-    // context is rank `stat_rank` of the peer list; the epoch counts the barriers of this side
+    // cross-GPU barrier (peer_barrier_kernel): 2 x MAX_PEERS arrival words behind the partials of every rank's buffer, one
+    // set per KIND of barrier (BARRIER_LATENTS on the main stream, BARRIER_STATS on the auxiliary stream: they interleave
+    // differently on different ranks); this context is rank `stat_rank` of the peer list; an epoch counts the barriers of
+    // its kind on this side
     int stat_rank = -1;
-    unsigned long long barrier_epoch = 0;
+    unsigned long long barrier_epoch[2] = {0, 0};
     double *pred_partials = nullptr;
     int pred_blocks = 0;
     // propagated posterior (-m / -l): per-item prior precision K*K x num, nullptr = none (bpmf_gpu_set_prop_posterior)
@@ -102,7 +105,15 @@ struct bpmf_gpu_ctx {
     cudaStream_t aux_stream = nullptr;    // the next iteration's hyper draw runs here, under the other side's sweep
     cudaEvent_t ev_stats[2] = {}, ev_hyper[2] = {};
     cudaEvent_t ev_sdone[2] = {};         // the statistics of a side (sum / prod / cov / norm) are complete (they may be computed on aux_stream)
+    cudaEvent_t ev_items[2] = {};         // the item kernel (and -o aggregation) of a side's sweep is complete: its statistics may start
     bool overlap_hyper = true;
+    // Multi-GPU sweeps (statistics peers set): the whole reduction chain of a sweep (block partials of the own items ->
+    // cross-GPU barrier -> sums -> cov -> next hyper draw) runs on the auxiliary stream UNDER the other side's sweep. The
+    // persistent item kernels fill every SM they are given (one CTA of 640 threads x 96 registers + 200 KB per SM), so they
+    // are launched on sm_count - reserve_sms SMs and the chain gets the rest. On one GPU the reductions cover the whole
+    // matrix and are as much work as two SMs do in a sweep: they stay on the main stream, on all SMs (measured).
+    bool stats_aux = true;
+    int reserve_sms = 2;
     cudaStream_t copy_stream = nullptr;   // bpmf_gpu_sample_host: downloads finished item ranges while the rest is sampled
     static constexpr int HOST_PARTS = 6;   // most parts a host-destination sweep is cut into (capi.cu: bpmf_gpu_sample_host)
     cudaEvent_t ev_part[HOST_PARTS] = {}, ev_copied = nullptr;
@@ -128,14 +139,17 @@ struct bpmf_gpu_ctx {
 
 // ---- launchers implemented in the kernel translation units ------------------------------------
 namespace bpmf {
+// SMs the persistent item kernels are launched on (the rest is left to the statistics chain on the auxiliary stream)
+inline bool stats_on_aux(const bpmf_gpu_ctx *c, int side) { return c->stats_aux && c->side[side].n_stat_peers > 1; }
+inline int item_sms(const bpmf_gpu_ctx *c, int side) { const int n = c->sm_count - (stats_on_aux(c, side) ? c->reserve_sms : 0); return n < 1 ? 1 : n; }
 // exact_kernels.cu (compiled with -fmad=false)
 cudaError_t launch_hyper(bpmf_gpu_ctx *c, int side, uint32_t iter, const double *d_sum, const double *d_cov, bool ahead);
 cudaError_t launch_items_exact(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha);
 cudaError_t launch_stats(bpmf_gpu_ctx *c, int side);
-cudaError_t launch_stats_partial(bpmf_gpu_ctx *c, int side);   // per-block partial sums (own blocks only when stat peers are set)
+cudaError_t launch_stats_partial(bpmf_gpu_ctx *c, int side, cudaStream_t stream);   // per-block partial sums (own blocks only when stat peers are set)
 cudaError_t launch_stats_final(bpmf_gpu_ctx *c, int side, cudaStream_t stream);   // fixed-order sum of the STATS_BLOCKS partials, cov
 int stats_block_items(int K, int num);                          // items per statistics block (the granularity of ranges)
-cudaError_t launch_peer_barrier(bpmf_gpu_ctx *c, int side);     // every rank's earlier work on the side has landed everywhere
+cudaError_t launch_peer_barrier(bpmf_gpu_ctx *c, int side, int kind, cudaStream_t stream);   // every rank's earlier work on that stream has landed everywhere
 cudaError_t launch_predict(bpmf_gpu_ctx *c, int side, int n);
 cudaError_t launch_aggregate(bpmf_gpu_ctx *c, int side);
 cudaError_t launch_finalize_aggregates(bpmf_gpu_ctx *c, int side, int nsamples);   // c++/bpmf.cpp:281-295, batched
@@ -150,7 +164,7 @@ int block_partial_doubles(int K);
 int block_heavy_chunk_size();
 // stream_kernel.cu
 cudaError_t launch_items_stream32(bpmf_gpu_ctx *c, int side, uint32_t iter, double alpha);
-cudaError_t launch_stats_partial32(bpmf_gpu_ctx *c, int side, int b0, int nb);
+cudaError_t launch_stats_partial32(bpmf_gpu_ctx *c, int side, int b0, int nb, cudaStream_t stream);
 int heavy_chunk_size();
 int heavy_partial_doubles();
 // build_kernels.cu

@@ -564,7 +564,7 @@ cudaError_t launch_items_exact(bpmf_gpu_ctx *c, int side, uint32_t iter, double 
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     long long n = (long long)s.to - s.from;
-    long long grid = (long long)c->sm_count * per_sm;
+    long long grid = (long long)item_sms(c, side) * per_sm;
     if (grid > n) grid = n;
     if (grid < 1) return cudaSuccess;
     items_exact_kernel<<<(unsigned)grid, threads, smem, c->stream>>>(p);
@@ -678,20 +678,16 @@ __global__ void peer_barrier_kernel(double *const *peers, int npeers, int me, si
     __threadfence_system();
 }
 
-cudaError_t launch_peer_barrier(bpmf_gpu_ctx *c, int side)
+// kind: which set of arrival words / which epoch counter (BARRIER_LATENTS, BARRIER_STATS): barriers of different kinds run
+// on different streams and every rank may interleave them differently. What a barrier orders against the peers' later
+// stores into this rank's buffers (the sums having read the statistics blocks, ...) is the caller's business (capi.cu).
+cudaError_t launch_peer_barrier(bpmf_gpu_ctx *c, int side, int kind, cudaStream_t stream)
 {
     SideDev &s = c->side[side];
     if (s.n_stat_peers < 2 || s.stat_rank < 0) return cudaSuccess;
-    // Once this rank has passed the barrier its peers may overwrite its statistics blocks (their next sweep of either side):
-    // the sums of the previous sweeps must have read them (they run on this stream today, so the wait is a formality that
-    // keeps the protocol correct wherever bpmf_gpu_reduce_stats_final puts them).
-    for (int sd = 0; sd < 2; ++sd) {
-        const cudaError_t ew = cudaStreamWaitEvent(c->stream, c->ev_sdone[sd], 0);
-        if (ew != cudaSuccess) return ew;
-    }
-    const size_t flag_off = (size_t)STATS_BLOCKS * ((size_t)c->K * c->K + c->K + 1);
-    ++s.barrier_epoch;
-    peer_barrier_kernel<<<1, 32, 0, c->stream>>>(s.stat_peers_dev, s.n_stat_peers, s.stat_rank, flag_off, s.barrier_epoch, c->d_err);
+    const size_t flag_off = (size_t)STATS_BLOCKS * ((size_t)c->K * c->K + c->K + 1) + (size_t)kind * MAX_PEERS;
+    ++s.barrier_epoch[kind];
+    peer_barrier_kernel<<<1, 32, 0, stream>>>(s.stat_peers_dev, s.n_stat_peers, s.stat_rank, flag_off, s.barrier_epoch[kind], c->d_err);
     c->launches++;
     return cudaGetLastError();
 }
@@ -707,7 +703,7 @@ int stats_block_items(int K, int num)
 
 // Per-block partial sums. With statistics peers set (multi-GPU) only the blocks of this context's item range are
 // reduced and each partial is stored into every rank's buffer; the range must then be aligned to stats_block_items.
-cudaError_t launch_stats_partial(bpmf_gpu_ctx *c, int side)
+cudaError_t launch_stats_partial(bpmf_gpu_ctx *c, int side, cudaStream_t stream)
 {
     SideDev &s = c->side[side];
     const int K = c->K, KK = K * K;
@@ -721,10 +717,10 @@ cudaError_t launch_stats_partial(bpmf_gpu_ctx *c, int side)
         nb = (s.from < s.to) ? b1 - b0 : 0;
     }
     if (nb < 1) return cudaSuccess;
-    if (K == 32) return launch_stats_partial32(c, side, b0, nb);          // tensor-core version, same partial layout (stream_kernel.cu)
+    if (K == 32) return launch_stats_partial32(c, side, b0, nb, stream);  // tensor-core version, same partial layout (stream_kernel.cu)
     const int ne = (KK + 255) / 256;
     const size_t smem = sizeof(double) * 32 * K;
-#define BPMF_STATS_CASE(NE) stats_partial_kernel<NE><<<nb, 256, smem, c->stream>>>(s.items, s.num, K, s.partials, b0, s.n_stat_peers, s.stat_peers_dev)
+#define BPMF_STATS_CASE(NE) stats_partial_kernel<NE><<<nb, 256, smem, stream>>>(s.items, s.num, K, s.partials, b0, s.n_stat_peers, s.stat_peers_dev)
     if (ne <= 1) BPMF_STATS_CASE(1);
     else if (ne <= 2) BPMF_STATS_CASE(2);
     else if (ne <= 4) BPMF_STATS_CASE(4);
@@ -753,7 +749,7 @@ cudaError_t launch_stats_final(bpmf_gpu_ctx *c, int side, cudaStream_t stream)
 
 cudaError_t launch_stats(bpmf_gpu_ctx *c, int side)
 {
-    const cudaError_t e = launch_stats_partial(c, side);
+    const cudaError_t e = launch_stats_partial(c, side, c->stream);
     return e != cudaSuccess ? e : launch_stats_final(c, side, c->stream);
 }
 

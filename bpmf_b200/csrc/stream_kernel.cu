@@ -71,6 +71,7 @@ struct StreamArgs {
     int heavy_thr;            // SKIP: items with more ratings than this belong to the chunked path and are passed over
     const double *propLambda; // PROP: K*K x num per-item prior precisions (-m / -l, sample.cpp:272-277)
     int oob_row;              // gather4 variant: a row index outside the other side's latent matrix (zero fill)
+    int sms;                  // (host side) SMs the kernel is launched on: item_sms()
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
@@ -1019,7 +1020,7 @@ cudaError_t launch_cfg(bpmf_gpu_ctx *c, const StreamArgs &p, long long n)
 #endif
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    long long grid = c->sm_count;                              // persistent: one CTA per SM
+    long long grid = p.sms;                                    // persistent: one CTA per SM
     // small sweeps are claimed CLAIM_TAIL items at a time (bulk_end == from): enough CTAs for every claim to find a warp
     const long long need = (n + (long long)NW * CLAIM_TAIL - 1) / ((long long)NW * CLAIM_TAIL);
     if (grid > need) grid = need;
@@ -1036,13 +1037,15 @@ cudaError_t launch_cfg(bpmf_gpu_ctx *c, const StreamArgs &p, long long n)
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int SW = 8;   // warps per stats block
 
-// Block b0 + blockIdx.x of the fixed STATS_BLOCKS decomposition; the partial goes to `partials` and to every peer's copy.
-__global__ void __launch_bounds__(SW * 32) stats_partial32_kernel(const double *__restrict__ items, int N, double *__restrict__ partials, int b0,
-                                                                  int npeers, double *const *__restrict__ peers)
+// One block of the fixed STATS_BLOCKS decomposition, computed by a group of SW warps (tid = 0 .. SW * 32 - 1 inside the group,
+// `bar` = the group's named barrier, sp = its SW x 672 doubles of shared memory); the partial goes to `partials` and to every
+// peer's copy. The order of every sum is fixed by the block id alone.
+__device__ __forceinline__ void group_sync(int bar) { asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(SW * 32) : "memory"); }
+
+__device__ __forceinline__ void stats_block32(const double *__restrict__ items, int N, double *__restrict__ partials, int blk_id, int npeers,
+                                              double *const *__restrict__ peers, double (*sp)[10 * 64 + 32], int tid, int bar)
 {
-    __shared__ double sp[SW][10 * 64 + 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-    const int blk_id = b0 + (int)blockIdx.x;
+    const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const long long nw = (long long)STATS_BLOCKS * SW, w = (long long)blk_id * SW + warp;
     long long chunk = (N + nw - 1) / nw;
     chunk = (chunk + 3) & ~3ll;
@@ -1079,7 +1082,7 @@ __global__ void __launch_bounds__(SW * 32) stats_partial32_kernel(const double *
 #pragma unroll
         for (int a = 0; a < 4; ++a) sp[warp][640 + 8 * a + g] = sx[a];
     }
-    __syncthreads();
+    group_sync(bar);
     // the block's partial, first in registers (every sp[][] value is still needed), then in sp itself
     double acc4[1024 / (SW * 32)], accs = 0.0;
 #pragma unroll
@@ -1098,18 +1101,18 @@ __global__ void __launch_bounds__(SW * 32) stats_partial32_kernel(const double *
 #pragma unroll
         for (int ww = 0; ww < SW; ++ww) accs += sp[ww][640 + tid];
     }
-    __syncthreads();
+    group_sync(bar);
     double *so = &sp[0][0];                                  // 1024 + 32 + 1 doubles
 #pragma unroll
     for (int q = 0; q < 1024 / (SW * 32); ++q) so[tid + q * SW * 32] = acc4[q];
     if (tid < 32) so[1024 + tid] = accs;
-    __syncthreads();
+    group_sync(bar);
     if (tid == 0) {   // norm = sum of squared norms = trace of the outer-product sum
         double nn = 0.0;
         for (int d = 0; d < 32; ++d) nn += so[d * 33];
         so[1024 + 32] = nn;
     }
-    __syncthreads();
+    group_sync(bar);
     const size_t base = (size_t)blk_id * (1024 + 32 + 1);
     for (int e = tid; e < 1024 + 32 + 1; e += SW * 32) {
         const double v = so[e];
@@ -1119,15 +1122,47 @@ __global__ void __launch_bounds__(SW * 32) stats_partial32_kernel(const double *
             if (dst && dst != partials) dst[base + e] = v;
         }
     }
+    group_sync(bar);                      // sp is free for the group's next block
+}
+
+// Block b0 + blockIdx.x, one block per CTA: the reductions on the main stream (all SMs)
+__global__ void __launch_bounds__(SW * 32) stats_partial32_kernel(const double *__restrict__ items, int N, double *__restrict__ partials, int b0,
+                                                                  int npeers, double *const *__restrict__ peers)
+{
+    __shared__ double sp[SW][10 * 64 + 32];
+    stats_block32(items, N, partials, b0 + (int)blockIdx.x, npeers, peers, sp, threadIdx.x, 0);
+}
+
+// The same blocks [b0, b0 + nb) by a FEW persistent CTAs of four groups each (grid = the SMs the item kernels leave free): the
+// reductions on the auxiliary stream, under the other side's sweep. A wide grid would spread over every SM in the gap between
+// two item kernels and keep the next one's CTAs (which need a whole SM each) waiting.
+constexpr int SG = 4;   // groups per CTA
+__global__ void __launch_bounds__(SG * SW * 32, 1) stats_partial32_persistent_kernel(const double *__restrict__ items, int N, double *__restrict__ partials,
+                                                                                   int b0, int nb, int npeers, double *const *__restrict__ peers)
+{
+    extern __shared__ __align__(16) unsigned char stats_smem[];
+    const int gi = threadIdx.x / (SW * 32), tid = threadIdx.x % (SW * 32);
+    double (*sp)[10 * 64 + 32] = reinterpret_cast<double (*)[10 * 64 + 32]>(stats_smem) + (size_t)gi * SW;
+    for (int vb = (int)blockIdx.x * SG + gi; vb < nb; vb += (int)gridDim.x * SG)
+        stats_block32(items, N, partials, b0 + vb, npeers, peers, sp, tid, 1 + gi);
 }
 
 }  // namespace
 
-cudaError_t launch_stats_partial32(bpmf_gpu_ctx *c, int side, int b0, int nb)
+cudaError_t launch_stats_partial32(bpmf_gpu_ctx *c, int side, int b0, int nb, cudaStream_t stream)
 {
     SideDev &s = c->side[side];
     if (nb < 1) return cudaSuccess;
-    stats_partial32_kernel<<<nb, SW * 32, 0, c->stream>>>(s.items, s.num, s.partials, b0, s.n_stat_peers, s.stat_peers_dev);
+    if (stream != c->stream && c->stats_aux) {
+        // auxiliary stream: as many CTAs as SMs are left free by the item kernels
+        constexpr size_t smem = sizeof(double) * SG * SW * (10 * 64 + 32);
+        const cudaError_t e = cudaFuncSetAttribute(stats_partial32_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // (per device)
+        if (e != cudaSuccess) return e;
+        const int grid = std::max(1, std::min(c->reserve_sms, (nb + SG - 1) / SG));
+        stats_partial32_persistent_kernel<<<grid, SG * SW * 32, smem, stream>>>(s.items, s.num, s.partials, b0, nb, s.n_stat_peers, s.stat_peers_dev);
+    } else {
+        stats_partial32_kernel<<<nb, SW * 32, 0, stream>>>(s.items, s.num, s.partials, b0, s.n_stat_peers, s.stat_peers_dev);
+    }
     c->launches++;
     return cudaGetLastError();
 }
@@ -1173,7 +1208,7 @@ static cudaError_t launch_g4(bpmf_gpu_ctx *c, StreamArgs p, long long n, int num
     auto kern = items_stream32g4_kernel<NS, NW, SKIP>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    long long grid = c->sm_count;
+    long long grid = p.sms;
     const long long need = (n + (long long)NW * CLAIM_TAIL - 1) / ((long long)NW * CLAIM_TAIL);
     if (grid > need) grid = need;
     kern<<<(unsigned)grid, NW * 32, smem, c->stream>>>(p, tmap);
@@ -1192,6 +1227,7 @@ static cudaError_t launch_stream_range(bpmf_gpu_ctx *c, int side, uint32_t iter,
     p.mu = s.hp.mu; p.LambdaF = s.hp.LambdaF;
     p.work_counter = s.work_counter; p.err = c->d_err; p.zero_row = c->d_zero_row; p.heavy_thr = s.heavy_thr; p.propLambda = s.propLambda;
     p.oob_row = o.num;
+    p.sms = item_sms(c, side);
     cudaError_t e = cudaMemsetAsync(s.work_counter, 0, 2 * sizeof(unsigned int), c->stream);
     if (e != cudaSuccess) return e;
     const long long n = (long long)to - from;
@@ -1202,7 +1238,7 @@ static cudaError_t launch_stream_range(bpmf_gpu_ctx *c, int side, uint32_t iter,
     p.guided = 0;
     {
         const int gq = c->stream_guided ? c->stream_guided : 4;
-        if (gq != 9) p.guided = (int)std::min<long long>(0x7fffffff, std::max<long long>(1, (long long)gq * c->sm_count * 20 / 4));
+        if (gq != 9) p.guided = (int)std::min<long long>(0x7fffffff, std::max<long long>(1, (long long)gq * p.sms * 20 / 4));
     }
     {   // the last ~4 items per resident warp are handed out CLAIM_TAIL at a time (v3 kernel); bulk region is a multiple of CLAIM
         static const int tail_per_warp = [] { const char *v = getenv("BPMF_STREAM_TAIL"); return v ? atoi(v) : 8; }();
