@@ -64,7 +64,7 @@ __host__ __device__ inline HyperLayout hyper_layout(int K, int nblk, size_t cap)
     return l;
 }
 
-static int hyper_threads(int K) { return K <= 32 ? 256 : K <= 64 ? 512 : 1024; }   // measured: bench_micro/hyper_timing.py
+static int hyper_threads(int K) { return K <= 32 ? 256 : 1024; }   // measured: bench_micro/hyper_timing.py
 
 #ifdef BPMF_HYPER_PROF     // phase probes: clock64 of thread 0 at the phase boundaries, printed by the kernel (bench_micro/hyper_timing.py)
 #define HSTAMP(i) do { if (threadIdx.x == 0) hprof[i] = clock64(); } while (0)
@@ -72,6 +72,9 @@ static int hyper_threads(int K) { return K <= 32 ? 256 : K <= 64 ? 512 : 1024; }
 #define HSTAMP(i) do { } while (0)
 #endif
 
+// SM / SR: the matrices / the random-stream arrays are in shared memory (compile-time, so that the accesses are LDS / STS and
+// not generic loads)
+template <bool SM, bool SR>
 __global__ void __launch_bounds__(1024) hyper_kernel(HyperArgs a, const size_t smem_cap)
 {
 #ifdef BPMF_HYPER_PROF
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(1024) hyper_kernel(HyperArgs a, const size_t s
     extern __shared__ __align__(16) unsigned char hyper_smem[];
     const HyperLayout lay = hyper_layout(K, nblk, smem_cap);
     double *Uout = a.LambdaU;                 // where U = LambdaU is kept while the kernel works on it
-    if (lay.mats) {
+    if (SM) {
         a.mats = reinterpret_cast<double *>(hyper_smem + lay.mats_off);
         Uout = a.mats + 4 * (size_t)KK;
         a.vecs = reinterpret_cast<double *>(hyper_smem + lay.vecs_off);
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(1024) hyper_kernel(HyperArgs a, const size_t s
         a.row_start = reinterpret_cast<int *>(hyper_smem + lay.rows_off);
         a.row_cls = a.row_start + (K + 1);
     }
-    if (lay.rng) {
+    if (SR) {
         unsigned char *q = hyper_smem + lay.rng_off;
         a.words = reinterpret_cast<uint32_t *>(q); q += (size_t)nblk * 16;
         a.acc = q; q += (((size_t)nblk * 2 + 15) / 16) * 16;
@@ -153,27 +156,84 @@ __global__ void __launch_bounds__(1024) hyper_kernel(HyperArgs a, const size_t s
     //  recorded here; their values are computed in parallel in step 5.
     double *au = a.mats + 3 * (size_t)KK;
     for (int e = tid; e < KK; e += T) au[e] = 0.0;
-    __syncthreads();
+    const int nu_c = K + N;  // nu + N, mvnormal.cpp:125
+    auto next_attempt = [&](int p) -> int {   // first accepted attempt at/after word offset p -> its q, or -1
+        const int q = p >> 1;
+        if (q >= nq) return -1;
+        const int c = q & 1, r = a.rank[q];
+        if (r >= s_total[c]) return -1;
+        return 2 * a.pos_of_rank[c * nblk + r] + c;
+    };
+    auto skip_normals = [&](int p, int n, int *start_rank, int *cls) -> int {  // consume n normals from p
+        const int q = p >> 1;
+        if (q >= nq) return -1;
+        const int c = q & 1, r = a.rank[q];
+        *start_rank = r; *cls = c;
+        if (n == 0) return p;
+        if (r + n - 1 >= s_total[c]) return -1;
+        return 2 * (2 * a.pos_of_rank[c * nblk + r + n - 1] + c) + 4;
+    };
+    // 4a. The walk is sequential only in the stream POSITIONS; the arithmetic of a gamma draw (two logarithms, a square root
+    // and a division on one thread: 2 000 cycles each) is not. A draw almost always takes its first normal and its first
+    // uniform (Marsaglia-Tsang accepts > 99.9 % at these shape parameters), so thread 0 first walks the positions under that
+    // assumption — integer table look-ups only —, then K threads do one draw each; if any draw would have gone round its
+    // loop again, the plain sequential walk below redoes everything. Either way the result is the sequential one.
+    __shared__ int s_gq[129], s_upos[129], s_spec;
     if (tid == 0) {
-        const int nu_c = K + N;  // nu + N, mvnormal.cpp:125
+        int pos = 0;
+        bool bad = 0.5 * (nu_c - (K - 1)) < 1.0;
+        for (int i = 0; i < K && !bad; ++i) {
+            const int q = next_attempt(pos);
+            if (q < 0) { bad = true; break; }
+            s_gq[i] = q;
+            pos = 2 * q + 4;
+            if ((pos >> 1) >= 2 * nblk || pos + 1 >= 4 * nblk) { bad = true; break; }
+            s_upos[i] = pos;
+            pos += 2;
+            int r0, c0;
+            pos = skip_normals(pos, K - i - 1, &r0, &c0);
+            if (pos < 0) { bad = true; break; }
+            pos = skip_normals(pos, K - i - 1, &r0, &c0);
+            if (pos < 0) { bad = true; break; }
+            a.row_start[i] = r0; a.row_cls[i] = c0;
+        }
+        if (!bad) {
+            int r0, c0;
+            pos = skip_normals(pos, K, &r0, &c0);
+            if (pos < 0) bad = true;
+            a.row_start[K] = r0; a.row_cls[K] = c0;
+        }
+        s_spec = bad ? 0 : 1;      // (bad: let the sequential walk find out what is wrong)
+    }
+    __syncthreads();
+    int spec_ok = s_spec;
+    if (spec_ok) {
+        bool mine = true;
+        if (tid < K) {
+            const int i = tid;
+            const double alpha = 0.5 * (nu_c - i);
+            const double a1 = alpha - 1.0 / 3.0;
+            const double a2 = 1.0 / sqrt(9.0 * a1);
+            const int q = s_gq[i], up = s_upos[i];
+            const Polar p = polar_attempt(a.words[2 * q], a.words[2 * q + 1], a.words[2 * q + 2], a.words[2 * q + 3]);
+            const double mult = polar_mult(p.r2);
+            const double n = p.y * mult;
+            double v = 1.0 + a2 * n;
+            if (v <= 0.0) mine = false;
+            else {
+                v = v * v * v;
+                const double u = canonical(a.words[up], a.words[up + 1]);
+                const bool again = (u > 1.0 - 0.0331 * n * n * n * n) && (log(u) > (0.5 * n * n + a1 * (1.0 - v + log(v))));
+                if (again) mine = false;
+                else au[i + i * K] = sqrt(2.0 * (a1 * v * 1.0));
+            }
+        }
+        spec_ok = __syncthreads_and(mine);
+    }
+    // 4c. the sequential walk (a draw went round its loop again, or the stream ran out)
+    if (!spec_ok && tid == 0) {
         int pos = 0;             // word offset, always even
         bool bad = false;
-        auto next_attempt = [&](int p) -> int {   // first accepted attempt at/after word offset p -> its q, or -1
-            const int q = p >> 1;
-            if (q >= nq) return -1;
-            const int c = q & 1, r = a.rank[q];
-            if (r >= s_total[c]) return -1;
-            return 2 * a.pos_of_rank[c * nblk + r] + c;
-        };
-        auto skip_normals = [&](int p, int n, int *start_rank, int *cls) -> int {  // consume n normals from p
-            const int q = p >> 1;
-            if (q >= nq) return -1;
-            const int c = q & 1, r = a.rank[q];
-            *start_rank = r; *cls = c;
-            if (n == 0) return p;
-            if (r + n - 1 >= s_total[c]) return -1;
-            return 2 * (2 * a.pos_of_rank[c * nblk + r + n - 1] + c) + 4;
-        };
         for (int i = 0; i < K && !bad; ++i) {
             const double alpha = 0.5 * (nu_c - i);
             if (alpha < 1.0) { bad = true; break; }  // would need the pow() branch; N >= 1 never gets here
@@ -299,13 +359,17 @@ __global__ void __launch_bounds__(1024) hyper_kernel(HyperArgs a, const size_t s
             const int p = a.piv[k];
             if (p != k) { const double t0 = bt[k * K + c]; bt[k * K + c] = bt[p * K + c]; bt[p * K + c] = t0; }
         }
+        // (the products of a row do not depend on its running sum: unrolled, they and their loads run ahead of the chain
+        //  of subtractions, whose order stays j ascending)
         for (int i = 0; i < K; ++i) {
             double s = bt[i * K + c];
+#pragma unroll 8
             for (int j = 0; j < i; ++j) s -= lu[i + j * K] * bt[j * K + c];
             bt[i * K + c] = s;
         }
         for (int i = K - 1; i >= 0; --i) {
             double s = bt[i * K + c];
+#pragma unroll 8
             for (int j = i + 1; j < K; ++j) s -= lu[i + j * K] * bt[j * K + c];
             bt[i * K + c] = s / lu[i + i * K];
         }
@@ -393,7 +457,8 @@ cudaError_t launch_hyper(bpmf_gpu_ctx *c, int side, uint32_t iter, const double 
         cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
         dcap = optin > 16384 ? (size_t)optin - 10240 : 1;      // s_scan and the other static arrays of the kernel take ~4.2 KB
         if (getenv("BPMF_HYPER_GLOBAL_SCRATCH")) dcap = 1;       // A/B: everything in global scratch, as before
-        if (dcap > 1 && cudaFuncSetAttribute(hyper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dcap) != cudaSuccess) {
+        if (dcap > 1 && (cudaFuncSetAttribute(hyper_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dcap) != cudaSuccess ||
+                         cudaFuncSetAttribute(hyper_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dcap) != cudaSuccess)) {
             cudaGetLastError();
             dcap = 1;
         }
@@ -404,7 +469,10 @@ cudaError_t launch_hyper(bpmf_gpu_ctx *c, int side, uint32_t iter, const double 
     static int threads_env = -1;
     if (threads_env < 0) { const char *t = getenv("BPMF_HYPER_THREADS"); threads_env = t ? atoi(t) : 0; }
     int threads = threads_env >= 32 && threads_env <= 1024 ? (threads_env / 32) * 32 : hyper_threads(c->K);
-    hyper_kernel<<<1, threads, lay.bytes, ahead ? c->aux_stream : c->stream>>>(a, dcap);
+    cudaStream_t hstream = ahead ? c->aux_stream : c->stream;
+    if (lay.mats && lay.rng) hyper_kernel<true, true><<<1, threads, lay.bytes, hstream>>>(a, dcap);
+    else if (lay.mats) hyper_kernel<true, false><<<1, threads, lay.bytes, hstream>>>(a, dcap);
+    else hyper_kernel<false, false><<<1, threads, 0, hstream>>>(a, dcap);
     c->launches++;
     return cudaGetLastError();
 }
