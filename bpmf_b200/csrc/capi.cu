@@ -44,7 +44,7 @@ void dfree(T *&p)
 
 void free_side(SideDev &s)
 {
-    dfree(s.colptr); dfree(s.rowidx); dfree(s.val);
+    dfree(s.colptr); dfree(s.rowidx); dfree(s.val); dfree(s.wval);
     dfree(s.t_colptr); dfree(s.t_rowidx); dfree(s.t_col); dfree(s.t_val); dfree(s.pavg); dfree(s.pm2);
     dfree(s.items_own); s.items = nullptr;
     dfree(s.peers_dev); dfree(s.stat_peers_dev);

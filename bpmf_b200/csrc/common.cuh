@@ -77,6 +77,11 @@ struct SideDev {          // the device mirror of one Sys (c++/bpmf.h:112-239)
     double *hv_partials = nullptr;                    // per chunk: partial Gram + rhs in the DMMA layout
     // dynamic work counter for the item kernels
     unsigned int *work_counter = nullptr;
+    // K == 32 stream kernel: the right-hand-side weights (val - mean_rating) * alpha of the ratings (sample.cpp:255), which do
+    // not change from sweep to sweep, computed once per alpha (8 bytes per rating) instead of per staged rating in every sweep
+    double *wval = nullptr;
+    double wval_alpha = 0.0;
+    bool wval_valid = false;
 };
 
 struct HyperScratch {     // global scratch of the single-block hyper kernel

@@ -43,7 +43,7 @@ constexpr int MBAR_OFF = META_OFF + 16;      // one mbarrier per stage (bulk-cop
 constexpr int STAGE_BYTES = META_OFF + 32;
 constexpr int LFS = 34;                     // row stride (doubles) of LambdaF in shared memory
 constexpr int SHARED_BYTES = 32 * LFS * 8 + 32 * 8;
-constexpr int TV_DEFAULT = 4 | 16;           // tail / fetch variant of the product kernels (see chol3_block_column, tail_variant)
+constexpr int TV_DEFAULT = 4 | 16 | 128;           // tail / fetch variant of the product kernels (see chol3_block_column, tail_variant)
 constexpr int CLAIM = 16;                   // consecutive items claimed per atomic
 constexpr int CLAIM_TAIL = 2;               // ... for the last ~1 % of the items, so that all warps finish together
 // NS = stages per warp, NW = warps per CTA (one CTA per SM)
@@ -72,6 +72,7 @@ struct StreamArgs {
     const double *propLambda; // PROP: K*K x num per-item prior precisions (-m / -l, sample.cpp:272-277)
     int oob_row;              // gather4 variant: a row index outside the other side's latent matrix (zero fill)
     int sms;                  // (host side) SMs the kernel is launched on: item_sms()
+    const double *wval;       // TV & 128: (val - mean_rating) * alpha per rating, precomputed (weights_kernel)
 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
@@ -464,8 +465,9 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs
     int g_base = 0, g_n = 0, f_it = 0;
     int cpr = 0;                          // per lane: colptr[g_base + lane] - colptr[g_base]
     int f_pos = 0, f_end = 0, f_start = 0, g_end = 0;
+    constexpr bool PW = (TV & 128) != 0 && !BULK;   // the ratings' weights are precomputed: p.wval instead of p.val
     const int32_t *g_idx = p.rowidx;      // rowidx / val at the group's first rating
-    const double *g_val = p.val;
+    const double *g_val = PW ? p.wval : p.val;
     int32_t n_idx = 0;                    // per lane: index / value of stream position f_pos + (lane & 15): the NEXT stage's
     double n_w = 0.0;
     bool f_done = false;
@@ -519,7 +521,7 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs
         const int64_t c0 = __ldg(p.colptr + base);
         cpr = (lane <= g_n) ? (int)(__ldg(p.colptr + base + lane) - c0) : 0;
         g_idx = p.rowidx + c0;
-        g_val = p.val + c0;
+        g_val = (PW ? p.wval : p.val) + c0;
         g_end = __shfl_sync(FULL, cpr, g_n);
         f_it = 0;
         f_start = 0;
@@ -578,7 +580,9 @@ __global__ void __launch_bounds__(NW * 32, 1) items_stream32v3_kernel(StreamArgs
             }
         }
         // rr weight (v - mean_rating) * alpha (sample.cpp:255)
-        if (FPERM ? (lane & 8) == 0 : lane < SR) reinterpret_cast<double *>(stg + W_OFF)[rowl] = (rowl < n) ? (n_w - p.mean_rating) * p.alpha : 0.0;
+        // (PW: rows past the item's end may carry the next item's weight; their latent rows are zero-filled, so they add 0)
+        if (FPERM ? (lane & 8) == 0 : lane < SR)
+            reinterpret_cast<double *>(stg + W_OFF)[rowl] = PW ? n_w : (rowl < n) ? (n_w - p.mean_rating) * p.alpha : 0.0;
         const int last = (f_pos + n == f_end);
         if (lane == 0) *reinterpret_cast<int4 *>(stg + META_OFF) = make_int4(n, g_base + f_it, f_pos == f_start, last);
         if (!BULK) cp_async_commit();
@@ -999,12 +1003,20 @@ __global__ void __launch_bounds__(32) heavy_tail32_kernel(StreamArgs p, const in
 #include "../../bench_micro/stream_roles.cuh"
 #endif
 
+// w[i] = (val[i] - mean_rating) * alpha: the same two roundings as in the kernels (a subtraction feeding a product cannot fuse)
+__global__ void weights_kernel(const double *__restrict__ val, double *__restrict__ w, long long n, double mean_rating, double alpha)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        w[i] = __dmul_rn(__dsub_rn(val[i], mean_rating), alpha);
+}
+
 // The TV mask (chol3_block_column, issue_stage) of a kernel version. The product kernels (3, 12, 13, 16) run TV = 4 | 16:
 // panel blocks of the factor from the trailing update's B fragments, stage indices held by the lanes that copy their rows
 // (7.33 -> 7.19 ms, profiles/r02b_tune_tail_variants2.log). 24 = neither, the others are the measured alternatives.
 constexpr int tail_variant(int VER)
 {
-    return VER == 15 ? (TV_DEFAULT | 1) : VER == 17 ? (TV_DEFAULT | 2) : VER == 19 ? (TV_DEFAULT | 8) : VER == 18 ? 16 : VER == 21 ? 4 : VER == 24 ? 0 : TV_DEFAULT;
+    return VER == 15 ? (TV_DEFAULT | 1) : VER == 17 ? (TV_DEFAULT | 2) : VER == 19 ? (TV_DEFAULT | 8) : VER == 18 ? (16 | 128) : VER == 21 ? (4 | 128) : VER == 24 ? 128 :
+           VER == 27 ? (4 | 16) : TV_DEFAULT;
 }
 
 template <int NS, int NW, int VER, int DBG = 0>
@@ -1228,6 +1240,21 @@ static cudaError_t launch_stream_range(bpmf_gpu_ctx *c, int side, uint32_t iter,
     p.work_counter = s.work_counter; p.err = c->d_err; p.zero_row = c->d_zero_row; p.heavy_thr = s.heavy_thr; p.propLambda = s.propLambda;
     p.oob_row = o.num;
     p.sms = item_sms(c, side);
+    p.wval = nullptr;
+    if (TV_DEFAULT & 128) {
+        cudaError_t e0 = cudaSuccess;
+        if (!s.wval) {
+            e0 = cudaMalloc(&s.wval, sizeof(double) * (size_t)(s.nnz + 32));
+            if (e0 != cudaSuccess) return e0;
+            s.wval_valid = false;
+        }
+        if (!s.wval_valid || s.wval_alpha != alpha) {
+            if ((e0 = cudaMemsetAsync(s.wval, 0, sizeof(double) * (size_t)(s.nnz + 32), c->stream)) != cudaSuccess) return e0;
+            if (s.nnz > 0) weights_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(s.val, s.wval, (long long)s.nnz, s.mean_rating, alpha);
+            s.wval_valid = true; s.wval_alpha = alpha;
+        }
+        p.wval = s.wval;
+    }
     cudaError_t e = cudaMemsetAsync(s.work_counter, 0, 2 * sizeof(unsigned int), c->stream);
     if (e != cudaSuccess) return e;
     const long long n = (long long)to - from;
@@ -1285,6 +1312,7 @@ static cudaError_t launch_stream_range(bpmf_gpu_ctx *c, int side, uint32_t iter,
     case 18220: e = launch_cfg<2, 20, 18>(c, p, n); break;       // without the factor's panel blocks from the trailing update's B fragments
     case 21220: e = launch_cfg<2, 20, 21>(c, p, n); break;       // without the permuted ownership of the stage's indices
     case 24220: e = launch_cfg<2, 20, 24>(c, p, n); break;       // without either (7.33 ms)
+    case 27220: e = launch_cfg<2, 20, 27>(c, p, n); break;       // with the ratings' weights computed per staged rating in every sweep
     case 14220: e = launch_g4<2, 20, false>(c, p, n, o.num); break;
     case 14216: e = launch_g4<2, 16, false>(c, p, n, o.num); break;
     case 14316: e = launch_g4<3, 16, false>(c, p, n, o.num); break;
