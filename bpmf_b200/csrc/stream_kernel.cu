@@ -43,7 +43,7 @@ constexpr int MBAR_OFF = META_OFF + 16;      // one mbarrier per stage (bulk-cop
 constexpr int STAGE_BYTES = META_OFF + 32;
 constexpr int LFS = 34;                     // row stride (doubles) of LambdaF in shared memory
 constexpr int SHARED_BYTES = 32 * LFS * 8 + 32 * 8;
-constexpr int TV_DEFAULT = 4 | 16 | 128;           // tail / fetch variant of the product kernels (see chol3_block_column, tail_variant)
+constexpr int TV_DEFAULT = 4 | 16 | 128 | 256;           // tail / fetch variant of the product kernels (see chol3_block_column, tail_variant)
 constexpr int CLAIM = 16;                   // consecutive items claimed per atomic
 constexpr int CLAIM_TAIL = 2;               // ... for the last ~1 % of the items, so that all warps finish together
 // NS = stages per warp, NW = warps per CTA (one CTA per SM)
@@ -327,6 +327,19 @@ __device__ __forceinline__ void tail32_warp(double (&c)[10][2], double (&rrp)[4]
         }
     }
     // rr = LambdaF*mu + sum over the quad's four ratings-of-a-group
+    double bb;
+    if (TV & 256) {
+        // through shared memory: lane 4g + t puts its four partials where lane r = 8a + g finds the quad's four values of ITS
+        // row side by side, and every lane adds its own row in the order of the shuffle tree, (x0 + x1) + (x2 + x3): 4 stores,
+        // 2 loads and 4 additions instead of 16 shuffles, 12 additions, 4 stores and a load
+        double *rs = Lp;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) rs[a * 32 + lane] = rrp[a];
+        __syncwarp();
+        const double2 v01 = *reinterpret_cast<const double2 *>(rs + 4 * lane), v23 = *reinterpret_cast<const double2 *>(rs + 4 * lane + 2);
+        bb = (PROP ? 0.0 : srr0[lane]) + ((v01.x + v01.y) + (v23.x + v23.y));
+        __syncwarp();                     // (the factor is written over rs later)
+    } else {
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         rrp[a] += __shfl_xor_sync(FULL, rrp[a], 1);
@@ -337,8 +350,9 @@ __device__ __forceinline__ void tail32_warp(double (&c)[10][2], double (&rrp)[4]
         for (int a = 0; a < 4; ++a) wb[8 * a + g] = (PROP ? 0.0 : srr0[8 * a + g]) + rrp[a];
     }
     __syncwarp();
+    bb = wb[lane];
+    }
     const double z = (DBG & 8) ? 0.25 * lane : __dmul_rn(zy[lane], polar_mult(zr[lane]));
-    double bb = wb[lane];
     if (PROP) bb += rr0;
     if (PR) __syncwarp();                 // zy | zr are free: the pivots go there
     // MM = LambdaF + alpha * G (sample.cpp:297-298), in place in the accumulator layout
@@ -1016,7 +1030,7 @@ __global__ void weights_kernel(const double *__restrict__ val, double *__restric
 constexpr int tail_variant(int VER)
 {
     return VER == 15 ? (TV_DEFAULT | 1) : VER == 17 ? (TV_DEFAULT | 2) : VER == 19 ? (TV_DEFAULT | 8) : VER == 18 ? (16 | 128) : VER == 21 ? (4 | 128) : VER == 24 ? 128 :
-           VER == 27 ? (4 | 16) : TV_DEFAULT;
+           VER == 27 ? (4 | 16) : VER == 28 ? (TV_DEFAULT & ~256) : TV_DEFAULT;
 }
 
 template <int NS, int NW, int VER, int DBG = 0>
@@ -1313,6 +1327,7 @@ static cudaError_t launch_stream_range(bpmf_gpu_ctx *c, int side, uint32_t iter,
     case 21220: e = launch_cfg<2, 20, 21>(c, p, n); break;       // without the permuted ownership of the stage's indices
     case 24220: e = launch_cfg<2, 20, 24>(c, p, n); break;       // without either (7.33 ms)
     case 27220: e = launch_cfg<2, 20, 27>(c, p, n); break;       // with the ratings' weights computed per staged rating in every sweep
+    case 28220: e = launch_cfg<2, 20, 28>(c, p, n); break;       // with the right-hand side's quad sums by shuffles instead of through shared memory
     case 14220: e = launch_g4<2, 20, false>(c, p, n, o.num); break;
     case 14216: e = launch_g4<2, 16, false>(c, p, n, o.num); break;
     case 14316: e = launch_g4<3, 16, false>(c, p, n, o.num); break;
