@@ -338,12 +338,19 @@ def test_slice_loading_sharded_aggregates_and_device_finalize(gpu, K):
     full.close(); part.close()
 
 
-def test_two_ranks_on_one_gpu_whole_protocol(gpu):
+@pytest.mark.parametrize("reductions", ["auxiliary stream", "main stream"])
+def test_two_ranks_on_one_gpu_whole_protocol(gpu, reductions, monkeypatch):
     """The multi-GPU sweep as ONE C call per rank (bpmf_gpu_sample with peers set): two "ranks" on one GPU, each on its own
     stream, each holding only the ratings of its own items; item kernels store into both replicas, every rank reduces its
-    own statistics blocks into both buffers, the device-side barrier (bpmf_gpu_peer_barrier) orders it all. Whole chains,
-    predict included, must be bit-identical to one context that does everything."""
+    own statistics blocks into both buffers, the device-side barriers (peer_barrier_kernel) order it all. Whole chains,
+    predict included, must be bit-identical to one context that does everything — with the reductions of a sweep on the
+    auxiliary stream under the other side's sweep (the default with peers: statistics barrier there, latents barrier on the
+    main stream) and with everything on the main stream (BPMF_STATS_MAIN, read when a context is created)."""
     torch = pytest.importorskip("torch")
+    if reductions == "main stream":
+        monkeypatch.setenv("BPMF_STATS_MAIN", "1")
+    else:
+        monkeypatch.delenv("BPMF_STATS_MAIN", raising=False)
     K = 32
     train, test = util.synth_ratings(5000, 4000, 70000, 9)
     orc = util.make_oracle(K, train, test, burnin=1)
@@ -387,7 +394,11 @@ def test_two_ranks_on_one_gpu_whole_protocol(gpu):
 
 @pytest.mark.parametrize("cfg,what", [(3216, "16 warps"), (6220, "TMA 1-D bulk copies (UBLKCP)"), (14220, "TMA tile::gather4 (UTMALDG.2D.GATHER4)"),
                                       (14316, "gather4, 3 stages x 16 warps"), (15220, "rank-one DMMA column steps"),
-                                      (900003220, "fixed bulk / tail claims instead of guided")])
+                                      (900003220, "fixed bulk / tail claims instead of guided"),
+                                      (17220, "pivots and reciprocals through shared memory"), (19220, "rank-one DMMA for block columns 2 and 3"),
+                                      (18220, "factor's panel blocks by the separate scatter"), (21220, "stage indices by lane = row"),
+                                      (24220, "neither of the two"), (27220, "rating weights computed per staged rating"),
+                                      (28220, "right-hand side's quad sums by shuffles")])
 def test_stream_kernel_variants_are_bit_identical(gpu, cfg, what):
     """The measured alternatives of the K = 32 kernel that stay selectable in the product build: other
     gather engines, claim schedules and the tensor-core column step compute the same bits as the default configuration —
