@@ -54,7 +54,8 @@ const char *bpmf_gpu_last_error(const bpmf_gpu_ctx *ctx); /* ctx may be NULL: la
 int bpmf_gpu_num_latent(const bpmf_gpu_ctx *ctx);
 /* cudaStream_t to enqueue on (NULL = legacy default stream). */
 int bpmf_gpu_set_stream(bpmf_gpu_ctx *ctx, void *cuda_stream);
-/* Sys::sync (c++/nocomm.h:35): wait for everything enqueued so far, report deferred kernel errors. */
+/* Sys::sync (c++/nocomm.h:35): wait for everything enqueued so far (the internal auxiliary stream included), report
+ * deferred kernel errors. */
 int bpmf_gpu_sync(bpmf_gpu_ctx *ctx);
 
 /* ---- data: the Sys constructors + Sys::init (c++/sample.cpp:112-137,179-190) ------------------
@@ -131,9 +132,11 @@ int bpmf_gpu_set_iter(bpmf_gpu_ctx *ctx, int side, int iter);
  * hp.sample(num, sum (always 0), cov), every item in [from,to) drawn by the
  * fused kernel, then sum / prod / norm reduced over ALL items and cov updated on the device.
  * Multi-GPU (bpmf_gpu_set_peers + bpmf_gpu_set_stats_peers on every rank, ranges on statistics-block boundaries): the same
- * call on every rank is the whole sweep — the item kernel stores each fresh column into every replica, every rank reduces
- * the statistics blocks of its range into all ranks' buffers, bpmf_gpu_peer_barrier, fixed-order sum: bit-identical to
- * one GPU. */
+ * call on every rank is the whole sweep — the item kernel stores each fresh column into every replica and a device-side
+ * barrier follows on the context's stream; every rank reduces the statistics blocks of its range into all ranks' buffers, a
+ * second device-side barrier, the fixed-order sum and the next hyper draw run on an internal auxiliary stream under the
+ * other side's sweep (bpmf_gpu_get_stats, bpmf_gpu_sync and the next bpmf_gpu_sample of the side wait for them): bit-identical
+ * to one GPU. */
 int bpmf_gpu_sample(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_variant);
 
 /* The same call with HOST-resident latent matrices on both sides, which is literally the reference's
@@ -169,7 +172,10 @@ int bpmf_gpu_get_hyper(bpmf_gpu_ctx *ctx, int side, double *mu, double *LambdaU,
 /* Sys::sample(long idx, Sys &in) for idx in [from,to) (c++/sample.cpp:263-336, 248-258) with the
  * side's current hyper-parameters; `iter` is the value the reference's Sys::iter has inside the call. */
 int bpmf_gpu_sample_items(bpmf_gpu_ctx *ctx, int side, uint32_t iter, double alpha, int kernel_variant);
-/* sums.combine()/prods.combine()/norms.combine() + cov (c++/sample.cpp:359-362,379-384) over all items */
+/* sums.combine()/prods.combine()/norms.combine() + cov (c++/sample.cpp:359-362,379-384) over all items. With statistics
+ * peers set (K = 32) the chain is enqueued on the internal auxiliary stream behind the side's item kernel, and the context's
+ * stream only gets the barrier that orders the pushed latent columns (see bpmf_gpu_sample); BPMF_STATS_MAIN=1 in the
+ * environment at bpmf_gpu_create keeps everything on the context's stream. */
 int bpmf_gpu_reduce_stats(bpmf_gpu_ctx *ctx, int side);
 /* The two halves of _reduce_stats. Multi-GPU hosts call _partial right after _sample_items, then their cross-rank barrier,
  * then _final: with statistics peers set (below) _partial reduces only the blocks of this context's item range and stores
