@@ -1165,7 +1165,9 @@ int bpmf_gpu_sample_host(bpmf_gpu_ctx *ctx, int side, double alpha, int kernel_v
     SideDev &o = ctx->side[1 - side];
     if (!s.loaded || !o.loaded) return fail(ctx, BPMF_GPU_EINVAL, "both sides must be loaded");
     CU(cudaSetDevice(ctx->device));
-    { const int qrc = quiesce_aux(ctx); if (qrc) return qrc; }
+    // (only a multi-GPU sweep leaves reductions that READ the latent matrices on the auxiliary stream; on one GPU the stream
+    //  holds nothing but the other side's next hyper draw, which this call must not wait for: 0.12 ms per sweep)
+    if (stats_on_aux(ctx, 0) || stats_on_aux(ctx, 1)) { const int qrc = quiesce_aux(ctx); if (qrc) return qrc; }
     const size_t K = (size_t)ctx->K;
     if (s.n_stat_peers > 1) {
         // One rank of a multi-GPU run: host memory holds THIS rank's slice of each latent matrix. Its slice of the other side
