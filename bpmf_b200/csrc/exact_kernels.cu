@@ -20,6 +20,7 @@ constexpr unsigned long long ERR_HYPER_NOT_PD = 5ull << 32;
 // =================================================================================================
 struct HyperArgs {
     int K, N, nblk;
+    int sequential;     // != 0: the plain sequential gamma walk (BPMF_HYPER_SEQUENTIAL: tests of the fall-back path)
     uint32_t iter;
     const double *sum;  // K or nullptr (zeros)
     const double *cov;  // K*K
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(1024) hyper_kernel(HyperArgs a, const size_t s
             if (pos < 0) bad = true;
             a.row_start[K] = r0; a.row_cls[K] = c0;
         }
-        s_spec = bad ? 0 : 1;      // (bad: let the sequential walk find out what is wrong)
+        s_spec = (bad || a.sequential) ? 0 : 1;      // (bad: let the sequential walk find out what is wrong)
     }
     __syncthreads();
     int spec_ok = s_spec;
@@ -444,6 +445,7 @@ cudaError_t launch_hyper(bpmf_gpu_ctx *c, int side, uint32_t iter, const double 
     const HyperDev &out = ahead ? s.hp_next : s.hp;
     HyperArgs a;
     a.K = c->K; a.N = s.num; a.nblk = hs.nblk; a.iter = iter;
+    a.sequential = getenv("BPMF_HYPER_SEQUENTIAL") != nullptr;
     a.sum = d_sum; a.cov = d_cov;
     a.words = hs.words; a.acc = hs.acc; a.rank = hs.rank; a.pos_of_rank = hs.pos_of_rank;
     a.row_start = hs.row_start; a.row_cls = hs.row_cls; a.piv = hs.piv;

@@ -61,6 +61,31 @@ def test_hyper_draw(gpu, oracle_lib, K, N, it):
     ctx.close()
 
 
+@pytest.mark.parametrize("walk", ["speculative", "sequential"])
+def test_hyper_draw_gamma_walk_paths(gpu, oracle_lib, walk, monkeypatch):
+    """The K gamma draws of the Bartlett factor (c++/mvnormal.cpp:64-73): positions first and the draws in parallel when every
+    draw takes its first normal and uniform, the plain sequential walk otherwise (csrc/exact_kernels.cu, step 4). Tiny N
+    makes the shape parameters small (Marsaglia-Tsang then rejects in a few per cent of the draws), so across these cases both
+    outcomes of the speculation occur; BPMF_HYPER_SEQUENTIAL forces the fall-back for all of them."""
+    if walk == "sequential":
+        monkeypatch.setenv("BPMF_HYPER_SEQUENTIAL", "1")
+    else:
+        monkeypatch.delenv("BPMF_HYPER_SEQUENTIAL", raising=False)
+    K = 32
+    for N in (1, 2, 3, 7):
+        ctx = gpu.Context(K)
+        ctx.load_side(MOVIES, N, 8, np.zeros(N + 1, np.int64), np.zeros(0, np.int32), np.zeros(0), 0.0)
+        for it in range(6):
+            cov = util.random_spd(K, 500 + 10 * N + it, scale=0.3)
+            mu_o, LU_o, LF_o = oracle_lib.hyper(K, N, it, cov.T.copy())
+            ctx.sample_hyper(MOVIES, it, None, cov.T.copy().reshape(-1))
+            mu, LU, LF = ctx.get_hyper(MOVIES)
+            assert np.abs(LU - LU_o).max() <= 1e-11 * np.abs(LU_o).max(), (N, it)
+            assert np.abs(LF - LF_o).max() <= 1e-11 * np.abs(LF_o).max(), (N, it)
+            assert np.abs(mu - mu_o).max() <= 1e-11 * max(1.0, np.abs(mu_o).max()), (N, it)
+        ctx.close()
+
+
 def test_hyper_draw_zero_cov_first_sweep(gpu, oracle_lib):
     # sweep 0: cov == 0 -> X = I (quirk Q6)
     K, N = 32, 1682
