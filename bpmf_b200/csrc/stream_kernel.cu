@@ -6,17 +6,21 @@
 //            cp.async (LDGSTS.128, L1-bypassing, zero-fill for the ragged end), NS-1 stages ahead of the
 //            arithmetic and ACROSS item boundaries, so the HBM/L2 latency of the random 256-byte gathers is
 //            overlapped with the tensor-core work and with the factorisation / solve tail of the previous item.
-//            Consecutive items are claimed CLAIM at a time from a global counter (the last ~1 % of a sweep CLAIM_TAIL at
-//            a time): their ratings are contiguous in the CSR arrays, so the <= 16 indices and values of a stage are one
-//            coalesced load, issued a whole stage ahead.
+//            Consecutive items are claimed from a global counter by guided self-scheduling (remaining / resident warps items,
+//            at most CLAIM, single items at the very end): their ratings are contiguous in the CSR arrays, so the <= 16 indices
+//            and weights of a stage are one coalesced load, issued a whole stage ahead. The weights (v - mean) * alpha are
+//            precomputed once per alpha (weights_kernel); a gather address is one IMAD.WIDE; lane 16 h + i holds the index of
+//            the row its half-warp copies in step i.
 //   Gram     fp64 tensor cores: mma.sync.m8n8k4 (DMMA). Lane 4g+t holds f[a] = y_t[8a+g] of rating t of a group of
 //            four; f[I] is the A fragment and f[J] the B fragment of block (I,J), so ten DMMAs update the lower
 //            triangle of 8x8 blocks and every gathered value is read from shared memory exactly once. The 288-byte
 //            row stride makes those fragment loads bank-conflict free. rr += y * w is 4 DFMAs per group.
 //   tail     tail32_warp: MM = LambdaF + alpha * G stays in the DMMA accumulator layout (20 registers per lane);
-//            square-root-free blocked LDL^T (8x8 diagonal blocks with warp shuffles, trailing blocks with DMMAs), the
-//            unit-lower factor goes to shared memory divided by the pivots, the two triangular solves are shuffle + FMA
-//            chains in "lane j owns row j" form; K normals from Philox4x32-10 (rng.cuh).
+//            square-root-free blocked LDL^T (8x8 diagonal blocks with warp shuffles — the last two columns of a block peeled
+//            off the loop —, trailing blocks with DMMAs whose B fragments are also the factor's panel blocks), the
+//            unit-lower factor goes to shared memory divided by the pivots and negated, the two triangular solves are
+//            shuffle + FMA chains in "lane j owns row j" form; K normals from Philox4x32-10 (rng.cuh).
+//            What an instruction costs there, and what was tried: DESIGN.md section 5.
 //   skew     items far heavier than the rest are cut into chunks (heavy_gram32_kernel / heavy_tail32_kernel below).
 // Variants that were built and measured slower live in bench_micro/stream_experiments.cuh and bench_micro/stream_roles.cuh
 // (compiled only with BPMF_STREAM_PROBES=1; logs in profiles/).
